@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — decode tok/s of the quantized-MoE hot path at DeepSeek-V3 shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): DeepSeek-V3 671B Q4_K_M single-stream decode, the MoE-block hot path of every
+token: 58 MoE layers x [router (fp32 GEMV + grouped top-8) -> 8 routed experts (gate/up Q4_K, down Q6_K,
+H=7168, I=2048, 256 experts resident per layer) -> 1 shared expert].  671B does not fit one B200, so a step
+walks 58 layers over `--resident-layers` distinct full-size weight sets (each 7.4 GB >> L2, revisit distance
+>= 2 sets >> L2: every byte comes from HBM); attention / dense layers / lm_head are NOT in the step and the
+metric says so.  Weights are synthetic well-formed GGUF blocks, activations random (data: synthetic).
+
+One step = one token per GPU through the 58 layers.  N > 1: experts are sharded E/N per GPU
+(expert-parallel); per layer the N tokens are all-gathered, each GPU runs the (token, expert) pairs it owns
+and a reduce-scatter returns every token's combined output — value = N tokens / step time (weak scaling).
+
+Printed JSON line: see the task contract; `roofline` is for the dominant kernel (gate/up GEMV) from a live
+CUDA-event pass, `cpu_baseline` / `--impl reference` time the reference's own CPU implementation
+(oracle/_ref, the unmodified llamafile MoE) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+E, K, H, I, N_MOE_LAYERS = 256, 8, 7168, 2048, 58
+N_GROUP, TOPK_GROUP, ROUTED_SCALE = 8, 4, 2.5
+Q4_K, Q6_K, BF16, F32 = 12, 14, 30, 0
+BYTES_GATE_UP_PER_EXPERT = 2 * I * H * 144 // 256           # 16,515,072
+BYTES_DOWN_PER_EXPERT = H * I * 210 // 256                  # 12,042,240
+BYTES_PER_EXPERT = BYTES_GATE_UP_PER_EXPERT + BYTES_DOWN_PER_EXPERT   # 28,557,312
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = float(rows[0][2])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, n in enumerate(names):
+                if any(len(r) >= 9 and r[5 + i].strip().lower() == "active" for r in rows):
+                    out["reasons"].append(n)
+            out["samples"] = len(sm)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+class RefCpuMoe:
+    """The reference's own CPU MoE (oracle/_ref: unmodified moe.cpp + llamafile + ggml) on synthetic weights of
+    the real per-expert shapes.  `n_experts` experts are resident in host RAM (bounded sample of the 256)."""
+
+    def __init__(self, n_experts=32, threads=None):
+        import numpy as np
+        import torch
+
+        from ktransformers_b200.util.synth import synth_blocks
+        from oracle.bindings import Oracle, Ref
+        self.np = np
+        self.kind = "reference" if Ref.available() else "port"
+        self.threads = threads or host_threads()
+        self.n = n_experts
+        self.gate = synth_blocks(Q4_K, n_experts * I * H, "cpu", 101).numpy()
+        self.up = synth_blocks(Q4_K, n_experts * I * H, "cpu", 102).numpy()
+        self.down = synth_blocks(Q6_K, n_experts * H * I, "cpu", 103).numpy()
+        if self.kind == "reference":
+            self.ref = Ref.get(self.threads)
+            self.threads = self.ref.threads
+            self.isa = self.ref.isa()
+            self.h = self.ref.moe_create(n_experts, K, H, I, self.gate, self.up, self.down, Q4_K, Q4_K, Q6_K, BF16)
+        else:
+            self.port = Oracle()
+            self.isa = "plain C (oracle/ktoracle.c, OpenMP)"
+        rng = np.random.default_rng(0)
+        self.x = (rng.standard_normal((1, H)) / 100).astype(np.float32)
+        from oracle.bindings import f32_to_bf16_bits
+        self.xb = f32_to_bf16_bits(self.x)
+        self.ids = [np.stack([rng.permutation(n_experts)[:K]]).astype(np.uint64) for _ in range(N_MOE_LAYERS)]
+        self.w = rng.random((1, K)).astype(np.float32)
+        self.out = np.zeros((1, H), np.uint16)
+
+    def layer(self, l):
+        if self.kind == "reference":
+            self.ref.moe_forward_handle(self.h, H, BF16, self.ids[l % N_MOE_LAYERS], self.w, self.xb, self.out)
+        else:
+            self.port.moe_forward(self.n, H, I, self.gate, self.up, self.down, Q4_K, Q4_K, Q6_K, BF16,
+                                  self.ids[l % N_MOE_LAYERS].astype(self.np.int64), self.w, self.xb)
+
+    def token(self):
+        for l in range(N_MOE_LAYERS):
+            self.layer(l)
+
+    def describe(self, layers_timed):
+        return (f"{self.kind} CPU MoE ({self.isa}), {self.threads} host threads: routed experts only (the reference keeps "
+                f"router/shared experts on the GPU), {layers_timed} layer-forwards of 8-of-{self.n} resident experts at real shapes; "
+                f"tok/s = 1/(58 x mean layer time)")
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cpu = RefCpuMoe()
+    for _ in range(args.warmup):
+        cpu.token()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.token()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = 1.0 / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8xint4->int32, fp32 scales (llamafile Q8_K x Q4_K/Q6_K)", "data": "synthetic", "config": workload_config(args, 1),
+            "cpu_baseline": {"value": v, "unit": "tok/s", "cores": cpu.threads, "kind": cpu.kind, "sample": cpu.describe(args.steps * N_MOE_LAYERS)},
+            "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+METRIC = "decode tok/s DeepSeek-V3 671B INT4 (Q4_K_M) MoE-block hot path; HBM GB/s vs roofline"
+
+
+def workload_config(args, world):
+    return {"workload": ("DeepSeek-V3 671B Q4_K_M decode bs=1 per GPU, MoE-block hot path: 58 layers x [router fp32 256x7168 + 8 routed "
+                         "experts (gate/up Q4_K, down Q6_K, H=7168 I=2048, E=256 resident/layer) + 1 shared expert]; attention, dense "
+                         "layers and lm_head NOT included"),
+            "resident_layer_sets": args.resident_layers, "layers_per_step": N_MOE_LAYERS, "tokens_per_step": world,
+            "parallelism": f"ep{world}" if world > 1 else "single",
+            "l2": "inputs larger than L2: each layer set is 7.4 GB and is revisited after >= 2 other sets",
+            "note": "layer inputs are not chained (random-init weights overflow bf16 within a few layers); every layer routes and computes on the step's hidden state with its own router/expert weights"}
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--resident-layers", type=int, default=8)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ktransformers_b200 import native
+    from ktransformers_b200.util.synth import synth_blocks
+
+    assert torch.cuda.is_available(), "the B200 path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = native.lib()
+    stream = torch.cuda.current_stream()
+    S = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+
+    E_local = E // world
+    L = args.resident_layers
+    hid = BF16 if world == 1 else F32        # EP: fp32 partial sums are reduce-scattered, then rounded once
+    hid_torch = torch.bfloat16 if world == 1 else torch.float32
+
+    # ---- resident weight sets ---------------------------------------------------------------------------------
+    layers = []
+    for l in range(L):
+        seed = 1000 * l + 17 * rank
+        gate = synth_blocks(Q4_K, E_local * I * H, dev, seed + 1)
+        up = synth_blocks(Q4_K, E_local * I * H, dev, seed + 2)
+        down = synth_blocks(Q6_K, E_local * H * I, dev, seed + 3)
+        cfg = native.MoeConfig(E_local, K, H, I, 64, 10, max(8, world), 1, gate.data_ptr(), up.data_ptr(), down.data_ptr(),
+                               Q4_K, Q4_K, Q6_K, hid, rank * E_local)
+        h = C.c_void_p()
+        native.check(lib.ktb200_moe_create(C.byref(cfg), local_rank, C.byref(h)))
+        native.check(lib.ktb200_moe_load_weights(h, S()))
+        sg, su, sd = (synth_blocks(Q4_K, I * H, dev, 1000 * l + 5), synth_blocks(Q4_K, I * H, dev, 1000 * l + 6),
+                      synth_blocks(Q6_K, H * I, dev, 1000 * l + 7))
+        mh = C.c_void_p()
+        native.check(lib.ktb200_mlp_create(H, I, sg.data_ptr(), su.data_ptr(), sd.data_ptr(), Q4_K, Q4_K, Q6_K, BF16, 8, local_rank, C.byref(mh)))
+        native.check(lib.ktb200_mlp_load_weights(mh, S()))
+        g = torch.Generator(device=dev); g.manual_seed(1000 * l + 9)
+        Wr = torch.randn((E, H), device=dev, generator=g, dtype=torch.float32)
+        br = torch.randn((E,), device=dev, generator=g, dtype=torch.float32)
+        gcfg = native.GateConfig(E, H, K, N_GROUP, TOPK_GROUP, 0, 0, 1, ROUTED_SCALE, Wr.data_ptr(), br.data_ptr(), BF16)
+        layers.append(dict(moe=h, mlp=mh, gcfg=gcfg, keep=(gate, up, down, sg, su, sd, Wr, br)))
+    torch.cuda.synchronize()
+
+    # ---- static buffers ---------------------------------------------------------------------------------------
+    T = world                                                  # tokens in flight per layer (one per GPU)
+    x_own = torch.zeros((1, H), dtype=torch.bfloat16, device=dev)          # this GPU's token
+    x_all = torch.zeros((T, H), dtype=torch.bfloat16, device=dev)
+    x_all_f32 = torch.zeros((T, H), dtype=torch.float32, device=dev)
+    ids = torch.zeros((T, K), dtype=torch.int64, device=dev)
+    wts = torch.zeros((T, K), dtype=torch.float32, device=dev)
+    part = torch.zeros((T, H), dtype=hid_torch, device=dev)                # routed output (EP: fp32 partial)
+    own_f32 = torch.zeros((1, H), dtype=torch.float32, device=dev)
+    y = torch.zeros((1, H), dtype=torch.bfloat16, device=dev)              # layer output for this GPU's token
+    acc = torch.zeros((1, H), dtype=torch.float32, device=dev)             # something that depends on every layer
+    x_host = torch.zeros((1, H), dtype=torch.bfloat16).pin_memory()
+    y_host = torch.zeros((1, H), dtype=torch.float32).pin_memory()
+    ids_host = torch.zeros((1, K), dtype=torch.int64).pin_memory()
+    w_host = torch.zeros((1, K), dtype=torch.float32).pin_memory()
+    out_host = torch.zeros((1, H), dtype=torch.bfloat16).pin_memory()
+
+    def layer_device(l):
+        Lr = layers[l % L]
+        if world > 1:
+            dist.all_gather_into_tensor(x_all, x_own)
+            xin = x_all
+        else:
+            xin = x_own
+        native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, xin.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))
+        if world > 1:
+            x_all_f32.copy_(xin)
+            native.check(lib.ktb200_moe_forward(Lr["moe"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(), None, S()))
+            dist.reduce_scatter_tensor(own_f32, part)
+            y.copy_(own_f32)
+        else:
+            native.check(lib.ktb200_moe_forward(Lr["moe"], 1, K, ids.data_ptr(), wts.data_ptr(), xin.data_ptr(), y.data_ptr(), None, S()))
+        # y += shared_experts(x)   (KDeepseekV3MoE.forward, experts.py:984-1011)
+        native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y.data_ptr(), 1, None, S()))
+        acc.add_(y)
+
+    def step_device():
+        acc.zero_()
+        for l in range(N_MOE_LAYERS):
+            layer_device(l)
+
+    # warm (allocations inside the library happen here, before capture)
+    n0 = native.launch_count()
+    step_device()
+    torch.cuda.synchronize()
+    launches_per_step = native.launch_count() - n0
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_device()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_device()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                print(f"# CUDA graph capture failed ({e}); running eagerly", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_device()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rng = np.random.default_rng(1234 + rank)
+
+    def fresh_input():
+        x_host.copy_(torch.from_numpy((rng.standard_normal((1, H)) / 100).astype(np.float32)).to(torch.bfloat16))
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        fresh_input(); x_own.copy_(x_host, non_blocking=True); run_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    fresh_input(); x_own.copy_(x_host); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- e2e: host buffers, copies inside the timed region ----------------------------------------------------
+    if world == 1:
+        # the reference-facing call: per layer ids/weights come off the GPU router into pinned memory, then
+        # MOE.forward(qlen,k,ids,w,input,output) with HOST pointers == ktb200_moe_forward_host
+        def e2e_step():
+            x_own.copy_(x_host, non_blocking=True)
+            for l in range(N_MOE_LAYERS):
+                Lr = layers[l % L]
+                native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), 1, x_own.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))
+                ids_host.copy_(ids, non_blocking=True); w_host.copy_(wts, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                native.check(lib.ktb200_moe_forward_host(Lr["moe"], 1, K, ids_host.data_ptr(), w_host.data_ptr(), x_host.data_ptr(), out_host.data_ptr(), S()))
+            return out_host
+        h2d = H * 2 + N_MOE_LAYERS * (H * 2 + K * 8 + K * 4)
+        d2h = N_MOE_LAYERS * (H * 2 + K * 8 + K * 4)
+        e2e_api = "per layer: router on GPU -> D2H ids/weights -> ktb200_moe_forward_host(host ids, weights, input -> host output)"
+    else:
+        def e2e_step():
+            x_own.copy_(x_host, non_blocking=True)
+            run_step()
+            y_host.copy_(acc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = H * 2, H * 4
+        e2e_api = "pinned host token -> H2D -> 58-layer EP step -> D2H of the step's result"
+    for _ in range(3):
+        fresh_input(); e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fresh_input(); e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world / float(t_e.item())
+
+    # ---- roofline: live CUDA-event pass over the two MoE kernels, cold weights every layer --------------------
+    roof = roof_down = None
+    if rank == 0:
+        gu, dn = [], []
+        a, b = C.c_float(), C.c_float()
+        xin = x_own if world == 1 else x_all_f32
+        for rep in range(2):
+            for l in range(N_MOE_LAYERS):
+                Lr = layers[l % L]
+                native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), 1, x_own.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))
+                if world > 1:
+                    ids.remainder_(E_local).add_(rank * E_local)     # all 8 local: measures the kernel, not the sharding
+                native.check(lib.ktb200_moe_forward_timed(Lr["moe"], 1, K, ids.data_ptr(), wts.data_ptr(), xin.data_ptr(), part.data_ptr(), S(), C.byref(a), C.byref(b)))
+                if rep:
+                    gu.append(a.value); dn.append(b.value)
+        peak, how = measured_peak_gbs()
+        ms_gu, ms_dn = statistics.mean(gu), statistics.mean(dn)
+        ach = K * BYTES_GATE_UP_PER_EXPERT / (ms_gu * 1e-3) / 1e9
+        roof = {"kernel": "rows_kernel<FmtQ4K,PAIR> (gate/up GEMV + SiLU*mul)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "peak_source": how, "traffic": None, "bytes_per_launch": K * BYTES_GATE_UP_PER_EXPERT, "ms_per_launch": ms_gu}
+        achd = K * BYTES_DOWN_PER_EXPERT / (ms_dn * 1e-3) / 1e9
+        roof_down = {"kernel": "reduce_kernel<FmtQ6K8> (down GEMV + weighted sum)", "bound": "hbm", "achieved": achd, "peak": peak, "unit": "GB/s",
+                     "frac": achd / peak, "bytes_per_launch": K * BYTES_DOWN_PER_EXPERT, "ms_per_launch": ms_dn}
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's CPU MoE on this box's host cores ---------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = RefCpuMoe()
+        for l in range(20):
+            cpu.layer(l)
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < 12.0 and n < 4000:
+            cpu.layer(n); n += 1
+        t_layer = (time.perf_counter() - t0) / n
+        cpu_baseline = {"value": 1.0 / (N_MOE_LAYERS * t_layer), "unit": "tok/s", "cores": cpu.threads, "kind": cpu.kind,
+                        "sample": cpu.describe(n), "ms_per_layer": t_layer * 1e3,
+                        "gbs": K * BYTES_PER_EXPERT / t_layer / 1e9}
+
+    if rank == 0:
+        step_bytes = N_MOE_LAYERS * ((K + 1) * BYTES_PER_EXPERT + E * H * 4)
+        line = {"metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8xint4/int6->int32 dp4a, fp32 scales+accumulate, bf16 in/out", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
+                "gpu_launches": launches_per_step * args.steps, "cuda_graph": graph is not None,
+                "roofline": roof, "roofline_down": roof_down, "cpu_baseline": cpu_baseline,
+                "step_hbm": {"algorithmic_bytes_per_token_per_gpu": step_bytes, "achieved_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                             "frac_of_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / measured_peak_gbs()[0]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,219 @@
+/* ktb200 — B200-native (sm_100a) drop-in for kt-kernel's quantized-MoE decode hot path.
+ *
+ * C-ABI boundary: plain pointers and sizes only, no torch / pybind types.  Every entry point
+ * names the reference interface it replaces.  All `*_dev` pointers are CUDA device pointers on the
+ * device the handle was created for; `stream` is a cudaStream_t passed as void*.  All calls are
+ * stream-ordered, never synchronise the device (except the *_host convenience calls and where
+ * stated) and never call back into Python, so they can be captured into a CUDA graph.
+ *
+ * Ownership (same contract as the reference, kt-kernel/ext_bindings.cpp:167-177 DEF_PTR_PROPERTY,
+ * archive/ktransformers/operators/experts.py:183-218): the caller owns every tensor; the library
+ * receives raw pointers and never frees them.  Weight tensors must stay alive as long as the
+ * handle; `*_load_weights` may permute bytes of a weight tensor IN PLACE (see below), exactly like
+ * the reference's load_weights re-packs into its own layout (llamafile/moe.hpp:194-251).
+ *
+ * Errors: every function returns 0 on success or a negative KTB200_E* code; ktb200_last_error()
+ * returns a thread-local message (reference: C++ exceptions -> Python, moe-tp.hpp:203-205,
+ * ext_bindings.cpp:88-92 invalid ggml_type -> ValueError).  Expert ids < 0 or >= expert_num are
+ * silently skipped (kt-kernel/operators/common.hpp:255-258 should_skip_expert).
+ */
+#ifndef KTB200_H
+#define KTB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KTB200_OK 0
+#define KTB200_EINVAL (-1)   /* bad argument / unsupported ggml type */
+#define KTB200_ECUDA (-2)    /* CUDA runtime error */
+#define KTB200_ESTATE (-3)   /* e.g. forward before load_weights ("Not Loaded", moe-tp.hpp:203-205) */
+#define KTB200_ENOMEM (-4)
+
+/* ggml type ids, identical to the reference (third_party/llama.cpp/ggml.h:349-380). */
+enum ktb200_ggml_type {
+    KTB200_TYPE_F32 = 0, KTB200_TYPE_F16 = 1, KTB200_TYPE_Q8_0 = 8, KTB200_TYPE_Q2_K = 10,
+    KTB200_TYPE_Q3_K = 11, KTB200_TYPE_Q4_K = 12, KTB200_TYPE_Q5_K = 13, KTB200_TYPE_Q6_K = 14,
+    KTB200_TYPE_Q8_K = 15, KTB200_TYPE_IQ4_XS = 23, KTB200_TYPE_BF16 = 30
+};
+
+const char* ktb200_last_error(void);
+const char* ktb200_version(void);
+/* bytes per block / elements per block of a ggml type (0 when unsupported):
+ * ggml_type_size / ggml_blck_size, archive/ktransformers/util/custom_gguf.py:72-102 */
+long ktb200_type_size(int ggml_type);
+long ktb200_blck_size(int ggml_type);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+unsigned long long ktb200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Routed experts.  Replaces cpuinfer_ext.moe.MOEConfig / MOE
+ *   archive/csrc/ktransformers_ext/ext_bindings.cpp:683-695 (MOEConfig ctor), :554-567 (forward)
+ *   archive/csrc/ktransformers_ext/operators/llamafile/moe.h:27-48, moe.cpp:146-380
+ * and kt_kernel_ext.moe.MOEConfig / MOE (kt-kernel/ext_bindings.cpp:746-831, 447-471).
+ * Field names and meaning are the reference's; `stride`, `group_min_len` are accepted for source
+ * compatibility and ignored (they are CPU work-splitting knobs).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ktb200_moe_config {
+    int expert_num;          /* E: experts resident behind gate/up/down pointers */
+    int routed_expert_num;   /* k: experts per token (num_experts_per_tok) */
+    int hidden_size;         /* H */
+    int intermediate_size;   /* I */
+    int stride;              /* ignored */
+    int group_min_len;       /* ignored */
+    int group_max_len;       /* max tokens per forward call (scratch is sized for it) */
+    int use_silu;            /* 1: silu(g)*u (moe.cpp:134-136), 0: relu(g)*u (:138-144) */
+    const void* gate_proj;   /* DEVICE ptr, ggml blocks, row-major [E][I][H]  */
+    const void* up_proj;     /* DEVICE ptr, [E][I][H] */
+    const void* down_proj;   /* DEVICE ptr, [E][H][I] */
+    int gate_type, up_type, down_type;   /* ggml types of the three tensors */
+    int hidden_type;         /* F32 / F16 / BF16: dtype of input and output rows */
+    int expert_id_offset;    /* expert-parallel shard: this handle owns global ids
+                                [offset, offset+expert_num); others are skipped */
+} ktb200_moe_config;
+
+typedef struct ktb200_moe ktb200_moe;
+
+int ktb200_moe_create(const ktb200_moe_config* cfg, int device, ktb200_moe** out);
+void ktb200_moe_destroy(ktb200_moe* moe);
+
+/* Replaces MOE::load_weights / load_weights_task (kt-kernel/ext_bindings.cpp:447-471).
+ * Q6_K tensors are permuted IN PLACE, once, into the 16-byte-aligned "8-row SoA" layout that the
+ * sm_100a kernels stream; other types are consumed as raw ggml blocks.
+ * Byte count is unchanged.  Idempotent per handle. */
+int ktb200_moe_load_weights(ktb200_moe* moe, void* stream);
+
+/* Replaces MOE::warm_up (moe.cpp:119-132): runs one token through every expert slot. */
+int ktb200_moe_warm_up(ktb200_moe* moe, void* stream);
+
+/* Replaces MOE::forward(qlen, k, expert_ids, weights, input, output, batch_size_tensor)
+ * (moe.cpp:367-380; kt-kernel forward_task(qlen_ptr,k,ids,w,in,out), ext_bindings.cpp:235-239).
+ *   expert_ids_dev [qlen][k] int64 (kt-kernel) — the archive's uint64 has the same bits
+ *   weights_dev    [qlen][k] float (already scaled by routed_scaling_factor)
+ *   input_dev/output_dev [qlen][H] of hidden_type
+ *   bsz_tensor_dev optional device int*: when non-null the effective qlen is min(qlen, *bsz) read ON
+ *     DEVICE (the reference reads batch_size_tensor[0] on the host, moe.cpp:368) so one captured
+ *     graph serves a variable batch; rows >= *bsz are left untouched.
+ * Arithmetic: identical to the reference CPU path — activations quantised to the weight type's
+ * vec_dot_type (Q8_K / Q8_0) with the reference's rounding, integer dot products, fp32 scales,
+ * fp32 accumulation over experts in expert_ids order, output rounded like ggml from_float. */
+int ktb200_moe_forward(ktb200_moe* moe, int qlen, int k, const int64_t* expert_ids_dev,
+                       const float* weights_dev, const void* input_dev, void* output_dev,
+                       const int* bsz_tensor_dev, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable), the shape of the reference's own call where
+ * ids/weights/input/output live in host memory (experts.py:297-313): H2D copies, forward, D2H copy,
+ * then stream synchronise.  This is what bench.py's e2e number times. */
+int ktb200_moe_forward_host(ktb200_moe* moe, int qlen, int k, const int64_t* expert_ids,
+                            const float* weights, const void* input, void* output, void* stream);
+
+/* Profiling aid for bench.py's roofline leg: same as ktb200_moe_forward, but brackets the two kernels
+ * (phase 1: gate/up GEMV + activation, phase 2: down GEMV + weighted sum) with CUDA events on `stream`,
+ * synchronises, and returns their durations in milliseconds.  Not capturable. */
+int ktb200_moe_forward_timed(ktb200_moe* moe, int qlen, int k, const int64_t* expert_ids_dev,
+                             const float* weights_dev, const void* input_dev, void* output_dev, void* stream,
+                             float* ms_gate_up, float* ms_down);
+
+/* scratch the forward uses (device, fp32 [group_max_len*k][I]) — exposed for tests / fusion */
+float* ktb200_moe_intermediate(ktb200_moe* moe);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense quantised linear and gated MLP (shared experts / dense layers / projections / lm_head).
+ * Replaces cpuinfer_ext.linear.Linear / mlp.MLP (archive ext_bindings.cpp, operators/llamafile/
+ * linear.cpp:37-70, mlp.cpp:47-125) and the dequant->Marlin path of KLinearMarlin
+ * (archive/ktransformers/operators/linear.py:595-721).  Weight: DEVICE ptr, ggml blocks [out][in].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ktb200_linear ktb200_linear;
+int ktb200_linear_create(int in_size, int out_size, const void* proj_dev, int proj_type, int hidden_type,
+                         int group_max_len, int device, ktb200_linear** out);
+void ktb200_linear_destroy(ktb200_linear* lin);
+int ktb200_linear_load_weights(ktb200_linear* lin, void* stream);
+/* y[qlen][out] = x[qlen][in] * W^T ; bias_dev optional fp32 [out] added before rounding */
+int ktb200_linear_forward(ktb200_linear* lin, int qlen, const void* input_dev, void* output_dev,
+                          const float* bias_dev, const int* bsz_tensor_dev, void* stream);
+
+typedef struct ktb200_mlp ktb200_mlp;
+int ktb200_mlp_create(int hidden_size, int intermediate_size, const void* gate_dev, const void* up_dev,
+                      const void* down_dev, int gate_type, int up_type, int down_type, int hidden_type,
+                      int group_max_len, int device, ktb200_mlp** out);
+void ktb200_mlp_destroy(ktb200_mlp* mlp);
+int ktb200_mlp_load_weights(ktb200_mlp* mlp, void* stream);
+/* out = down(silu(gate x) * up x); when accumulate != 0, out += result (fp32 add before rounding):
+ * fuses KDeepseekV3MoE's `y += shared_experts(identity)` (experts.py:984-1011). */
+int ktb200_mlp_forward(ktb200_mlp* mlp, int qlen, const void* input_dev, void* output_dev, int accumulate,
+                       const int* bsz_tensor_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Activation quantisation exposed for parity tests: from_float(x, Q8_K | Q8_0)
+ * (operators/llamafile/conversion.h:27-36 -> ggml-quants.c:3593-3630, :936-1000).
+ * out_dev receives packed ggml blocks (292 B / 256 el for Q8_K, 34 B / 32 el for Q8_0).
+ * ------------------------------------------------------------------------------------------ */
+int ktb200_quantize_activations(const void* x_dev, int hidden_type, long n_rows, long n_cols, int act_type,
+                                void* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GGUF block dequantisation (load path).  Replaces KTransformersOps.dequantize_{q8_0,q2_k,q3_k,
+ * q4_k,q5_k,q6_k,iq4_xs}(data, num_bytes, blk_size, ele_per_blk, device, dtype)
+ * (kt-kernel/cuda/custom_gguf/dequant.cu:343-413, 502-595, 759-789).  src_dev is RAW ggml blocks.
+ * out_type: F32 / F16 / BF16.
+ * ------------------------------------------------------------------------------------------ */
+int ktb200_dequantize(const void* src_dev, int ggml_type, long n_elements, void* out_dev, int out_type,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Router.  Replaces MoEGate.forward (archive/ktransformers/models/modeling_deepseek_v3.py:430-481,
+ * reached through KMoEGate, operators/gate.py:91-127) and, for softmax scoring,
+ * topk_softmax (kt-kernel/cuda/moe/moe_topk_softmax_kernels.cu:405-462).
+ *   logits = x(fp32) . W^T (fp32) ; scores = sigmoid | softmax ; noaux_tc: s' = scores + bias,
+ *   group score = sum of top-2 s' in the group, keep topk_group groups, top_k experts by s',
+ *   weights = scores[idx] (normalised if norm_topk_prob) * routed_scaling_factor.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ktb200_gate_config {
+    int n_experts;             /* n_routed_experts */
+    int hidden_size;
+    int top_k;
+    int n_group;               /* 1 = no grouping */
+    int topk_group;
+    int scoring;               /* 0 sigmoid (V3), 1 softmax (V2) */
+    int topk_method;           /* 0 noaux_tc (V3), 1 greedy, 2 group_limited_greedy (V2) */
+    int norm_topk_prob;
+    float routed_scaling_factor;
+    const float* weight;       /* DEVICE fp32 [n_experts][hidden] */
+    const float* bias;         /* DEVICE fp32 [n_experts] e_score_correction_bias, or NULL */
+    int hidden_type;           /* dtype of x */
+} ktb200_gate_config;
+/* idx_dev int64 [qlen][top_k] (order: descending biased score, like torch.topk sorted=True — the
+ * reference uses sorted=False whose order is unspecified; tests compare as sets), w_dev fp32.
+ * logits_dev optional fp32 [qlen][n_experts] scratch/out (NULL -> internal). */
+int ktb200_moe_gate_forward(const ktb200_gate_config* cfg, int qlen, const void* x_dev, int64_t* idx_dev,
+                            float* w_dev, float* logits_dev, const int* bsz_tensor_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Absorbed-MLA paged decode attention.  Replaces MLAWrapper.run / BatchMLAPagedAttentionWrapper
+ * (archive/ktransformers/operators/flashinfer_wrapper.py:117-161; attention.py:419-447) and the
+ * Triton split-KV decode (triton_attention.py:358-385).
+ *   q_nope [B][Hq][512] , q_pe [B][Hq][64]  (bf16)      ; kv cache [pages][page_size][576] bf16
+ *   (512 latent ‖ 64 rope), page_table int32 [B][max_pages], kv_len int32 [B]
+ *   out [B][Hq][512] bf16 ; lse_out optional fp32 [B][Hq] (natural log)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ktb200_mla_params {
+    int batch, num_heads, page_size, max_pages_per_seq, num_kv_splits; /* splits <=0: auto */
+    float sm_scale;
+    const void* q_nope; const void* q_pe; const void* kv_cache;
+    const int* page_table; const int* kv_len;
+    void* out; float* lse_out;
+    void* workspace; size_t workspace_bytes;  /* device scratch for split partials */
+} ktb200_mla_params;
+size_t ktb200_mla_workspace_bytes(int batch, int num_heads, int max_splits);
+int ktb200_mla_decode(const ktb200_mla_params* p, void* stream);
+
+/* paged latent KV write: StaticCache.update (archive/ktransformers/models/custom_cache.py:147-200)
+ * kv_cache[page_idx[t]][page_offset[t]][0:512] = ckv[t], [512:576] = k_pe[t] */
+int ktb200_mla_kv_write(void* kv_cache, int page_size, const void* ckv, const void* k_pe, const int* page_idx,
+                        const int* page_offset, int n_tokens, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KTB200_H */

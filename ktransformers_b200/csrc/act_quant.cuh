@@ -1,0 +1,117 @@
+// Activation quantisation to the reference's vec_dot types, bit-exact with the as-built x86
+// reference (see oracle/ktoracle.c for the pinned semantics):
+//   Q8_K  quantize_row_q8_K_reference  third_party/llama.cpp/ggml-quants.c:3593-3630
+//   Q8_0  quantize_row_q8_0 (AVX path) third_party/llama.cpp/ggml-quants.c:936-1000
+#pragma once
+#include "common.cuh"
+
+namespace ktb {
+
+// One warp quantises one 256-element block held as 8 consecutive floats per lane
+// (lane l owns elements 8l .. 8l+7).  Outputs:
+//   q8  : 256 int8 written as 2 words per lane at q8_out[2*lane .. 2*lane+1]   (word = 4 int8)
+//   d   : block scale (lane 0 writes *d_out)
+//   bsums: 16 int16 sums of 16 consecutive q8 (even lanes write bsums_out[lane/2])
+//
+// Reference semantics reproduced exactly:
+//   * `max` is the signed value of the FIRST element with the largest |x| (strict > scan).
+//   * iscale = -127.f / max  (IEEE division);  d = 1 / iscale (IEEE division)
+//   * q = min(127, nearest_int(iscale * x)) where the multiply and the 1.5*2^23 magic add are ONE
+//     fused multiply-add (what gcc emits for the reference on every FMA-capable x86-64 build).
+//   * an all-zero block gives d = 0, q = 0 (bsums forced to 0; the reference leaves them stale but
+//     they are only ever multiplied by d == 0).
+__device__ __forceinline__ void warp_quantize_q8k_block(const float (&x)[8], int lane, uint32_t* q8_out,
+                                                        float* d_out, int16_t* bsums_out) {
+    // local first-max scan
+    float amax = 0.f, mx = 0.f;
+    int midx = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float ax = fabsf(x[i]);
+        if (ax > amax) { amax = ax; mx = x[i]; midx = i; }
+    }
+    int gidx = lane * 8 + midx;
+    // warp arg-max: larger |x| wins, ties -> smaller index (== first in scan order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float oa = __shfl_xor_sync(0xffffffffu, amax, o);
+        float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        int oi = __shfl_xor_sync(0xffffffffu, gidx, o);
+        if (oa > amax || (oa == amax && oi < gidx)) { amax = oa; mx = om; gidx = oi; }
+    }
+    uint32_t w0 = 0, w1 = 0;
+    int s = 0;
+    float d = 0.f;
+    if (amax != 0.f) {
+        const float iscale = __fdiv_rn(-127.f, mx);
+        int q[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float val = __fmaf_rn(iscale, x[i], 12582912.f);
+            int v = (int)(__float_as_uint(val) & 0x007fffffu) - 0x00400000;
+            q[i] = v < 127 ? v : 127;
+            s += q[i];
+        }
+        w0 = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) |
+             ((uint32_t)(q[3] & 0xff) << 24);
+        w1 = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) |
+             ((uint32_t)(q[7] & 0xff) << 24);
+        d = __fdiv_rn(1.f, iscale);
+    }
+    q8_out[2 * lane] = w0;
+    q8_out[2 * lane + 1] = w1;
+    int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);
+    if ((lane & 1) == 0) bsums_out[lane >> 1] = (int16_t)s2;
+    if (lane == 0) *d_out = d;
+}
+
+// Quantise `n` (multiple of 256) values of one row into shared (or global) staging arrays, all warps
+// of the CTA cooperating.  src is either a hidden-type row (hidden_type F32/F16/BF16) or fp32.
+//   q8    [n] int8 (as uint32 words)      dx [n/256] float        bsums [n/16] int16
+__device__ __forceinline__ void cta_quantize_q8k_row(const void* src, long src_off, int hidden_type, int n,
+                                                     uint32_t* q8, float* dx, int16_t* bsums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < n / QK_K; b += nwarps) {
+        float x[8];
+        const long base = src_off + (long)b * QK_K + lane * 8;
+        if (hidden_type == KTB200_TYPE_F32) {
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + base);
+            float4 a = p[0], c = p[1];
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+        } else {
+            const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + base);
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (hidden_type == KTB200_TYPE_BF16) {
+                    x[2 * i] = __uint_as_float(w[i] << 16);
+                    x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+                } else {
+                    x[2 * i] = fp16_bits_to_f32((uint16_t)(w[i] & 0xffff));
+                    x[2 * i + 1] = fp16_bits_to_f32((uint16_t)(w[i] >> 16));
+                }
+            }
+        }
+        warp_quantize_q8k_block(x, lane, q8 + b * (QK_K / 4), dx + b, bsums + b * 16);
+    }
+}
+
+// Q8_0: one warp handles 8 consecutive 32-element blocks? Keep it simple: each lane owns one element of
+// a 32-block, a warp quantises one block per step.  q8 [n] int8 (byte array), d [n/32] float (the
+// fp16-rounded scale, widened), matching block_q8_0 {half d; int8 qs[32]}.
+__device__ __forceinline__ void warp_quantize_q8_0_block(float x, int lane, int8_t* q_out, float* d_out,
+                                                         uint16_t* d_bits_out) {
+    float amax = fabsf(x);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float d = __fdiv_rn(amax, 127.f);
+    const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+    const __half hd = __float2half_rn(d);
+    q_out[lane] = (int8_t)__float2int_rn(__fmul_rn(x, id));  // round-to-nearest-even, like _mm256_round_ps
+    if (lane == 0) {
+        *d_out = __half2float(hd);
+        if (d_bits_out) *d_bits_out = __half_as_ushort(hd);
+    }
+}
+
+}  // namespace ktb

@@ -1,0 +1,536 @@
+// Routed experts, dense linear and gated MLP on the streaming integer GEMV kernels (gemv.cuh).
+// C-ABI entry points declared in include/ktb200.h.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gemv.cuh"
+
+namespace ktb {
+
+// ------------------------------------------------------------------------------------------
+// Q6_K "8-row SoA" re-layout, in place.  For every group of 8 consecutive rows (nb blocks each):
+//   raw : row r, block b at (r*nb + b)*210 : {ql[128] qh[64] scales[16] d[2]}
+//   soa : [ql: r][b][128] | [qh: r][b][64] | [scales: r][b][16] | [d: r][b][2]
+// Same byte count; every slice a lane loads becomes 16-byte aligned (210-byte raw blocks are only
+// 2-byte aligned, which would force 16-bit loads).  One CTA per 8-row group, staged through smem.
+__global__ void __launch_bounds__(256) repack_q6k_kernel(uint8_t* w, long n_groups, int nb) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const long gbytes = 8L * SZ_Q6_K * nb;  // multiple of 16
+    for (long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        uint8_t* base = w + g * gbytes;
+        for (long i = threadIdx.x; i < gbytes / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(base)[i];
+        __syncthreads();
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(smem);
+        uint16_t* dst = reinterpret_cast<uint16_t*>(base);
+        const long s_qh = 1024L * nb, s_sc = 1536L * nb, s_d = 1664L * nb;
+        for (long i = threadIdx.x; i < gbytes / 2; i += blockDim.x) {
+            const long off = 2 * i;
+            long r, b, x, sect;
+            if (off < s_qh) {
+                r = off / (128L * nb); b = (off % (128L * nb)) / 128; x = off % 128; sect = 0;
+            } else if (off < s_sc) {
+                const long o = off - s_qh;
+                r = o / (64L * nb); b = (o % (64L * nb)) / 64; x = o % 64; sect = 128;
+            } else if (off < s_d) {
+                const long o = off - s_sc;
+                r = o / (16L * nb); b = (o % (16L * nb)) / 16; x = o % 16; sect = 192;
+            } else {
+                const long o = off - s_d;
+                r = o / (2L * nb); b = (o % (2L * nb)) / 2; x = 0; sect = 208;
+            }
+            dst[i] = src[((r * nb + b) * SZ_Q6_K + sect + x) / 2];
+        }
+        __syncthreads();
+    }
+}
+
+static int repack_q6k(void* w, long rows_total, int ncols, int device, cudaStream_t stream) {
+    const int nb = ncols / QK_K;
+    const long n_groups = rows_total / 8;
+    const size_t smem = (size_t)8 * SZ_Q6_K * nb;
+    if (smem > 200 * 1024) {
+        set_error("Q6_K repack: row too long (%d cols)", ncols);
+        return KTB200_EINVAL;
+    }
+    KTB_CUDA_CHECK(cudaFuncSetAttribute(repack_q6k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long grid = n_groups < (long)num_sms(device) * 8 ? n_groups : (long)num_sms(device) * 8;
+    if (grid < 1) grid = 1;
+    repack_q6k_kernel<<<(unsigned)grid, 256, smem, stream>>>(reinterpret_cast<uint8_t*>(w), n_groups, nb);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+enum FmtId { FMT_Q4K, FMT_Q5K, FMT_Q6K8, FMT_GENK, FMT_NONE };
+
+static FmtId pick_fmt(int type, bool soa) {
+    if (type == KTB200_TYPE_Q4_K) return FMT_Q4K;
+    if (type == KTB200_TYPE_Q5_K) return FMT_Q5K;
+    if (type == KTB200_TYPE_Q6_K && soa) return FMT_Q6K8;
+    if (is_kquant(type)) return FMT_GENK;
+    return FMT_NONE;
+}
+static int units_per_block(FmtId f) {
+    switch (f) {
+        case FMT_Q4K: case FMT_Q5K: return 8;
+        case FMT_Q6K8: return 4;
+        default: return 16;
+    }
+}
+
+template <typename K>
+static int set_smem_attr(K kernel, size_t smem) {
+    if (smem > 48 * 1024) {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    return KTB200_OK;
+}
+
+template <class Fmt, bool PAIR>
+static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t stream) {
+    const int nblk = p.ncols / QK_K;
+    const int cpl = (nblk * Fmt::kUnitsPerBlock + 31) / 32;  // units per lane per row
+    const size_t smem = (size_t)p.ncols + (size_t)nblk * 4 + (size_t)p.ncols / 8;
+    int gx = (2 * num_sms(device) + T - 1) / T;
+    const long total = (long)p.slots * p.rows;
+    if (gx > total) gx = (int)total;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, T);
+#define KTB_ROWS(RW, NB)                                                                   \
+    do {                                                                                   \
+        int rc = set_smem_attr(rows_kernel<Fmt, PAIR, RW, NB>, smem);                      \
+        if (rc) return rc;                                                                 \
+        rows_kernel<Fmt, PAIR, RW, NB><<<grid, kGemvThreads, smem, stream>>>(p);           \
+    } while (0)
+    if (cpl >= 4) KTB_ROWS(1, 4);
+    else if (cpl >= 2) KTB_ROWS(2, 2);
+    else KTB_ROWS(4, 1);
+#undef KTB_ROWS
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+template <bool PAIR>
+static int launch_rows(FmtId f, const RowsParams& p, int T, int device, cudaStream_t stream) {
+    switch (f) {
+        case FMT_Q4K: return launch_rows_fmt<FmtQ4K, PAIR>(p, T, device, stream);
+        case FMT_Q5K: return launch_rows_fmt<FmtQ5K, PAIR>(p, T, device, stream);
+        case FMT_Q6K8: return launch_rows_fmt<FmtQ6K8, PAIR>(p, T, device, stream);
+        case FMT_GENK: return launch_rows_fmt<FmtGenK, PAIR>(p, T, device, stream);
+        default: set_error("unsupported weight type"); return KTB200_EINVAL;
+    }
+}
+
+template <class Fmt>
+static int launch_reduce_fmt(const ReduceParams& p, int T, int device, cudaStream_t stream) {
+    const int nblk = p.ncols / QK_K;
+    const int cpl = (nblk * Fmt::kUnitsPerBlock + 31) / 32;
+    int gx = (2 * num_sms(device) + T - 1) / T;
+    if (gx > p.rows) gx = p.rows;
+    if (gx < 1) gx = 1;
+    const int nrows_max = (p.rows + gx - 1) / gx + 1;
+    const size_t per_slot = (size_t)p.ncols + (size_t)nblk * 4 + (size_t)p.ncols / 8;
+    const size_t smem = per_slot * p.slots + (size_t)nrows_max * p.slots * 4;
+    if (smem > 220 * 1024) {
+        set_error("reduce kernel: k=%d x ncols=%d does not fit shared memory", p.slots, p.ncols);
+        return KTB200_EINVAL;
+    }
+    dim3 grid(gx, T);
+#define KTB_RED(RW, NB)                                                                    \
+    do {                                                                                   \
+        int rc = set_smem_attr(reduce_kernel<Fmt, RW, NB>, smem);                          \
+        if (rc) return rc;                                                                 \
+        reduce_kernel<Fmt, RW, NB><<<grid, kGemvThreads, smem, stream>>>(p);               \
+    } while (0)
+    if (cpl >= 4) KTB_RED(1, 4);
+    else if (cpl >= 2) KTB_RED(2, 2);
+    else KTB_RED(4, 1);
+#undef KTB_RED
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+static int launch_reduce(FmtId f, const ReduceParams& p, int T, int device, cudaStream_t stream) {
+    switch (f) {
+        case FMT_Q4K: return launch_reduce_fmt<FmtQ4K>(p, T, device, stream);
+        case FMT_Q5K: return launch_reduce_fmt<FmtQ5K>(p, T, device, stream);
+        case FMT_Q6K8: return launch_reduce_fmt<FmtQ6K8>(p, T, device, stream);
+        case FMT_GENK: return launch_reduce_fmt<FmtGenK>(p, T, device, stream);
+        default: set_error("unsupported weight type"); return KTB200_EINVAL;
+    }
+}
+
+static bool weight_type_ok(int t) { return is_kquant(t); }
+
+// quantize API kernel: one warp per 256-block, packed block_q8_K output (292 B)
+__global__ void __launch_bounds__(256) quantize_q8k_kernel(const void* x, int hidden_type, long n_blocks, uint8_t* out) {
+    const int lane = threadIdx.x & 31;
+    const long b = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = load_hidden(x, b * QK_K + lane * 8 + i, hidden_type);
+    uint8_t* blk = out + b * SZ_Q8_K;
+    warp_quantize_q8k_block(v, lane, reinterpret_cast<uint32_t*>(blk + 4), reinterpret_cast<float*>(blk),
+                            reinterpret_cast<int16_t*>(blk + 4 + QK_K));
+}
+__global__ void __launch_bounds__(256) quantize_q8_0_kernel(const void* x, int hidden_type, long n_blocks, uint8_t* out) {
+    const int lane = threadIdx.x & 31;
+    const long b = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    float d;
+    uint8_t* blk = out + b * SZ_Q8_0;
+    warp_quantize_q8_0_block(load_hidden(x, b * 32 + lane, hidden_type), lane, reinterpret_cast<int8_t*>(blk + 2), &d,
+                             reinterpret_cast<uint16_t*>(blk));
+}
+
+}  // namespace ktb
+
+using namespace ktb;
+
+// ------------------------------------------------------------------------------------------
+struct ktb200_moe {
+    ktb200_moe_config cfg;
+    int device;
+    bool loaded;
+    bool gu_soa, down_soa;
+    float* inter;      // [group_max_len * k][I]
+    // host-call staging
+    int64_t* ids_d;
+    float* w_d;
+    void* in_d;
+    void* out_d;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(0), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+extern "C" {
+
+int ktb200_moe_create(const ktb200_moe_config* c, int device, ktb200_moe** out) {
+    if (!c || !out) { set_error("null argument"); return KTB200_EINVAL; }
+    if (c->expert_num <= 0 || c->routed_expert_num <= 0 || c->hidden_size <= 0 || c->intermediate_size <= 0 ||
+        c->group_max_len <= 0) { set_error("MOEConfig: non-positive dimension"); return KTB200_EINVAL; }
+    if (!weight_type_ok(c->gate_type) || !weight_type_ok(c->up_type) || !weight_type_ok(c->down_type)) {
+        set_error("MOEConfig: unsupported ggml weight type (gate %d up %d down %d)", c->gate_type, c->up_type, c->down_type);
+        return KTB200_EINVAL;
+    }
+    if (!is_hidden_type(c->hidden_type)) { set_error("MOEConfig: hidden_type %d must be F32/F16/BF16", c->hidden_type); return KTB200_EINVAL; }
+    if (c->hidden_size % QK_K || c->intermediate_size % QK_K) {
+        set_error("MOEConfig: hidden_size %d and intermediate_size %d must be multiples of 256 for K-quant tensors",
+                  c->hidden_size, c->intermediate_size);
+        return KTB200_EINVAL;
+    }
+    if (!c->gate_proj || !c->up_proj || !c->down_proj) { set_error("MOEConfig: null weight pointer"); return KTB200_EINVAL; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return KTB200_ECUDA; }
+    ktb200_moe* m = new (std::nothrow) ktb200_moe();
+    if (!m) return KTB200_ENOMEM;
+    m->cfg = *c;
+    m->device = device;
+    m->loaded = false;
+    m->gu_soa = m->down_soa = false;
+    m->inter = nullptr; m->ids_d = nullptr; m->w_d = nullptr; m->in_d = nullptr; m->out_d = nullptr;
+    const size_t slots = (size_t)c->group_max_len * c->routed_expert_num;
+    const size_t hid = (size_t)c->group_max_len * c->hidden_size * type_size(c->hidden_type);
+    cudaError_t e = cudaMalloc(&m->inter, slots * c->intermediate_size * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->ids_d, slots * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&m->w_d, slots * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->in_d, hid);
+    if (e == cudaSuccess) e = cudaMalloc(&m->out_d, hid);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+        ktb200_moe_destroy(m);
+        return KTB200_ENOMEM;
+    }
+    *out = m;
+    return KTB200_OK;
+}
+
+void ktb200_moe_destroy(ktb200_moe* m) {
+    if (!m) return;
+    DeviceGuard g(m->device);
+    cudaFree(m->inter); cudaFree(m->ids_d); cudaFree(m->w_d); cudaFree(m->in_d); cudaFree(m->out_d);
+    delete m;
+}
+
+int ktb200_moe_load_weights(ktb200_moe* m, void* stream) {
+    if (!m) { set_error("null handle"); return KTB200_EINVAL; }
+    if (m->loaded) return KTB200_OK;
+    DeviceGuard g(m->device);
+    const ktb200_moe_config& c = m->cfg;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c.gate_type == KTB200_TYPE_Q6_K && c.up_type == KTB200_TYPE_Q6_K && c.intermediate_size % 8 == 0) {
+        int rc = repack_q6k(const_cast<void*>(c.gate_proj), (long)c.expert_num * c.intermediate_size, c.hidden_size, m->device, s);
+        if (rc) return rc;
+        rc = repack_q6k(const_cast<void*>(c.up_proj), (long)c.expert_num * c.intermediate_size, c.hidden_size, m->device, s);
+        if (rc) return rc;
+        m->gu_soa = true;
+    }
+    if (c.down_type == KTB200_TYPE_Q6_K && c.hidden_size % 8 == 0) {
+        int rc = repack_q6k(const_cast<void*>(c.down_proj), (long)c.expert_num * c.hidden_size, c.intermediate_size, m->device, s);
+        if (rc) return rc;
+        m->down_soa = true;
+    }
+    m->loaded = true;
+    return KTB200_OK;
+}
+
+float* ktb200_moe_intermediate(ktb200_moe* m) { return m ? m->inter : nullptr; }
+
+static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
+                            void* output, const int* bsz, cudaStream_t s, cudaEvent_t mid) {
+    if (!m) { set_error("null handle"); return KTB200_EINVAL; }
+    if (!m->loaded) { set_error("Not Loaded"); return KTB200_ESTATE; }
+    if (qlen <= 0) return KTB200_OK;
+    const ktb200_moe_config& c = m->cfg;
+    if (k <= 0 || k > c.routed_expert_num) { set_error("forward: k=%d outside (0, routed_expert_num=%d]", k, c.routed_expert_num); return KTB200_EINVAL; }
+    if (qlen > c.group_max_len) { set_error("forward: qlen=%d exceeds group_max_len=%d", qlen, c.group_max_len); return KTB200_EINVAL; }
+    if (!ids || !weights || !input || !output) { set_error("forward: null pointer"); return KTB200_EINVAL; }
+    DeviceGuard g(m->device);
+
+    FmtId fg = pick_fmt(c.gate_type, m->gu_soa), fu = pick_fmt(c.up_type, m->gu_soa);
+    if (fg != fu) fg = fu = FMT_GENK;  // mixed gate/up types: the generic path reads the type per matrix
+    RowsParams rp{};
+    rp.w0 = c.gate_proj; rp.w1 = c.up_proj; rp.type0 = c.gate_type; rp.type1 = c.up_type;
+    rp.n_experts = c.expert_num; rp.rows = c.intermediate_size; rp.ncols = c.hidden_size; rp.slots = k;
+    rp.ids = ids; rp.id_offset = c.expert_id_offset; rp.x = input; rp.hidden_type = c.hidden_type;
+    rp.use_silu = c.use_silu; rp.out_f32 = m->inter; rp.out_hidden = nullptr; rp.bias = nullptr; rp.bsz = bsz;
+    int rc = launch_rows<true>(fg, rp, qlen, m->device, s);
+    if (rc) return rc;
+    if (mid) KTB_CUDA_CHECK(cudaEventRecord(mid, s));
+
+    ReduceParams dp{};
+    dp.w = c.down_proj; dp.type = c.down_type; dp.n_experts = c.expert_num; dp.rows = c.hidden_size;
+    dp.ncols = c.intermediate_size; dp.slots = k; dp.ids = ids; dp.id_offset = c.expert_id_offset;
+    dp.weights = weights; dp.a = m->inter; dp.out = output; dp.hidden_type = c.hidden_type; dp.accumulate = 0; dp.bsz = bsz;
+    return launch_reduce(pick_fmt(c.down_type, m->down_soa), dp, qlen, m->device, s);
+}
+
+int ktb200_moe_forward(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
+                       void* output, const int* bsz, void* stream) {
+    return moe_forward_impl(m, qlen, k, ids, weights, input, output, bsz, (cudaStream_t)stream, nullptr);
+}
+
+int ktb200_moe_forward_timed(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
+                             void* output, void* stream, float* ms_gate_up, float* ms_down) {
+    if (!m) { set_error("null handle"); return KTB200_EINVAL; }
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1, e2;
+    KTB_CUDA_CHECK(cudaEventCreate(&e0));
+    KTB_CUDA_CHECK(cudaEventCreate(&e1));
+    KTB_CUDA_CHECK(cudaEventCreate(&e2));
+    KTB_CUDA_CHECK(cudaEventRecord(e0, s));
+    int rc = moe_forward_impl(m, qlen, k, ids, weights, input, output, nullptr, s, e1);
+    if (rc == KTB200_OK) {
+        cudaEventRecord(e2, s);
+        cudaError_t e = cudaEventSynchronize(e2);
+        if (e != cudaSuccess) { set_error("timed forward: %s", cudaGetErrorString(e)); rc = KTB200_ECUDA; }
+        else {
+            if (ms_gate_up) cudaEventElapsedTime(ms_gate_up, e0, e1);
+            if (ms_down) cudaEventElapsedTime(ms_down, e1, e2);
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return rc;
+}
+
+int ktb200_moe_warm_up(ktb200_moe* m, void* stream) {
+    if (!m) { set_error("null handle"); return KTB200_EINVAL; }
+    if (!m->loaded) { set_error("Not Loaded"); return KTB200_ESTATE; }
+    DeviceGuard g(m->device);
+    const ktb200_moe_config& c = m->cfg;
+    cudaStream_t s = (cudaStream_t)stream;
+    // zero input, weight 0, every expert once (moe.cpp:119-132)
+    KTB_CUDA_CHECK(cudaMemsetAsync(m->in_d, 0, (size_t)c.hidden_size * type_size(c.hidden_type), s));
+    KTB_CUDA_CHECK(cudaMemsetAsync(m->w_d, 0, sizeof(float), s));
+    for (int e = 0; e < c.expert_num; e++) {
+        const int64_t id = e + c.expert_id_offset;
+        KTB_CUDA_CHECK(cudaMemcpyAsync(m->ids_d, &id, sizeof(id), cudaMemcpyHostToDevice, s));
+        KTB_CUDA_CHECK(cudaStreamSynchronize(s));
+        int rc = ktb200_moe_forward(m, 1, 1, m->ids_d, m->w_d, m->in_d, m->out_d, nullptr, stream);
+        if (rc) return rc;
+    }
+    KTB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return KTB200_OK;
+}
+
+int ktb200_moe_forward_host(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
+                            void* output, void* stream) {
+    if (!m) { set_error("null handle"); return KTB200_EINVAL; }
+    if (qlen <= 0) return KTB200_OK;
+    const ktb200_moe_config& c = m->cfg;
+    if (qlen > c.group_max_len || k <= 0 || k > c.routed_expert_num) { set_error("forward_host: qlen/k out of range"); return KTB200_EINVAL; }
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t hid = (size_t)qlen * c.hidden_size * type_size(c.hidden_type);
+    KTB_CUDA_CHECK(cudaMemcpyAsync(m->ids_d, ids, (size_t)qlen * k * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    KTB_CUDA_CHECK(cudaMemcpyAsync(m->w_d, weights, (size_t)qlen * k * sizeof(float), cudaMemcpyHostToDevice, s));
+    KTB_CUDA_CHECK(cudaMemcpyAsync(m->in_d, input, hid, cudaMemcpyHostToDevice, s));
+    int rc = ktb200_moe_forward(m, qlen, k, m->ids_d, m->w_d, m->in_d, m->out_d, nullptr, stream);
+    if (rc) return rc;
+    KTB_CUDA_CHECK(cudaMemcpyAsync(output, m->out_d, hid, cudaMemcpyDeviceToHost, s));
+    KTB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return KTB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ linear
+struct ktb200_linear {
+    int in_size, out_size, proj_type, hidden_type, group_max_len, device;
+    const void* proj;
+    bool loaded, soa;
+};
+
+int ktb200_linear_create(int in_size, int out_size, const void* proj, int proj_type, int hidden_type, int group_max_len,
+                         int device, ktb200_linear** out) {
+    if (!out || !proj) { set_error("null argument"); return KTB200_EINVAL; }
+    if (!weight_type_ok(proj_type)) { set_error("LinearConfig: unsupported ggml type %d", proj_type); return KTB200_EINVAL; }
+    if (!is_hidden_type(hidden_type)) { set_error("LinearConfig: bad hidden_type %d", hidden_type); return KTB200_EINVAL; }
+    if (in_size <= 0 || out_size <= 0 || in_size % QK_K) { set_error("LinearConfig: input_size %d must be a positive multiple of 256", in_size); return KTB200_EINVAL; }
+    ktb200_linear* l = new (std::nothrow) ktb200_linear();
+    if (!l) return KTB200_ENOMEM;
+    l->in_size = in_size; l->out_size = out_size; l->proj = proj; l->proj_type = proj_type; l->hidden_type = hidden_type;
+    l->group_max_len = group_max_len; l->device = device; l->loaded = false; l->soa = false;
+    *out = l;
+    return KTB200_OK;
+}
+void ktb200_linear_destroy(ktb200_linear* l) { delete l; }
+
+int ktb200_linear_load_weights(ktb200_linear* l, void* stream) {
+    if (!l) { set_error("null handle"); return KTB200_EINVAL; }
+    if (l->loaded) return KTB200_OK;
+    DeviceGuard g(l->device);
+    if (l->proj_type == KTB200_TYPE_Q6_K && l->out_size % 8 == 0 && (size_t)8 * SZ_Q6_K * (l->in_size / QK_K) <= 200 * 1024) {
+        int rc = repack_q6k(const_cast<void*>(l->proj), l->out_size, l->in_size, l->device, (cudaStream_t)stream);
+        if (rc) return rc;
+        l->soa = true;
+    }
+    l->loaded = true;
+    return KTB200_OK;
+}
+
+int ktb200_linear_forward(ktb200_linear* l, int qlen, const void* input, void* output, const float* bias, const int* bsz,
+                          void* stream) {
+    if (!l) { set_error("null handle"); return KTB200_EINVAL; }
+    if (!l->loaded) { set_error("Not Loaded"); return KTB200_ESTATE; }
+    if (qlen <= 0) return KTB200_OK;
+    if (!input || !output) { set_error("forward: null pointer"); return KTB200_EINVAL; }
+    DeviceGuard g(l->device);
+    RowsParams rp{};
+    rp.w0 = l->proj; rp.w1 = nullptr; rp.type0 = rp.type1 = l->proj_type; rp.n_experts = 1; rp.rows = l->out_size;
+    rp.ncols = l->in_size; rp.slots = 1; rp.ids = nullptr; rp.id_offset = 0; rp.x = input; rp.hidden_type = l->hidden_type;
+    rp.use_silu = 0; rp.out_f32 = nullptr; rp.out_hidden = output; rp.bias = bias; rp.bsz = bsz;
+    return launch_rows<false>(pick_fmt(l->proj_type, l->soa), rp, qlen, l->device, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------ mlp
+struct ktb200_mlp {
+    int H, I, gate_type, up_type, down_type, hidden_type, group_max_len, device;
+    const void *gate, *up, *down;
+    bool loaded, gu_soa, down_soa;
+    float* inter;
+};
+
+int ktb200_mlp_create(int H, int I, const void* gate, const void* up, const void* down, int gate_type, int up_type,
+                      int down_type, int hidden_type, int group_max_len, int device, ktb200_mlp** out) {
+    if (!out || !gate || !up || !down) { set_error("null argument"); return KTB200_EINVAL; }
+    if (!weight_type_ok(gate_type) || !weight_type_ok(up_type) || !weight_type_ok(down_type)) { set_error("MLPConfig: unsupported ggml type"); return KTB200_EINVAL; }
+    if (!is_hidden_type(hidden_type)) { set_error("MLPConfig: bad hidden_type"); return KTB200_EINVAL; }
+    if (H <= 0 || I <= 0 || H % QK_K || I % QK_K || group_max_len <= 0) { set_error("MLPConfig: sizes must be positive multiples of 256"); return KTB200_EINVAL; }
+    DeviceGuard g(device);
+    ktb200_mlp* m = new (std::nothrow) ktb200_mlp();
+    if (!m) return KTB200_ENOMEM;
+    m->H = H; m->I = I; m->gate = gate; m->up = up; m->down = down; m->gate_type = gate_type; m->up_type = up_type;
+    m->down_type = down_type; m->hidden_type = hidden_type; m->group_max_len = group_max_len; m->device = device;
+    m->loaded = m->gu_soa = m->down_soa = false; m->inter = nullptr;
+    if (cudaMalloc(&m->inter, (size_t)group_max_len * I * sizeof(float)) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        delete m;
+        return KTB200_ENOMEM;
+    }
+    *out = m;
+    return KTB200_OK;
+}
+void ktb200_mlp_destroy(ktb200_mlp* m) {
+    if (!m) return;
+    DeviceGuard g(m->device);
+    cudaFree(m->inter);
+    delete m;
+}
+int ktb200_mlp_load_weights(ktb200_mlp* m, void* stream) {
+    if (!m) { set_error("null handle"); return KTB200_EINVAL; }
+    if (m->loaded) return KTB200_OK;
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m->gate_type == KTB200_TYPE_Q6_K && m->up_type == KTB200_TYPE_Q6_K && m->I % 8 == 0) {
+        int rc = repack_q6k(const_cast<void*>(m->gate), m->I, m->H, m->device, s);
+        if (rc) return rc;
+        rc = repack_q6k(const_cast<void*>(m->up), m->I, m->H, m->device, s);
+        if (rc) return rc;
+        m->gu_soa = true;
+    }
+    if (m->down_type == KTB200_TYPE_Q6_K && m->H % 8 == 0 && (size_t)8 * SZ_Q6_K * (m->I / QK_K) <= 200 * 1024) {
+        int rc = repack_q6k(const_cast<void*>(m->down), m->H, m->I, m->device, s);
+        if (rc) return rc;
+        m->down_soa = true;
+    }
+    m->loaded = true;
+    return KTB200_OK;
+}
+int ktb200_mlp_forward(ktb200_mlp* m, int qlen, const void* input, void* output, int accumulate, const int* bsz, void* stream) {
+    if (!m) { set_error("null handle"); return KTB200_EINVAL; }
+    if (!m->loaded) { set_error("Not Loaded"); return KTB200_ESTATE; }
+    if (qlen <= 0) return KTB200_OK;
+    if (qlen > m->group_max_len) { set_error("forward: qlen=%d exceeds group_max_len=%d", qlen, m->group_max_len); return KTB200_EINVAL; }
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    FmtId fg = pick_fmt(m->gate_type, m->gu_soa), fu = pick_fmt(m->up_type, m->gu_soa);
+    if (fg != fu) fg = fu = FMT_GENK;
+    RowsParams rp{};
+    rp.w0 = m->gate; rp.w1 = m->up; rp.type0 = m->gate_type; rp.type1 = m->up_type; rp.n_experts = 1; rp.rows = m->I;
+    rp.ncols = m->H; rp.slots = 1; rp.ids = nullptr; rp.x = input; rp.hidden_type = m->hidden_type; rp.use_silu = 1;
+    rp.out_f32 = m->inter; rp.bsz = bsz;
+    int rc = launch_rows<true>(fg, rp, qlen, m->device, s);
+    if (rc) return rc;
+    ReduceParams dp{};
+    dp.w = m->down; dp.type = m->down_type; dp.n_experts = 1; dp.rows = m->H; dp.ncols = m->I; dp.slots = 1; dp.ids = nullptr;
+    dp.weights = nullptr; dp.a = m->inter; dp.out = output; dp.hidden_type = m->hidden_type; dp.accumulate = accumulate; dp.bsz = bsz;
+    return launch_reduce(pick_fmt(m->down_type, m->down_soa), dp, qlen, m->device, s);
+}
+
+// ------------------------------------------------------------------------------------------ quantize API
+int ktb200_quantize_activations(const void* x, int hidden_type, long n_rows, long n_cols, int act_type, void* out, void* stream) {
+    if (!x || !out) { set_error("null pointer"); return KTB200_EINVAL; }
+    if (!is_hidden_type(hidden_type)) { set_error("bad hidden_type %d", hidden_type); return KTB200_EINVAL; }
+    const long n = n_rows * n_cols;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (act_type == KTB200_TYPE_Q8_K) {
+        if (n_cols % QK_K) { set_error("Q8_K needs n_cols %% 256 == 0"); return KTB200_EINVAL; }
+        const long nb = n / QK_K;
+        if (nb == 0) return KTB200_OK;
+        quantize_q8k_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(x, hidden_type, nb, reinterpret_cast<uint8_t*>(out));
+    } else if (act_type == KTB200_TYPE_Q8_0) {
+        if (n_cols % 32) { set_error("Q8_0 needs n_cols %% 32 == 0"); return KTB200_EINVAL; }
+        const long nb = n / 32;
+        if (nb == 0) return KTB200_OK;
+        quantize_q8_0_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(x, hidden_type, nb, reinterpret_cast<uint8_t*>(out));
+    } else {
+        set_error("activation type %d is not a vec_dot type", act_type);
+        return KTB200_EINVAL;
+    }
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""Helpers for the GPU parity tests: drive the C-ABI (include/ktb200.h) with torch-owned device memory."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ktransformers_b200 import native
+
+NP_HID = {0: np.float32, 1: np.float16, 30: np.uint16}
+TORCH_HID = {0: torch.float32, 1: torch.float16, 30: torch.bfloat16}
+
+
+def dev(a, dtype=None):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint16:
+        a = a.view(np.int16)
+    t = torch.from_numpy(a)
+    if dtype is not None:
+        t = t.view(dtype)
+    return t.cuda()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Moe:
+    """ktb200_moe handle owning device copies of raw ggml blocks (uploaded from numpy or given as cuda tensors)."""
+
+    def __init__(self, E, k, H, I, gate, up, down, gt, ut, dt, hidden_type, max_tokens=64, use_silu=1, offset=0):
+        self.lib = native.lib()
+        self.E, self.k, self.H, self.I, self.hidden_type = E, k, H, I, hidden_type
+        self.gate = gate if isinstance(gate, torch.Tensor) else dev(gate)
+        self.up = up if isinstance(up, torch.Tensor) else dev(up)
+        self.down = down if isinstance(down, torch.Tensor) else dev(down)
+        cfg = native.MoeConfig(E, k, H, I, 64, 10, max_tokens, use_silu, self.gate.data_ptr(), self.up.data_ptr(),
+                               self.down.data_ptr(), gt, ut, dt, hidden_type, offset)
+        self.h = C.c_void_p()
+        native.check(self.lib.ktb200_moe_create(C.byref(cfg), torch.cuda.current_device(), C.byref(self.h)))
+        native.check(self.lib.ktb200_moe_load_weights(self.h, stream()))
+
+    def forward(self, ids, w, x, bsz=None, out=None):
+        """numpy in, numpy out (x / out in the numpy carrier of hidden_type: bf16 as uint16 bits)."""
+        qlen, k = ids.shape
+        ids_d, w_d = dev(ids.astype(np.int64)), dev(w.astype(np.float32))
+        x_d = dev(x, TORCH_HID[self.hidden_type] if self.hidden_type == 30 else None)
+        out_d = torch.zeros((qlen, self.H), dtype=TORCH_HID[self.hidden_type], device="cuda") if out is None else out
+        bsz_d = torch.tensor([bsz], dtype=torch.int32, device="cuda") if bsz is not None else None
+        native.check(self.lib.ktb200_moe_forward(self.h, qlen, k, ids_d.data_ptr(), w_d.data_ptr(), x_d.data_ptr(),
+                                                 out_d.data_ptr(), bsz_d.data_ptr() if bsz_d is not None else None, stream()))
+        torch.cuda.synchronize()
+        o = out_d.cpu()
+        return o.view(torch.int16).numpy().view(np.uint16) if self.hidden_type == 30 else o.numpy()
+
+    def forward_host(self, ids, w, x):
+        qlen, k = ids.shape
+        out = np.zeros((qlen, self.H), NP_HID[self.hidden_type])
+        ids, w, x = np.ascontiguousarray(ids, np.int64), np.ascontiguousarray(w, np.float32), np.ascontiguousarray(x)
+        native.check(self.lib.ktb200_moe_forward_host(self.h, qlen, k, ids.ctypes.data, w.ctypes.data, x.ctypes.data,
+                                                      out.ctypes.data, stream()))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.ktb200_moe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def linear_forward(in_size, out_size, proj, proj_type, hidden_type, x, bias=None):
+    lib = native.lib()
+    p = proj if isinstance(proj, torch.Tensor) else dev(proj)
+    h = C.c_void_p()
+    native.check(lib.ktb200_linear_create(in_size, out_size, p.data_ptr(), proj_type, hidden_type, 64, torch.cuda.current_device(), C.byref(h)))
+    native.check(lib.ktb200_linear_load_weights(h, stream()))
+    x_d = dev(x, TORCH_HID[hidden_type] if hidden_type == 30 else None)
+    out = torch.zeros((x.shape[0], out_size), dtype=TORCH_HID[hidden_type], device="cuda")
+    b = dev(bias.astype(np.float32)) if bias is not None else None
+    native.check(lib.ktb200_linear_forward(h, x.shape[0], x_d.data_ptr(), out.data_ptr(), b.data_ptr() if b is not None else None, None, stream()))
+    torch.cuda.synchronize()
+    lib.ktb200_linear_destroy(h)
+    o = out.cpu()
+    return o.view(torch.int16).numpy().view(np.uint16) if hidden_type == 30 else o.numpy()
+
+
+def mlp_forward(H, I, g, u, d, gt, ut, dt, hidden_type, x, accumulate_into=None):
+    lib = native.lib()
+    gd, ud, dd = (t if isinstance(t, torch.Tensor) else dev(t) for t in (g, u, d))
+    h = C.c_void_p()
+    native.check(lib.ktb200_mlp_create(H, I, gd.data_ptr(), ud.data_ptr(), dd.data_ptr(), gt, ut, dt, hidden_type, 64, torch.cuda.current_device(), C.byref(h)))
+    native.check(lib.ktb200_mlp_load_weights(h, stream()))
+    x_d = dev(x, TORCH_HID[hidden_type] if hidden_type == 30 else None)
+    if accumulate_into is not None:
+        out = dev(accumulate_into, TORCH_HID[hidden_type] if hidden_type == 30 else None).clone()
+    else:
+        out = torch.zeros((x.shape[0], H), dtype=TORCH_HID[hidden_type], device="cuda")
+    native.check(lib.ktb200_mlp_forward(h, x.shape[0], x_d.data_ptr(), out.data_ptr(), int(accumulate_into is not None), None, stream()))
+    torch.cuda.synchronize()
+    lib.ktb200_mlp_destroy(h)
+    o = out.cpu()
+    return o.view(torch.int16).numpy().view(np.uint16) if hidden_type == 30 else o.numpy()
+
+
+def quantize(x, hidden_type, act_type):
+    lib = native.lib()
+    rows, cols = x.shape
+    x_d = dev(x, TORCH_HID[hidden_type] if hidden_type == 30 else None)
+    per = {15: (256, 292), 8: (32, 34)}[act_type]
+    out = torch.zeros(rows * cols // per[0] * per[1], dtype=torch.uint8, device="cuda")
+    native.check(lib.ktb200_quantize_activations(x_d.data_ptr(), hidden_type, rows, cols, act_type, out.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy().reshape(rows, -1)
+
+
+def dequantize(raw, ggml_type, n, out_type=0):
+    lib = native.lib()
+    r = raw if isinstance(raw, torch.Tensor) else dev(raw)
+    out = torch.zeros(n, dtype=TORCH_HID[out_type], device="cuda")
+    native.check(lib.ktb200_dequantize(r.data_ptr(), ggml_type, n, out.data_ptr(), out_type, stream()))
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def gate_forward(x, W, bias, top_k, n_group, topk_group, scoring=0, topk_method=0, norm=1, scale=2.5, hidden_type=0, want_logits=False):
+    lib = native.lib()
+    T, H = x.shape
+    E = W.shape[0]
+    Wd, bd = dev(W.astype(np.float32)), (dev(bias.astype(np.float32)) if bias is not None else None)
+    x_d = dev(x, TORCH_HID[hidden_type] if hidden_type == 30 else None)
+    idx = torch.zeros((T, top_k), dtype=torch.int64, device="cuda")
+    w = torch.zeros((T, top_k), dtype=torch.float32, device="cuda")
+    logits = torch.zeros((T, E), dtype=torch.float32, device="cuda") if want_logits else None
+    cfg = native.GateConfig(E, H, top_k, n_group, topk_group, scoring, topk_method, norm, scale, Wd.data_ptr(),
+                            bd.data_ptr() if bd is not None else None, hidden_type)
+    native.check(lib.ktb200_moe_gate_forward(C.byref(cfg), T, x_d.data_ptr(), idx.data_ptr(), w.data_ptr(),
+                                             logits.data_ptr() if logits is not None else None, None, stream()))
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), w.cpu().numpy(), (logits.cpu().numpy() if logits is not None else None)
