@@ -91,10 +91,18 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- reference arm
 def host_threads() -> int:
+    """logical CPUs this process may use: affinity mask capped by the cgroup CPU quota."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except Exception:
-        return max(1, os.cpu_count() or 1)
+        n = max(1, os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 class RefCpuMoe:
@@ -129,6 +137,32 @@ class RefCpuMoe:
         self.ids = [np.stack([rng.permutation(n_experts)[:K]]).astype(np.uint64) for _ in range(N_MOE_LAYERS)]
         self.w = rng.random((1, K)).astype(np.float32)
         self.out = np.zeros((1, H), np.uint16)
+        self.tuned = None
+        if self.kind == "reference" and threads is None:
+            self.tune_threads()
+
+    def tune_threads(self):
+        """The reference sizes CPUInfer to the physical core count (bench_moe.py:30-32); its work-stealing pool spins,
+        so oversubscribing SMT siblings or a cgroup quota is catastrophic.  Give it its best shot: try a ladder of
+        thread counts and keep the fastest."""
+        cap = host_threads()
+        ladder = sorted({n for n in (4, 8, 16, 24, 32, 48, 64, 96, 128, cap // 2, cap) if 1 <= n <= cap})
+        best = None
+        self.tuned = {}
+        for n in ladder:
+            self.threads = self.ref.init(n)
+            for l in range(2):
+                self.layer(l)
+            t0 = time.perf_counter()
+            for l in range(5):
+                self.layer(l)
+            dt = (time.perf_counter() - t0) / 5
+            self.tuned[n] = round(dt * 1e3, 3)
+            if best is None or dt < best[1]:
+                best = (n, dt)
+            if dt > 4 * best[1]:
+                break
+        self.threads = self.ref.init(best[0])
 
     def layer(self, l):
         if self.kind == "reference":
@@ -142,7 +176,8 @@ class RefCpuMoe:
             self.layer(l)
 
     def describe(self, layers_timed):
-        return (f"{self.kind} CPU MoE ({self.isa}), {self.threads} host threads: routed experts only (the reference keeps "
+        tuned = f" (thread ladder ms/layer: {self.tuned})" if self.tuned else ""
+        return (f"{self.kind} CPU MoE ({self.isa}), {self.threads} host threads{tuned}: routed experts only (the reference keeps "
                 f"router/shared experts on the GPU), {layers_timed} layer-forwards of 8-of-{self.n} resident experts at real shapes; "
                 f"tok/s = 1/(58 x mean layer time)")
 

@@ -65,34 +65,62 @@ __device__ __forceinline__ void warp_quantize_q8k_block(const float (&x)[8], int
     if (lane == 0) *d_out = d;
 }
 
-// Quantise `n` (multiple of 256) values of one row into shared (or global) staging arrays, all warps
-// of the CTA cooperating.  src is either a hidden-type row (hidden_type F32/F16/BF16) or fp32.
-//   q8    [n] int8 (as uint32 words)      dx [n/256] float        bsums [n/16] int16
-__device__ __forceinline__ void cta_quantize_q8k_row(const void* src, long src_off, int hidden_type, int n,
-                                                     uint32_t* q8, float* dx, int16_t* bsums) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int b = warp; b < n / QK_K; b += nwarps) {
-        float x[8];
-        const long base = src_off + (long)b * QK_K + lane * 8;
-        if (hidden_type == KTB200_TYPE_F32) {
-            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + base);
-            float4 a = p[0], c = p[1];
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
-        } else {
-            const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + base);
-            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+// Load the 8 values lane `lane` owns of block `b` of a row (hidden-type or fp32 source).
+__device__ __forceinline__ void load_block8(const void* src, long base, int hidden_type, float (&x)[8]) {
+    if (hidden_type == KTB200_TYPE_F32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + base);
+        const float4 a = p[0], c = p[1];
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+    } else {
+        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + base);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (hidden_type == KTB200_TYPE_BF16) {
-                    x[2 * i] = __uint_as_float(w[i] << 16);
-                    x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-                } else {
-                    x[2 * i] = fp16_bits_to_f32((uint16_t)(w[i] & 0xffff));
-                    x[2 * i + 1] = fp16_bits_to_f32((uint16_t)(w[i] >> 16));
-                }
+        for (int i = 0; i < 4; i++) {
+            if (hidden_type == KTB200_TYPE_BF16) {
+                x[2 * i] = __uint_as_float(w[i] << 16);
+                x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            } else {
+                x[2 * i] = fp16_bits_to_f32((uint16_t)(w[i] & 0xffff));
+                x[2 * i + 1] = fp16_bits_to_f32((uint16_t)(w[i] >> 16));
             }
         }
-        warp_quantize_q8k_block(x, lane, q8 + b * (QK_K / 4), dx + b, bsums + b * 16);
+    }
+}
+
+// Quantise `nrows` rows of `n` (multiple of 256) values into shared staging arrays, all warps of the CTA
+// cooperating.  Row r lives at src + row_off[r-th] ... expressed as src_off + r*src_stride (elements);
+// rows with skip[r] are left untouched.  Blocks are dealt round-robin to warps and processed G at a
+// time: the G global loads are issued back to back BEFORE any of the shuffle reductions, so the prologue
+// pays the memory latency once per group instead of once per block.
+//   q8 [nrows][n] int8    dx [nrows][n/256] float    bsums [nrows][n/16] int16
+template <int G>
+__device__ __forceinline__ void cta_quantize_q8k_rows(const void* src, long src_off, long src_stride, int hidden_type,
+                                                      int nrows, int n, unsigned skip_mask, uint8_t* q8, float* dx,
+                                                      int16_t* bsums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int bpr = n / QK_K, total = nrows * bpr;
+    for (int g0 = warp; g0 < total; g0 += nwarps * G) {
+        float x[G][8];
+        bool live[G];
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            const int gb = g0 + i * nwarps;
+            live[i] = gb < total;
+            if (live[i]) {
+                const int r = gb / bpr, b = gb - r * bpr;
+                live[i] = !((skip_mask >> r) & 1u);
+                if (live[i]) load_block8(src, src_off + (long)r * src_stride + (long)b * QK_K + lane * 8, hidden_type, x[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            if (live[i]) {   // warp-uniform
+                const int gb = g0 + i * nwarps;
+                const int r = gb / bpr, b = gb - r * bpr;
+                warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(q8 + (size_t)r * n) + b * (QK_K / 4),
+                                        dx + r * bpr + b, bsums + r * (n / 16) + b * 16);
+            }
+        }
     }
 }
 

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) rows_kernel(const RowsParams 
     uint8_t* q8 = smem;                                                        // ncols
     float* dx = reinterpret_cast<float*>(smem + p.ncols);                      // nblk
     int16_t* bsums = reinterpret_cast<int16_t*>(smem + p.ncols + nblk * 4);    // ncols/16
-    cta_quantize_q8k_row(p.x, (long)t * p.ncols, p.hidden_type, p.ncols, reinterpret_cast<uint32_t*>(q8), dx, bsums);
+    cta_quantize_q8k_rows<4>(p.x, (long)t * p.ncols, 0, p.hidden_type, 1, p.ncols, 0u, q8, dx, bsums);
     __syncthreads();
     const ActQ8K act{q8, dx, bsums};
 
@@ -160,11 +160,14 @@ __global__ void __launch_bounds__(kGemvThreads, 2) reduce_kernel(const ReducePar
     const int r0 = (int)((long)p.rows * blockIdx.x / gridDim.x), r1 = (int)((long)p.rows * (blockIdx.x + 1) / gridDim.x);
     const int nrows = r1 - r0;
 
-    for (int j = 0; j < k; j++) {
-        long e = p.ids ? (long)p.ids[(long)t * k + j] - p.id_offset : 0;
-        if (e < 0 || e >= p.n_experts) continue;  // skipped experts contribute nothing (common.hpp:255-258)
-        cta_quantize_q8k_row(p.a, ((long)t * k + j) * p.ncols, KTB200_TYPE_F32, p.ncols,
-                             reinterpret_cast<uint32_t*>(q8 + (size_t)j * p.ncols), dx + j * nblk, bsums + j * (p.ncols / 16));
+    {
+        // skipped experts contribute nothing (common.hpp:255-258): do not even read their activations
+        unsigned skip = 0;
+        for (int j = 0; j < k; j++) {
+            long e = p.ids ? (long)p.ids[(long)t * k + j] - p.id_offset : 0;
+            if (e < 0 || e >= p.n_experts) skip |= 1u << j;
+        }
+        cta_quantize_q8k_rows<8>(p.a, (long)t * k * p.ncols, p.ncols, KTB200_TYPE_F32, k, p.ncols, skip, q8, dx, bsums);
     }
     __syncthreads();
 
