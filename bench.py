@@ -308,14 +308,13 @@ def main():
             native.check(lib.ktb200_moe_forward(Lr["moe"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(), None, S()))
             dist.reduce_scatter_tensor(own_f32, part)
             y.copy_(own_f32)
+            # y += shared_experts(x)   (KDeepseekV3MoE.forward, experts.py:984-1011)
+            native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y.data_ptr(), 1, None, S()))
         else:
-            native.check(lib.ktb200_moe_forward(Lr["moe"], 1, K, ids.data_ptr(), wts.data_ptr(), xin.data_ptr(), y.data_ptr(), None, S()))
-        # y += shared_experts(x)   (KDeepseekV3MoE.forward, experts.py:984-1011)
-        native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y.data_ptr(), 1, None, S()))
-        acc.add_(y)
+            # routed + shared expert in the same two launches (y = experts(x); y += shared_experts(x))
+            native.check(lib.ktb200_moe_forward_shared(Lr["moe"], Lr["mlp"], 1, K, ids.data_ptr(), wts.data_ptr(), xin.data_ptr(), y.data_ptr(), None, S()))
 
     def step_device():
-        acc.zero_()
         for l in range(N_MOE_LAYERS):
             layer_device(l)
 
@@ -399,7 +398,7 @@ def main():
         def e2e_step():
             x_own.copy_(x_host, non_blocking=True)
             run_step()
-            y_host.copy_(acc, non_blocking=True)
+            y_host.copy_(y, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         h2d, d2h = H * 2, H * 4
         e2e_api = "pinned host token -> H2D -> 58-layer EP step -> D2H of the step's result"

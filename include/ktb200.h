@@ -144,6 +144,15 @@ int ktb200_mlp_load_weights(ktb200_mlp* mlp, void* stream);
 int ktb200_mlp_forward(ktb200_mlp* mlp, int qlen, const void* input_dev, void* output_dev, int accumulate,
                        const int* bsz_tensor_dev, void* stream);
 
+/* KDeepseekV3MoE.forward in one call (experts.py:974-1012): out = round(experts(x)) + round(shared_experts(x)),
+ * each term rounded to hidden_type first, exactly like `y = experts(...); y += shared_experts(identity)` on
+ * hidden-type tensors.  When the shared expert has the routed experts' shapes and ggml types (DeepSeek-V3) it is
+ * computed as an extra slot INSIDE the two routed launches; otherwise it runs as a separate ktb200_mlp_forward.
+ * `shared` may be NULL (== ktb200_moe_forward). */
+int ktb200_moe_forward_shared(ktb200_moe* moe, ktb200_mlp* shared, int qlen, int k, const int64_t* expert_ids_dev,
+                              const float* weights_dev, const void* input_dev, void* output_dev,
+                              const int* bsz_tensor_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Activation quantisation exposed for parity tests: from_float(x, Q8_K | Q8_0)
  * (operators/llamafile/conversion.h:27-36 -> ggml-quants.c:3593-3630, :936-1000).

@@ -4,95 +4,50 @@
 // which the reference runs as ~10 ATen kernels per layer (fp32 F.linear, sigmoid, two topk, scatter,
 // masked_fill, gather, sum, div, mul).
 //
-//   gate_logits_kernel : fp32 GEMV  logits[t][e] = x_t(fp32) . W[e]   (HBM-bound: E*H*4 bytes)
-//                        grid (E, S): each CTA streams 1/S of one expert row with float4 loads and
-//                        reuses it for every token; S partial sums per logit are added in fixed order
-//                        by the selection kernel (deterministic, no atomics).
-//   gate_select_kernel : one warp per token: scoring, bias, group top-2 / max, group top-k, expert
-//                        top-k by iterative warp arg-max (ties -> lowest index), gather, normalise, scale.
+// ONE kernel:
+//   phase 1  fp32 GEMV  logits[t][e] = x_t(fp32) . W[e]   (HBM-bound: E*H*4 bytes).  A CTA of 4 warps owns 4
+//            expert rows x one column split; each warp streams its row slice with 16-byte loads (8 in flight
+//            per lane) against the token slice staged in shared memory, and writes one partial sum per
+//            (token, expert, split).  Partials are added in fixed split order: deterministic, no float atomics.
+//   phase 2  the LAST CTA to finish (atomic ticket, self-resetting, graph-replay safe) selects: one warp per
+//            token — scoring, bias, group top-2 / max, group top-k, expert top-k by iterative arg-max with
+//            REDUX max/min (ties -> lowest index), gather, normalise, scale.
 #include "common.cuh"
 
 namespace ktb {
 
-constexpr int kGateThreads = 128;
+constexpr int kGateWarps = 4;
+constexpr int kGateThreads = kGateWarps * 32;
 constexpr int kGateTokTile = 8;
 
-__global__ void __launch_bounds__(kGateThreads) gate_logits_kernel(const float* __restrict__ W, const void* __restrict__ x,
-                                                                   int hidden_type, int E, int H, int T,
-                                                                   float* __restrict__ partial /*[T][E][S]*/,
-                                                                   const int* bsz) {
-    const int e = blockIdx.x, s = blockIdx.y, S = gridDim.y;
-    int Teff = T;
-    if (bsz) Teff = min(T, *bsz);
-    // column range of this split, in float4 units
-    const int n4 = H / 4;
-    const int c0 = (int)((long)n4 * s / S), c1 = (int)((long)n4 * (s + 1) / S);
-    const float4* wrow = reinterpret_cast<const float4*>(W + (long)e * H);
-    __shared__ float red[kGateTokTile][kGateThreads / 32];
-    for (int t0 = 0; t0 < Teff; t0 += kGateTokTile) {
-        float acc[kGateTokTile];
-#pragma unroll
-        for (int i = 0; i < kGateTokTile; i++) acc[i] = 0.f;
-        for (int c = c0 + threadIdx.x; c < c1; c += kGateThreads) {
-            const float4 w = __ldg(wrow + c);
-#pragma unroll
-            for (int i = 0; i < kGateTokTile; i++) {
-                const int t = t0 + i;
-                if (t < Teff) {
-                    const long base = (long)t * H + 4L * c;
-                    const float x0 = load_hidden(x, base, hidden_type), x1 = load_hidden(x, base + 1, hidden_type);
-                    const float x2 = load_hidden(x, base + 2, hidden_type), x3 = load_hidden(x, base + 3, hidden_type);
-                    acc[i] = fmaf(w.x, x0, acc[i]);
-                    acc[i] = fmaf(w.y, x1, acc[i]);
-                    acc[i] = fmaf(w.z, x2, acc[i]);
-                    acc[i] = fmaf(w.w, x3, acc[i]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kGateTokTile; i++) {
-            const float v = warp_sum(acc[i]);
-            if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < kGateTokTile) {
-            const int t = t0 + threadIdx.x;
-            if (t < Teff) {
-                float v = 0.f;
-                for (int w = 0; w < kGateThreads / 32; w++) v += red[threadIdx.x][w];
-                partial[((long)t * E + e) * S + s] = v;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-struct GateSelParams {
-    int E, top_k, n_group, topk_group, scoring, topk_method, norm_topk_prob, S;
+struct GateParams {
+    const float* W;
+    const void* x;
+    int hidden_type, E, H, T, S;
+    int top_k, n_group, topk_group, scoring, topk_method, norm_topk_prob;
     float routed_scaling_factor;
     const float* bias;
-    const float* partial;
-    float* logits_out;  // optional [T][E]
+    float* partial;      // [T][E][S]
+    float* logits_out;   // optional [T][E]
     int64_t* idx;
     float* w;
     const int* bsz;
+    unsigned* ticket;
 };
 
-// one warp per token; dynamic smem: scores[E] | choice[E]
-__global__ void __launch_bounds__(32) gate_select_kernel(const GateSelParams p) {
-    extern __shared__ float sm[];
-    const int t = blockIdx.x, lane = threadIdx.x;
-    if (p.bsz && t >= *p.bsz) return;
-    float* scores = sm;
-    float* choice = sm + p.E;
-    const int E = p.E;
+// order-preserving float -> uint32 key
+__device__ __forceinline__ unsigned fkey(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
-    // logits (+ optional export), scoring
+__device__ void gate_select_token(const GateParams& p, int t, int lane, float* scores, float* choice) {
+    const int E = p.E;
     float lmax = -INFINITY;
     for (int e = lane; e < E; e += 32) {
         float v = 0.f;
         const float* pp = p.partial + ((long)t * E + e) * p.S;
-        for (int s = 0; s < p.S; s++) v += pp[s];
+        for (int s = 0; s < p.S; s++) v += __ldcg(pp + s);   // written by other SMs in this launch: read at L2
         if (p.logits_out) p.logits_out[(long)t * E + e] = v;
         scores[e] = v;
         lmax = fmaxf(lmax, v);
@@ -110,20 +65,37 @@ __global__ void __launch_bounds__(32) gate_select_kernel(const GateSelParams p) 
     for (int e = lane; e < E; e += 32) choice[e] = scores[e] + ((p.topk_method == 0 && p.bias) ? p.bias[e] : 0.f);
     __syncwarp();
 
-    // group selection
+    // group selection (noaux_tc: sum of the group's top-2 biased scores; group_limited_greedy: group max)
     if (p.n_group > 1 && p.topk_method != 1) {
         const int gs = E / p.n_group;
         float gscore = -INFINITY;
-        if (lane < p.n_group) {
+        const bool pow2 = (p.n_group & (p.n_group - 1)) == 0;
+        if (pow2) {
+            // 32/n_group lanes cooperate on one group, then merge their (max1, max2) pairs
+            const int lpg = 32 / p.n_group, g = lane / lpg, sub = lane % lpg;
+            float m1 = -INFINITY, m2 = -INFINITY;
+            for (int i = sub; i < gs; i += lpg) {
+                const float v = choice[g * gs + i];
+                if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) { m2 = v; }
+            }
+            for (int o = 1; o < lpg; o <<= 1) {
+                const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+                const float hi = fmaxf(m1, o1), lo = fminf(m1, o1);
+                m2 = fmaxf(lo, fmaxf(m2, o2));
+                m1 = hi;
+            }
+            const float gsc = (p.topk_method == 0) ? (m1 + m2) : m1;
+            gscore = __shfl_sync(0xffffffffu, gsc, (lane % p.n_group) * lpg);   // lane g (< n_group) gets group g's score
+            if (lane >= p.n_group) gscore = -INFINITY;
+        } else if (lane < p.n_group) {
             float m1 = -INFINITY, m2 = -INFINITY;
             for (int i = 0; i < gs; i++) {
                 const float v = choice[lane * gs + i];
                 if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) { m2 = v; }
             }
-            gscore = (p.topk_method == 0) ? (m1 + m2) : m1;  // noaux_tc: top-2 sum ; group_limited_greedy: max
+            gscore = (p.topk_method == 0) ? (m1 + m2) : m1;
         }
-        // rank among groups (higher first, ties -> lower index)
-        int rank = 0;
+        int rank = 0;  // higher first, ties -> lower index
         for (int g = 0; g < p.n_group; g++) {
             const float og = __shfl_sync(0xffffffffu, gscore, g);
             if (lane < p.n_group && (og > gscore || (og == gscore && g < lane))) rank++;
@@ -136,33 +108,28 @@ __global__ void __launch_bounds__(32) gate_select_kernel(const GateSelParams p) 
     }
 
     // top-k by iterative arg-max; ties -> lowest expert index
-    float wsum = 0.f;
-    float myw = 0.f;  // lane i keeps weight i (top_k <= 32)
+    float wsum = 0.f, myw = 0.f;
     long myidx = 0;
     for (int i = 0; i < p.top_k; i++) {
-        float bv = -INFINITY;
+        unsigned bk = 0;
         int bi = 0x7fffffff;
         for (int e = lane; e < E; e += 32) {
-            const float v = choice[e];
-            if (v > bv || (v == bv && e < bi)) { bv = v; bi = e; }
+            const unsigned kk = fkey(choice[e]);
+            if (kk > bk) { bk = kk; bi = e; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (bi == 0x7fffffff) bi = 0;  // all -inf/NaN: degenerate
-        // V3 gathers from the un-biased scores; V2 takes the (masked) score itself
-        const float wv = (p.topk_method == 2) ? bv : scores[bi];
-        if (lane == i) { myw = wv; myidx = bi; }
+        const unsigned mx = __reduce_max_sync(0xffffffffu, bk);
+        int win = __reduce_min_sync(0xffffffffu, (bk == mx) ? bi : 0x7fffffff);
+        if (win == 0x7fffffff) win = 0;  // degenerate (all NaN)
+        // V3 gathers from the un-biased scores; V2 group_limited takes the (masked) score itself
+        const float wv = (p.topk_method == 2) ? choice[win] : scores[win];
+        if (lane == i) { myw = wv; myidx = win; }
         wsum += wv;
-        if (lane == 0) choice[bi] = -INFINITY;
+        __syncwarp();
+        if (lane == 0) choice[win] = -INFINITY;
         __syncwarp();
     }
-    // normalisation / scaling: V3 (modeling_deepseek_v3.py:474-479): norm (if top_k>1 && norm) THEN always scale;
-    // V2 (modeling_deepseek.py:455-459): norm XOR scale.
-    // torch sums topk_weight in index order 0..k-1; wsum above is that same order.
+    // V3 (modeling_deepseek_v3.py:474-479): normalise (if top_k>1 && norm_topk_prob) THEN always scale;
+    // V2 (modeling_deepseek.py:455-459): normalise XOR scale.
     if (lane < p.top_k) {
         float w = myw;
         const bool do_norm = p.top_k > 1 && p.norm_topk_prob;
@@ -173,9 +140,86 @@ __global__ void __launch_bounds__(32) gate_select_kernel(const GateSelParams p) 
     }
 }
 
-// per-device scratch for the S partial sums
+__global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);   // [tok tile][slice cols]  (phase 1) / scores+choice (phase 2)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int Teff = p.T;
+    if (p.bsz) Teff = min(p.T, *p.bsz);
+    const int s = blockIdx.y, S = p.S;
+    const int n4 = p.H / 4;
+    const int c0 = (int)((long)n4 * s / S), c1 = (int)((long)n4 * (s + 1) / S);   // float4 column range of this split
+    const int nc4 = c1 - c0;
+    const int e = blockIdx.x * kGateWarps + warp;
+    const float4* wrow = reinterpret_cast<const float4*>(p.W + (long)(e < p.E ? e : 0) * p.H) + c0;
+
+    for (int t0 = 0; t0 < Teff; t0 += kGateTokTile) {
+        const int nt = min(kGateTokTile, Teff - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt * nc4 * 4; i += kGateThreads) {
+            const int tt = i / (nc4 * 4), c = i - tt * (nc4 * 4);
+            xs[i] = load_hidden(p.x, (long)(t0 + tt) * p.H + 4L * c0 + c, p.hidden_type);
+        }
+        __syncthreads();
+        if (e < p.E) {
+            float acc[kGateTokTile];
+#pragma unroll
+            for (int i = 0; i < kGateTokTile; i++) acc[i] = 0.f;
+            for (int cb = lane; cb < nc4; cb += 32 * 8) {
+                float4 w[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int c = cb + 32 * u;
+                    if (c < nc4) w[u] = __ldg(wrow + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int c = cb + 32 * u;
+                    if (c < nc4) {
+#pragma unroll
+                        for (int i = 0; i < kGateTokTile; i++) {
+                            if (i < nt) {
+                                const float4 xv = reinterpret_cast<const float4*>(xs + (size_t)i * nc4 * 4)[c];
+                                acc[i] = fmaf(w[u].x, xv.x, acc[i]);
+                                acc[i] = fmaf(w[u].y, xv.y, acc[i]);
+                                acc[i] = fmaf(w[u].z, xv.z, acc[i]);
+                                acc[i] = fmaf(w[u].w, xv.w, acc[i]);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kGateTokTile; i++) {
+                if (i < nt) {
+                    const float v = warp_sum(acc[i]);
+                    if (lane == 0) p.partial[((long)(t0 + i) * p.E + e) * S + s] = v;
+                }
+            }
+        }
+    }
+
+    // ---- last CTA selects -------------------------------------------------------------------------------
+    __shared__ unsigned s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned prev = atomicAdd(p.ticket, 1u);
+        s_last = (prev == total - 1);
+        if (s_last) *p.ticket = 0;   // self-reset: the next launch (or graph replay) starts from zero
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float* sc = xs;                 // per warp: scores[E] | choice[E]
+    for (int t = warp; t < Teff; t += kGateWarps) gate_select_token(p, t, lane, sc + (size_t)warp * 2 * p.E, sc + (size_t)warp * 2 * p.E + p.E);
+}
+
+// per-device scratch: partial sums + ticket
 static float* g_partial[64] = {nullptr};
 static size_t g_partial_cap[64] = {0};
+static unsigned* g_ticket[64] = {nullptr};
 
 }  // namespace ktb
 
@@ -196,27 +240,35 @@ extern "C" int ktb200_moe_gate_forward(const ktb200_gate_config* c, int qlen, co
     if (!is_hidden_type(c->hidden_type) || !c->weight) { set_error("gate: bad hidden_type or null weight"); return KTB200_EINVAL; }
     int dev = 0;
     KTB_CUDA_CHECK(cudaGetDevice(&dev));
+    const int d = dev & 63;
     cudaStream_t s = (cudaStream_t)stream;
-    // splits so that E*S ~ 4 CTAs per SM
-    int S = (4 * num_sms(dev) + c->n_experts - 1) / c->n_experts;
+    const int row_ctas = (c->n_experts + kGateWarps - 1) / kGateWarps;
+    int S = (2 * num_sms(dev) + row_ctas - 1) / row_ctas;   // ~2 CTAs per SM
     if (S < 1) S = 1;
-    if (S > 16) S = 16;
-    while (S > 1 && c->hidden_size / 4 / S < 32) S--;
+    if (S > 8) S = 8;
+    while (S > 1 && c->hidden_size / 4 / S < 64) S--;
     const size_t need = (size_t)qlen * c->n_experts * S * sizeof(float);
-    if (need > g_partial_cap[dev & 63]) {
-        // grow-only scratch; allocation is NOT capturable, so warm up once with the largest qlen before graph capture
-        if (g_partial[dev & 63]) cudaFree(g_partial[dev & 63]);
-        size_t cap = need < (1u << 20) ? (1u << 20) : need;
-        KTB_CUDA_CHECK(cudaMalloc(&g_partial[dev & 63], cap));
-        g_partial_cap[dev & 63] = cap;
+    if (need > g_partial_cap[d] || !g_ticket[d]) {
+        // grow-only scratch; allocation is NOT capturable: call once with the largest qlen before graph capture
+        if (g_partial[d]) cudaFree(g_partial[d]);
+        const size_t cap = need < (1u << 20) ? (1u << 20) : need;
+        KTB_CUDA_CHECK(cudaMalloc(&g_partial[d], cap));
+        g_partial_cap[d] = cap;
+        if (!g_ticket[d]) {
+            KTB_CUDA_CHECK(cudaMalloc(&g_ticket[d], sizeof(unsigned)));
+            KTB_CUDA_CHECK(cudaMemset(g_ticket[d], 0, sizeof(unsigned)));
+        }
     }
-    float* partial = g_partial[dev & 63];
-    gate_logits_kernel<<<dim3(c->n_experts, S), kGateThreads, 0, s>>>(c->weight, x, c->hidden_type, c->n_experts,
-                                                                     c->hidden_size, qlen, partial, bsz);
-    KTB_LAUNCH_CHECK();
-    GateSelParams p{c->n_experts, c->top_k, c->n_group, c->topk_group, c->scoring, c->topk_method, c->norm_topk_prob, S,
-                    c->routed_scaling_factor, c->bias, partial, logits, idx, w, bsz};
-    gate_select_kernel<<<qlen, 32, 2 * c->n_experts * sizeof(float), s>>>(p);
+    GateParams p{c->weight, x, c->hidden_type, c->n_experts, c->hidden_size, qlen, S, c->top_k, c->n_group, c->topk_group,
+                 c->scoring, c->topk_method, c->norm_topk_prob, c->routed_scaling_factor, c->bias, g_partial[d], logits,
+                 idx, w, bsz, g_ticket[d]};
+    const int nc4_max = c->hidden_size / 4 / S + 1;
+    const int nt = qlen < kGateTokTile ? qlen : kGateTokTile;
+    size_t smem = (size_t)nt * nc4_max * 16;
+    const size_t smem_sel = (size_t)kGateWarps * 2 * c->n_experts * sizeof(float);
+    if (smem_sel > smem) smem = smem_sel;
+    if (smem > 48 * 1024) KTB_CUDA_CHECK(cudaFuncSetAttribute(gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gate_kernel<<<dim3(row_ctas, S), kGateThreads, smem, s>>>(p);
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
 }

@@ -1,6 +1,7 @@
 // Routed experts, dense linear and gated MLP on the streaming integer GEMV kernels (gemv.cuh).
 // C-ABI entry points declared in include/ktb200.h.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -73,14 +74,6 @@ static FmtId pick_fmt(int type, bool soa) {
     if (is_kquant(type)) return FMT_GENK;
     return FMT_NONE;
 }
-static int units_per_block(FmtId f) {
-    switch (f) {
-        case FMT_Q4K: case FMT_Q5K: return 8;
-        case FMT_Q6K8: return 4;
-        default: return 16;
-    }
-}
-
 template <typename K>
 static int set_smem_attr(K kernel, size_t smem) {
     if (smem > 48 * 1024) {
@@ -89,25 +82,38 @@ static int set_smem_attr(K kernel, size_t smem) {
     return KTB200_OK;
 }
 
+// Tuning knobs (read once): KTB200_MINB = CTAs per SM the main kernels are compiled/launched for (2 or 3),
+// KTB200_NB = steps per load batch for the long-row gate/up kernel (2 or 4).
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static int cfg_minb() { static int v = env_int("KTB200_MINB", 2); return v == 3 ? 3 : 2; }
+static int cfg_nb() { static int v = env_int("KTB200_NB", 4); return v == 2 ? 2 : 4; }
+
 template <class Fmt, bool PAIR>
-static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t stream) {
+static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t stream, bool tunable) {
     const int nblk = p.ncols / QK_K;
-    const int cpl = (nblk * Fmt::kUnitsPerBlock + 31) / 32;  // units per lane per row
+    const int nsteps = (nblk + Fmt::kBlocksPerStep - 1) / Fmt::kBlocksPerStep;
     const size_t smem = (size_t)p.ncols + (size_t)nblk * 4 + (size_t)p.ncols / 8;
-    int gx = (2 * num_sms(device) + T - 1) / T;
-    const long total = (long)p.slots * p.rows;
+    const int minb = tunable ? cfg_minb() : 2;
+    int gx = (minb * num_sms(device) + T - 1) / T;
+    const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
     if (gx > total) gx = (int)total;
     if (gx < 1) gx = 1;
     dim3 grid(gx, T);
-#define KTB_ROWS(RW, NB)                                                                   \
+#define KTB_ROWS(RW, NB, MINB)                                                             \
     do {                                                                                   \
-        int rc = set_smem_attr(rows_kernel<Fmt, PAIR, RW, NB>, smem);                      \
+        int rc = set_smem_attr(rows_kernel<Fmt, PAIR, RW, NB, MINB>, smem);                \
         if (rc) return rc;                                                                 \
-        rows_kernel<Fmt, PAIR, RW, NB><<<grid, kGemvThreads, smem, stream>>>(p);           \
+        rows_kernel<Fmt, PAIR, RW, NB, MINB><<<grid, kGemvThreads, smem, stream>>>(p);     \
     } while (0)
-    if (cpl >= 4) KTB_ROWS(1, 4);
-    else if (cpl >= 2) KTB_ROWS(2, 2);
-    else KTB_ROWS(4, 1);
+    if (nsteps >= 4) {
+        if (tunable && minb == 3) KTB_ROWS(1, 2, 3);
+        else if (tunable && cfg_nb() == 2) KTB_ROWS(1, 2, 2);
+        else KTB_ROWS(1, 4, 2);
+    } else if (nsteps >= 2) KTB_ROWS(2, 2, 2);
+    else KTB_ROWS(4, 1, 2);
 #undef KTB_ROWS
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
@@ -116,38 +122,42 @@ static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t 
 template <bool PAIR>
 static int launch_rows(FmtId f, const RowsParams& p, int T, int device, cudaStream_t stream) {
     switch (f) {
-        case FMT_Q4K: return launch_rows_fmt<FmtQ4K, PAIR>(p, T, device, stream);
-        case FMT_Q5K: return launch_rows_fmt<FmtQ5K, PAIR>(p, T, device, stream);
-        case FMT_Q6K8: return launch_rows_fmt<FmtQ6K8, PAIR>(p, T, device, stream);
-        case FMT_GENK: return launch_rows_fmt<FmtGenK, PAIR>(p, T, device, stream);
+        case FMT_Q4K: return launch_rows_fmt<FmtQ4K, PAIR>(p, T, device, stream, true);
+        case FMT_Q5K: return launch_rows_fmt<FmtQ5K, PAIR>(p, T, device, stream, false);
+        case FMT_Q6K8: return launch_rows_fmt<FmtQ6K8, PAIR>(p, T, device, stream, false);
+        case FMT_GENK: return launch_rows_fmt<FmtGenK, PAIR>(p, T, device, stream, false);
         default: set_error("unsupported weight type"); return KTB200_EINVAL;
     }
 }
 
-template <class Fmt>
-static int launch_reduce_fmt(const ReduceParams& p, int T, int device, cudaStream_t stream) {
+template <class Fmt, int NBMAX>
+static int launch_reduce_fmt(const ReduceParams& p, int T, int device, cudaStream_t stream, bool tunable) {
     const int nblk = p.ncols / QK_K;
-    const int cpl = (nblk * Fmt::kUnitsPerBlock + 31) / 32;
-    int gx = (2 * num_sms(device) + T - 1) / T;
+    const int nsteps = (nblk + Fmt::kBlocksPerStep - 1) / Fmt::kBlocksPerStep;
+    const int minb = tunable ? cfg_minb() : 2;
+    const int ns = p.slots + (p.xw ? 1 : 0);
+    int gx = (minb * num_sms(device) + T - 1) / T;
     if (gx > p.rows) gx = p.rows;
     if (gx < 1) gx = 1;
     const int nrows_max = (p.rows + gx - 1) / gx + 1;
     const size_t per_slot = (size_t)p.ncols + (size_t)nblk * 4 + (size_t)p.ncols / 8;
-    const size_t smem = per_slot * p.slots + (size_t)nrows_max * p.slots * 4;
+    const size_t smem = per_slot * ns + (size_t)nrows_max * ns * 4;
     if (smem > 220 * 1024) {
-        set_error("reduce kernel: k=%d x ncols=%d does not fit shared memory", p.slots, p.ncols);
+        set_error("reduce kernel: k=%d x ncols=%d does not fit shared memory", ns, p.ncols);
         return KTB200_EINVAL;
     }
     dim3 grid(gx, T);
-#define KTB_RED(RW, NB)                                                                    \
+#define KTB_RED(NB, MINB)                                                                  \
     do {                                                                                   \
-        int rc = set_smem_attr(reduce_kernel<Fmt, RW, NB>, smem);                          \
+        int rc = set_smem_attr(reduce_kernel<Fmt, NB, MINB>, smem);                        \
         if (rc) return rc;                                                                 \
-        reduce_kernel<Fmt, RW, NB><<<grid, kGemvThreads, smem, stream>>>(p);               \
+        reduce_kernel<Fmt, NB, MINB><<<grid, kGemvThreads, smem, stream>>>(p);             \
     } while (0)
-    if (cpl >= 4) KTB_RED(1, 4);
-    else if (cpl >= 2) KTB_RED(2, 2);
-    else KTB_RED(4, 1);
+    if (NBMAX >= 2 && nsteps >= 2) {
+        if (minb == 3) KTB_RED((NBMAX >= 2 ? 2 : 1), 3); else KTB_RED((NBMAX >= 2 ? 2 : 1), 2);
+    } else {
+        if (minb == 3) KTB_RED(1, 3); else KTB_RED(1, 2);
+    }
 #undef KTB_RED
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
@@ -155,10 +165,10 @@ static int launch_reduce_fmt(const ReduceParams& p, int T, int device, cudaStrea
 
 static int launch_reduce(FmtId f, const ReduceParams& p, int T, int device, cudaStream_t stream) {
     switch (f) {
-        case FMT_Q4K: return launch_reduce_fmt<FmtQ4K>(p, T, device, stream);
-        case FMT_Q5K: return launch_reduce_fmt<FmtQ5K>(p, T, device, stream);
-        case FMT_Q6K8: return launch_reduce_fmt<FmtQ6K8>(p, T, device, stream);
-        case FMT_GENK: return launch_reduce_fmt<FmtGenK>(p, T, device, stream);
+        case FMT_Q4K: return launch_reduce_fmt<FmtQ4K, 2>(p, T, device, stream, true);
+        case FMT_Q5K: return launch_reduce_fmt<FmtQ5K, 1>(p, T, device, stream, false);
+        case FMT_Q6K8: return launch_reduce_fmt<FmtQ6K8, 1>(p, T, device, stream, true);
+        case FMT_GENK: return launch_reduce_fmt<FmtGenK, 1>(p, T, device, stream, false);
         default: set_error("unsupported weight type"); return KTB200_EINVAL;
     }
 }
@@ -192,6 +202,13 @@ __global__ void __launch_bounds__(256) quantize_q8_0_kernel(const void* x, int h
 using namespace ktb;
 
 // ------------------------------------------------------------------------------------------
+struct ktb200_mlp {
+    int H, I, gate_type, up_type, down_type, hidden_type, group_max_len, device;
+    const void *gate, *up, *down;
+    bool loaded, gu_soa, down_soa;
+    float* inter;
+};
+
 struct ktb200_moe {
     ktb200_moe_config cfg;
     int device;
@@ -243,7 +260,8 @@ int ktb200_moe_create(const ktb200_moe_config* c, int device, ktb200_moe** out) 
     m->inter = nullptr; m->ids_d = nullptr; m->w_d = nullptr; m->in_d = nullptr; m->out_d = nullptr;
     const size_t slots = (size_t)c->group_max_len * c->routed_expert_num;
     const size_t hid = (size_t)c->group_max_len * c->hidden_size * type_size(c->hidden_type);
-    cudaError_t e = cudaMalloc(&m->inter, slots * c->intermediate_size * sizeof(float));
+    // +1 slot per token: the optionally fused shared expert (ktb200_moe_forward_shared)
+    cudaError_t e = cudaMalloc(&m->inter, (slots + c->group_max_len) * c->intermediate_size * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&m->ids_d, slots * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMalloc(&m->w_d, slots * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&m->in_d, hid);
@@ -289,7 +307,7 @@ int ktb200_moe_load_weights(ktb200_moe* m, void* stream) {
 float* ktb200_moe_intermediate(ktb200_moe* m) { return m ? m->inter : nullptr; }
 
 static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
-                            void* output, const int* bsz, cudaStream_t s, cudaEvent_t mid) {
+                            void* output, const int* bsz, cudaStream_t s, cudaEvent_t mid, const ktb200_mlp* sh = nullptr) {
     if (!m) { set_error("null handle"); return KTB200_EINVAL; }
     if (!m->loaded) { set_error("Not Loaded"); return KTB200_ESTATE; }
     if (qlen <= 0) return KTB200_OK;
@@ -306,6 +324,13 @@ static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, 
     rp.n_experts = c.expert_num; rp.rows = c.intermediate_size; rp.ncols = c.hidden_size; rp.slots = k;
     rp.ids = ids; rp.id_offset = c.expert_id_offset; rp.x = input; rp.hidden_type = c.hidden_type;
     rp.use_silu = c.use_silu; rp.out_f32 = m->inter; rp.out_hidden = nullptr; rp.bias = nullptr; rp.bsz = bsz;
+    const FmtId fd = pick_fmt(c.down_type, m->down_soa);
+    // the shared expert rides in the same two launches as slot k when its tensors have the routed experts'
+    // shapes and layouts (DeepSeek-V3: n_shared_experts = 1, same quant types); otherwise it runs separately
+    const bool fuse = sh && sh->loaded && sh->H == c.hidden_size && sh->I == c.intermediate_size && c.use_silu &&
+                      sh->hidden_type == c.hidden_type && sh->gate_type == c.gate_type && sh->up_type == c.up_type &&
+                      sh->down_type == c.down_type && sh->gu_soa == m->gu_soa && sh->down_soa == m->down_soa;
+    if (fuse) { rp.x0 = sh->gate; rp.x1 = sh->up; }
     int rc = launch_rows<true>(fg, rp, qlen, m->device, s);
     if (rc) return rc;
     if (mid) KTB_CUDA_CHECK(cudaEventRecord(mid, s));
@@ -314,7 +339,16 @@ static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, 
     dp.w = c.down_proj; dp.type = c.down_type; dp.n_experts = c.expert_num; dp.rows = c.hidden_size;
     dp.ncols = c.intermediate_size; dp.slots = k; dp.ids = ids; dp.id_offset = c.expert_id_offset;
     dp.weights = weights; dp.a = m->inter; dp.out = output; dp.hidden_type = c.hidden_type; dp.accumulate = 0; dp.bsz = bsz;
-    return launch_reduce(pick_fmt(c.down_type, m->down_soa), dp, qlen, m->device, s);
+    if (fuse) dp.xw = sh->down;
+    rc = launch_reduce(fd, dp, qlen, m->device, s);
+    if (rc || !sh || fuse) return rc;
+    return ktb200_mlp_forward(const_cast<ktb200_mlp*>(sh), qlen, input, output, 1, bsz, (void*)s);
+}
+
+int ktb200_moe_forward_shared(ktb200_moe* m, ktb200_mlp* shared, int qlen, int k, const int64_t* ids, const float* weights,
+                              const void* input, void* output, const int* bsz, void* stream) {
+    if (shared && !shared->loaded) { set_error("shared expert: Not Loaded"); return KTB200_ESTATE; }
+    return moe_forward_impl(m, qlen, k, ids, weights, input, output, bsz, (cudaStream_t)stream, nullptr, shared);
 }
 
 int ktb200_moe_forward(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
@@ -435,12 +469,6 @@ int ktb200_linear_forward(ktb200_linear* l, int qlen, const void* input, void* o
 }
 
 // ------------------------------------------------------------------------------------------ mlp
-struct ktb200_mlp {
-    int H, I, gate_type, up_type, down_type, hidden_type, group_max_len, device;
-    const void *gate, *up, *down;
-    bool loaded, gu_soa, down_soa;
-    float* inter;
-};
 
 int ktb200_mlp_create(int H, int I, const void* gate, const void* up, const void* down, int gate_type, int up_type,
                       int down_type, int hidden_type, int group_max_len, int device, ktb200_mlp** out) {

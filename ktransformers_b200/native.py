@@ -72,6 +72,7 @@ SYMBOLS = {
     "ktb200_mlp_destroy": (None, [_VP]),
     "ktb200_mlp_load_weights": (_I, [_VP, _VP]),
     "ktb200_mlp_forward": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP]),
+    "ktb200_moe_forward_shared": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ktb200_quantize_activations": (_I, [_VP, _I, _L, _L, _I, _VP, _VP]),
     "ktb200_dequantize": (_I, [_VP, _I, _L, _VP, _I, _VP]),
     "ktb200_moe_gate_forward": (_I, [C.POINTER(GateConfig), _I, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -72,6 +72,33 @@ class Moe:
             pass
 
 
+class Mlp:
+    def __init__(self, H, I, g, u, d, gt, ut, dt, hidden_type):
+        self.lib = native.lib()
+        self.keep = tuple(t if isinstance(t, torch.Tensor) else dev(t) for t in (g, u, d))
+        self.h = C.c_void_p()
+        native.check(self.lib.ktb200_mlp_create(H, I, self.keep[0].data_ptr(), self.keep[1].data_ptr(), self.keep[2].data_ptr(),
+                                                gt, ut, dt, hidden_type, 64, torch.cuda.current_device(), C.byref(self.h)))
+        native.check(self.lib.ktb200_mlp_load_weights(self.h, stream()))
+
+    def close(self):
+        if self.h:
+            self.lib.ktb200_mlp_destroy(self.h)
+            self.h = None
+
+
+def moe_forward_shared(moe: "Moe", mlp: "Mlp", ids, w, x):
+    qlen, k = ids.shape
+    ids_d, w_d = dev(ids.astype(np.int64)), dev(w.astype(np.float32))
+    x_d = dev(x, TORCH_HID[moe.hidden_type] if moe.hidden_type == 30 else None)
+    out_d = torch.zeros((qlen, moe.H), dtype=TORCH_HID[moe.hidden_type], device="cuda")
+    native.check(moe.lib.ktb200_moe_forward_shared(moe.h, mlp.h if mlp is not None else None, qlen, k, ids_d.data_ptr(), w_d.data_ptr(),
+                                                   x_d.data_ptr(), out_d.data_ptr(), None, stream()))
+    torch.cuda.synchronize()
+    o = out_d.cpu()
+    return o.view(torch.int16).numpy().view(np.uint16) if moe.hidden_type == 30 else o.numpy()
+
+
 def linear_forward(in_size, out_size, proj, proj_type, hidden_type, x, bias=None):
     lib = native.lib()
     p = proj if isinstance(proj, torch.Tensor) else dev(proj)

@@ -187,6 +187,33 @@ def test_moe_expert_parallel_shards_sum_to_full():
     assert relmax(acc, full) < 1e-5
 
 
+@pytest.mark.parametrize("sgt,sdt,fused", [(Q4_K, Q6_K, True), (Q5_K, Q4_K, False)])
+def test_moe_with_shared_expert_matches_two_rounded_terms(oracle, sgt, sdt, fused):
+    """KDeepseekV3MoE: y = experts(x); y += shared_experts(x) on bf16 tensors — each term rounded, then the sum.
+    Same quant types as the routed experts -> the shared expert is an extra slot inside the two routed launches;
+    different types -> it runs as a separate MLP.  Both must give the reference's two-rounding result."""
+    E, k, H, I = 8, 4, 1024, 512
+    gate, up, down = _synth(Q4_K, E * I * H, 71), _synth(Q4_K, E * I * H, 72), _synth(Q6_K, E * H * I, 73)
+    sg, su, sd = _synth(sgt, I * H, 74), _synth(sgt, I * H, 75), _synth(sdt, H * I, 76)
+    g_np, u_np, d_np, sg_np, su_np, sd_np = (t.cpu().numpy() for t in (gate, up, down, sg, su, sd))
+    m = G.Moe(E, k, H, I, gate, up, down, Q4_K, Q4_K, Q6_K, BF16)
+    mlp = G.Mlp(H, I, sg, su, sd, sgt, sgt, sdt, BF16)
+    rng = np.random.default_rng(17)
+    for qlen in (1, 5):
+        x = f32_to_bf16_bits((rng.standard_normal((qlen, H)) / 100).astype(np.float32))
+        ids = np.stack([rng.permutation(E)[:k] for _ in range(qlen)]).astype(np.int64)
+        w = rng.random((qlen, k)).astype(np.float32)
+        n0 = native.launch_count()
+        got = G.moe_forward_shared(m, mlp, ids, w, x)
+        assert native.launch_count() - n0 == (2 if fused else 4)
+        routed = oracle.moe_forward(E, H, I, g_np, u_np, d_np, Q4_K, Q4_K, Q6_K, BF16, ids, w, x)
+        shared = oracle.mlp_forward(H, I, sg_np, su_np, sd_np, sgt, sgt, sdt, BF16, x)
+        want = (torch.from_numpy(routed.view(np.int16)).view(torch.bfloat16) + torch.from_numpy(shared.view(np.int16)).view(torch.bfloat16))
+        assert_bf16_close(got, want.view(torch.int16).numpy().view(np.uint16))
+        assert np.array_equal(G.moe_forward_shared(m, None, ids, w, x), m.forward(ids, w, x))
+    m.close(); mlp.close()
+
+
 # ------------------------------------------------------------------------------------------ linear / mlp
 def test_linear_and_mlp_vs_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "linear_mlp.npz"))
