@@ -432,7 +432,7 @@ def main():
                     gu.append(a.value); dn.append(b.value)
         peak, how = measured_peak_gbs()
         ms_gu, ms_dn = statistics.mean(gu), statistics.mean(dn)
-        ach = K * BYTES_GATE_UP_PER_EXPERT / (ms_gu * 1e-3) / 1e9
+        ach = K * BYTES_GATE_UP_PER_EXPERT / (ms_gu * 1e-3) / 1e9   # routed launch only (ktb200_moe_forward_timed has no shared slot)
         roof = {"kernel": "rows_kernel<FmtQ4K,PAIR> (gate/up GEMV + SiLU*mul)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "peak_source": how, "traffic": None, "bytes_per_launch": K * BYTES_GATE_UP_PER_EXPERT, "ms_per_launch": ms_gu}
         achd = K * BYTES_DOWN_PER_EXPERT / (ms_dn * 1e-3) / 1e9

@@ -168,3 +168,29 @@ def gate_forward(x, W, bias, top_k, n_group, topk_group, scoring=0, topk_method=
                                              logits.data_ptr() if logits is not None else None, None, stream()))
     torch.cuda.synchronize()
     return idx.cpu().numpy(), w.cpu().numpy(), (logits.cpu().numpy() if logits is not None else None)
+
+
+def mla_decode(q_nope, q_pe, kv_cache, page_table, kv_len, sm_scale, num_kv_splits=0):
+    """numpy float32 arrays holding bf16 values -> (out [B,H,512] float32, lse [B,H])"""
+    lib = native.lib()
+    B, Hq, _ = q_nope.shape
+    to_bf = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).cuda()
+    qn, qp, kv = to_bf(q_nope), to_bf(q_pe), to_bf(kv_cache)
+    pt = torch.from_numpy(np.ascontiguousarray(page_table.astype(np.int32))).cuda()
+    kl = torch.from_numpy(np.ascontiguousarray(kv_len.astype(np.int32))).cuda()
+    out = torch.zeros((B, Hq, 512), dtype=torch.bfloat16, device="cuda")
+    lse = torch.zeros((B, Hq), dtype=torch.float32, device="cuda")
+    ws_bytes = lib.ktb200_mla_workspace_bytes(B, Hq, 0)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
+    p = native.MlaParams(B, Hq, kv_cache.shape[1], page_table.shape[1], num_kv_splits, float(sm_scale), qn.data_ptr(), qp.data_ptr(),
+                         kv.data_ptr(), pt.data_ptr(), kl.data_ptr(), out.data_ptr(), lse.data_ptr(), ws.data_ptr(), ws_bytes)
+    native.check(lib.ktb200_mla_decode(C.byref(p), stream()))
+    torch.cuda.synchronize()
+    return out.float().cpu().numpy(), lse.cpu().numpy()
+
+
+def mla_kv_write(kv_cache_t, page_size, ckv, k_pe, page_idx, page_off):
+    lib = native.lib()
+    native.check(lib.ktb200_mla_kv_write(kv_cache_t.data_ptr(), page_size, ckv.data_ptr(), k_pe.data_ptr(), page_idx.data_ptr(),
+                                         page_off.data_ptr(), ckv.shape[0], stream()))
+    torch.cuda.synchronize()

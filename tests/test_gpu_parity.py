@@ -293,6 +293,62 @@ def test_gate_vs_oracle_full_shapes(E, H, k, ng, tg, scoring, method, norm, scal
     assert idx_b.shape == idx.shape and (idx_b >= 0).all() and (idx_b < E).all()
 
 
+# ------------------------------------------------------------------------------------------ MLA decode
+def _mla_case(rng, B, Hq, page_size, lens, shuffle_pages=True):
+    from oracle.mla_oracle import bf16_round
+    max_pages = max((l + page_size - 1) // page_size for l in lens)
+    n_pages = B * max_pages + 3
+    kv = bf16_round(rng.standard_normal((n_pages, page_size, 576)).astype(np.float32))
+    perm = rng.permutation(n_pages) if shuffle_pages else np.arange(n_pages)
+    page_table = perm[: B * max_pages].reshape(B, max_pages).astype(np.int32)
+    q_nope = bf16_round((rng.standard_normal((B, Hq, 512)) * 0.5).astype(np.float32))
+    q_pe = bf16_round((rng.standard_normal((B, Hq, 64)) * 0.5).astype(np.float32))
+    return q_nope, q_pe, kv, page_table, np.array(lens, np.int32)
+
+
+@pytest.mark.parametrize("B,Hq,page_size,lens,splits", [
+    (1, 128, 64, [1], 0), (1, 128, 64, [33], 0), (1, 128, 64, [1000], 0), (1, 128, 64, [4096], 0),
+    (3, 128, 64, [17, 640, 2049], 0), (2, 16, 32, [95, 128], 0), (1, 128, 256, [777], 3), (2, 40, 64, [64, 65], 1),
+])
+def test_mla_decode_vs_oracle(B, Hq, page_size, lens, splits):
+    from oracle import mla_oracle
+    rng = np.random.default_rng(sum(lens) + Hq)
+    q_nope, q_pe, kv, pt, kl = _mla_case(rng, B, Hq, page_size, lens)
+    scale = (128 + 64) ** -0.5
+    out, lse = G.mla_decode(q_nope, q_pe, kv, pt, kl, scale, num_kv_splits=splits)
+    want, want_lse = mla_oracle.mla_decode(q_nope, q_pe, kv, pt, kl, scale, p_bf16=True)
+    exact, _ = mla_oracle.mla_decode(q_nope, q_pe, kv, pt, kl, scale, p_bf16=False)
+    ref_mag = np.abs(exact).max()
+    # vs the bf16-P restatement: bf16 output rounding + fp32 accumulation order only
+    assert np.abs(out - want).max() <= 2.0 ** -7 * ref_mag + 1e-3 * ref_mag
+    # vs exact softmax attention: bf16 P noise (reference's own bound is 1e-1 max / 2e-1 rel-mean, test_mla_qlen.py:345)
+    assert np.abs(out - exact).max() <= 2e-2 * ref_mag
+    assert np.abs(out - exact).mean() <= 5e-3 * np.abs(exact).mean() + 1e-6
+    np.testing.assert_allclose(lse, want_lse, rtol=0, atol=2e-3)
+
+
+def test_mla_kv_write_then_decode_roundtrip():
+    """StaticCache.update semantics: writing tokens through the paged write kernel and attending over them equals
+    attending over a cache built on the host."""
+    rng = np.random.default_rng(5)
+    B, Hq, page_size, L = 1, 128, 64, 200
+    q_nope, q_pe, kv, pt, kl = _mla_case(rng, B, Hq, page_size, [L])
+    kv_t = torch.zeros(kv.shape, dtype=torch.bfloat16, device="cuda")
+    toks = np.arange(L)
+    from oracle.mla_oracle import gather_kv
+    rows = gather_kv(kv, pt[0], L, page_size)
+    ckv = torch.from_numpy(rows[:, :512].copy()).to(torch.bfloat16).cuda()
+    kpe = torch.from_numpy(rows[:, 512:].copy()).to(torch.bfloat16).cuda()
+    pidx = torch.from_numpy(pt[0][toks // page_size].astype(np.int32)).cuda()
+    poff = torch.from_numpy((toks % page_size).astype(np.int32)).cuda()
+    G.mla_kv_write(kv_t, page_size, ckv, kpe, pidx, poff)
+    written = kv_t.float().cpu().numpy()
+    assert np.array_equal(gather_kv(written, pt[0], L, page_size), rows)
+    a, _ = G.mla_decode(q_nope, q_pe, written, pt, kl, 0.07)
+    b, _ = G.mla_decode(q_nope, q_pe, kv, pt, kl, 0.07)
+    assert np.array_equal(a, b)
+
+
 # ------------------------------------------------------------------------------------------ full BASELINE shapes
 def test_v3_full_shape_decode_vs_oracle_and_properties(oracle):
     """DeepSeek-V3 routed experts at real size (E=256 resident, k=8, H=7168, I=2048, Q4_K/Q4_K/Q6_K), bs=1."""
