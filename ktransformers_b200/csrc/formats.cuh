@@ -56,6 +56,7 @@ struct FmtQ4K {
     __device__ static __forceinline__ Row row(const void* base, long row_idx, int ncols, int /*type*/) {
         return Row{reinterpret_cast<const uint8_t*>(base) + row_idx * (long)(ncols / QK_K) * SZ_Q4_K};
     }
+    __device__ static __forceinline__ void prefetch(const Row& r, int nblk) { prefetch_l2_bulk(r.p, nblk * SZ_Q4_K); }
     __device__ static __forceinline__ void load(const Row& r, int blk, const Lane& L, Regs& R) {
         const uint8_t* b = r.p + blk * SZ_Q4_K;
         R.hdr = ldg_stream16(b);
@@ -112,6 +113,11 @@ struct FmtQ6K8 {
         const uint8_t* g = reinterpret_cast<const uint8_t*>(base) + G * (8 * SZ_Q6_K) * nb;
         return Row{g + r8 * 128 * nb, g + 1024 * nb + r8 * 64 * nb, g + 1536 * nb + r8 * 16 * nb,
                    g + 1664 * nb + r8 * 2 * nb};
+    }
+    __device__ static __forceinline__ void prefetch(const Row& r, int nblk) {
+        prefetch_l2_bulk(r.ql, nblk * 128);
+        prefetch_l2_bulk(r.qh, nblk * 64);
+        prefetch_l2_bulk(r.sc, nblk * 16);
     }
     __device__ static __forceinline__ void load(const Row& r, int blk, const Lane& L, Regs& R) {
         R.a = ldg_stream16(r.ql + blk * 128 + L.ql_off);
@@ -175,6 +181,7 @@ struct FmtQ5K {
     __device__ static __forceinline__ Row row(const void* base, long row_idx, int ncols, int) {
         return Row{reinterpret_cast<const uint8_t*>(base) + row_idx * (long)(ncols / QK_K) * SZ_Q5_K};
     }
+    __device__ static __forceinline__ void prefetch(const Row& r, int nblk) { prefetch_l2_bulk(r.p, nblk * SZ_Q5_K); }
     __device__ static __forceinline__ void load(const Row& r, int blk, const Lane& L, Regs& R) {
         const uint8_t* b = r.p + blk * SZ_Q5_K;
         R.hdr = ldg_stream16(b);
@@ -333,6 +340,7 @@ struct FmtGenK {
         const int bsz = (int)type_size(type);
         return Row{reinterpret_cast<const uint8_t*>(base) + row_idx * (long)(ncols / QK_K) * bsz, type, bsz};
     }
+    __device__ static __forceinline__ void prefetch(const Row&, int) {}
     __device__ static __forceinline__ void load(const Row& r, int blk, const Lane& L, Regs& R) {
         unpack_group16(r.type, r.p + (long)blk * r.bsz, L.g, R);
     }

@@ -27,7 +27,7 @@ struct GateParams {
     int top_k, n_group, topk_group, scoring, topk_method, norm_topk_prob;
     float routed_scaling_factor;
     const float* bias;
-    float* partial;      // [T][E][S]
+    float* partial;      // [T][S][E]
     float* logits_out;   // optional [T][E]
     int64_t* idx;
     float* w;
@@ -41,28 +41,59 @@ __device__ __forceinline__ unsigned fkey(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+constexpr int kGateEPL = 16;   // experts per lane held in registers (E <= 512)
+
 __device__ void gate_select_token(const GateParams& p, int t, int lane, float* scores, float* choice) {
     const int E = p.E;
+    // logits = sum of the S partials (fixed order), lane owns experts e = lane + 32*i
+    float v[kGateEPL];
+#pragma unroll
+    for (int i = 0; i < kGateEPL; i++) v[i] = 0.f;
+    for (int s = 0; s < p.S; s++) {
+        const float* pp = p.partial + ((long)t * p.S + s) * E;
+#pragma unroll
+        for (int i = 0; i < kGateEPL; i++) {
+            const int e = lane + 32 * i;
+            if (e < E) v[i] += __ldcg(pp + e);   // written by other SMs in this launch: read at L2
+        }
+    }
     float lmax = -INFINITY;
-    for (int e = lane; e < E; e += 32) {
-        float v = 0.f;
-        const float* pp = p.partial + ((long)t * E + e) * p.S;
-        for (int s = 0; s < p.S; s++) v += __ldcg(pp + s);   // written by other SMs in this launch: read at L2
-        if (p.logits_out) p.logits_out[(long)t * E + e] = v;
-        scores[e] = v;
-        lmax = fmaxf(lmax, v);
+#pragma unroll
+    for (int i = 0; i < kGateEPL; i++) {
+        const int e = lane + 32 * i;
+        if (e < E) {
+            if (p.logits_out) p.logits_out[(long)t * E + e] = v[i];
+            lmax = fmaxf(lmax, v[i]);
+        }
     }
     if (p.scoring == 0) {  // sigmoid
-        for (int e = lane; e < E; e += 32) scores[e] = __fdiv_rn(1.0f, 1.0f + expf(-scores[e]));
+#pragma unroll
+        for (int i = 0; i < kGateEPL; i++) v[i] = __fdiv_rn(1.0f, 1.0f + expf(-v[i]));
     } else {               // softmax(dim=-1, fp32)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
         float sum = 0.f;
-        for (int e = lane; e < E; e += 32) { const float ex = expf(scores[e] - lmax); scores[e] = ex; sum += ex; }
+#pragma unroll
+        for (int i = 0; i < kGateEPL; i++) {
+            const int e = lane + 32 * i;
+            v[i] = (e < E) ? expf(v[i] - lmax) : 0.f;
+            sum += v[i];
+        }
         sum = warp_sum(sum);
-        for (int e = lane; e < E; e += 32) scores[e] = __fdiv_rn(scores[e], sum);
+#pragma unroll
+        for (int i = 0; i < kGateEPL; i++) v[i] = __fdiv_rn(v[i], sum);
     }
-    for (int e = lane; e < E; e += 32) choice[e] = scores[e] + ((p.topk_method == 0 && p.bias) ? p.bias[e] : 0.f);
+    float c[kGateEPL];   // selection scores
+#pragma unroll
+    for (int i = 0; i < kGateEPL; i++) {
+        const int e = lane + 32 * i;
+        c[i] = -INFINITY;
+        if (e < E) {
+            c[i] = v[i] + ((p.topk_method == 0 && p.bias) ? p.bias[e] : 0.f);
+            scores[e] = v[i];
+            choice[e] = c[i];
+        }
+    }
     __syncwarp();
 
     // group selection (noaux_tc: sum of the group's top-2 biased scores; group_limited_greedy: group max)
@@ -75,8 +106,8 @@ __device__ void gate_select_token(const GateParams& p, int t, int lane, float* s
             const int lpg = 32 / p.n_group, g = lane / lpg, sub = lane % lpg;
             float m1 = -INFINITY, m2 = -INFINITY;
             for (int i = sub; i < gs; i += lpg) {
-                const float v = choice[g * gs + i];
-                if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) { m2 = v; }
+                const float x = choice[g * gs + i];
+                if (x > m1) { m2 = m1; m1 = x; } else if (x > m2) { m2 = x; }
             }
             for (int o = 1; o < lpg; o <<= 1) {
                 const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
@@ -90,8 +121,8 @@ __device__ void gate_select_token(const GateParams& p, int t, int lane, float* s
         } else if (lane < p.n_group) {
             float m1 = -INFINITY, m2 = -INFINITY;
             for (int i = 0; i < gs; i++) {
-                const float v = choice[lane * gs + i];
-                if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) { m2 = v; }
+                const float x = choice[lane * gs + i];
+                if (x > m1) { m2 = m1; m1 = x; } else if (x > m2) { m2 = x; }
             }
             gscore = (p.topk_method == 0) ? (m1 + m2) : m1;
         }
@@ -102,31 +133,38 @@ __device__ void gate_select_token(const GateParams& p, int t, int lane, float* s
         }
         const unsigned sel = __ballot_sync(0xffffffffu, lane < p.n_group && rank < p.topk_group);
         const float fill = (p.topk_method == 0) ? -INFINITY : 0.0f;  // V3 masks with -inf, V2 with 0.0
-        for (int e = lane; e < E; e += 32)
-            if (!((sel >> (e / gs)) & 1u)) choice[e] = fill;
-        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kGateEPL; i++) {
+            const int e = lane + 32 * i;
+            if (e < E && !((sel >> (e / gs)) & 1u)) c[i] = fill;
+        }
     }
 
-    // top-k by iterative arg-max; ties -> lowest expert index
+    // top-k by iterative arg-max over the register-resident scores; ties -> lowest expert index
     float wsum = 0.f, myw = 0.f;
     long myidx = 0;
-    for (int i = 0; i < p.top_k; i++) {
+    for (int it = 0; it < p.top_k; it++) {
         unsigned bk = 0;
         int bi = 0x7fffffff;
-        for (int e = lane; e < E; e += 32) {
-            const unsigned kk = fkey(choice[e]);
+#pragma unroll
+        for (int i = 0; i < kGateEPL; i++) {
+            const int e = lane + 32 * i;
+            const unsigned kk = (e < E) ? fkey(c[i]) : 0u;
             if (kk > bk) { bk = kk; bi = e; }
         }
         const unsigned mx = __reduce_max_sync(0xffffffffu, bk);
         int win = __reduce_min_sync(0xffffffffu, (bk == mx) ? bi : 0x7fffffff);
         if (win == 0x7fffffff) win = 0;  // degenerate (all NaN)
-        // V3 gathers from the un-biased scores; V2 group_limited takes the (masked) score itself
-        const float wv = (p.topk_method == 2) ? choice[win] : scores[win];
-        if (lane == i) { myw = wv; myidx = win; }
+        // the winner's owner broadcasts its selection score; V3 gathers the weight from the un-biased scores,
+        // V2 group_limited takes the (masked) score itself
+        float cw = 0.f;
+#pragma unroll
+        for (int i = 0; i < kGateEPL; i++)
+            if (lane + 32 * i == win) { cw = c[i]; c[i] = -INFINITY; }
+        cw = __shfl_sync(0xffffffffu, cw, win & 31);
+        const float wv = (p.topk_method == 2) ? cw : scores[win];
+        if (lane == it) { myw = wv; myidx = win; }
         wsum += wv;
-        __syncwarp();
-        if (lane == 0) choice[win] = -INFINITY;
-        __syncwarp();
     }
     // V3 (modeling_deepseek_v3.py:474-479): normalise (if top_k>1 && norm_topk_prob) THEN always scale;
     // V2 (modeling_deepseek.py:455-459): normalise XOR scale.
@@ -156,10 +194,9 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
     for (int t0 = 0; t0 < Teff; t0 += kGateTokTile) {
         const int nt = min(kGateTokTile, Teff - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < nt * nc4 * 4; i += kGateThreads) {
-            const int tt = i / (nc4 * 4), c = i - tt * (nc4 * 4);
-            xs[i] = load_hidden(p.x, (long)(t0 + tt) * p.H + 4L * c0 + c, p.hidden_type);
-        }
+        for (int tt = 0; tt < nt; tt++)
+            for (int c = threadIdx.x; c < nc4 * 4; c += kGateThreads)
+                xs[tt * nc4 * 4 + c] = load_hidden(p.x, (long)(t0 + tt) * p.H + 4L * c0 + c, p.hidden_type);
         __syncthreads();
         if (e < p.E) {
             float acc[kGateTokTile];
@@ -193,7 +230,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
             for (int i = 0; i < kGateTokTile; i++) {
                 if (i < nt) {
                     const float v = warp_sum(acc[i]);
-                    if (lane == 0) p.partial[((long)(t0 + i) * p.E + e) * S + s] = v;
+                    if (lane == 0) p.partial[((long)(t0 + i) * S + s) * p.E + e] = v;
                 }
             }
         }
@@ -228,6 +265,7 @@ extern "C" int ktb200_moe_gate_forward(const ktb200_gate_config* c, int qlen, co
     using namespace ktb;
     if (!c || !x || !idx || !w) { set_error("null pointer"); return KTB200_EINVAL; }
     if (qlen <= 0) return KTB200_OK;
+    if (c->n_experts > 32 * kGateEPL) { set_error("gate: at most %d experts", 32 * kGateEPL); return KTB200_EINVAL; }
     if (c->n_experts <= 0 || c->hidden_size <= 0 || c->hidden_size % 4 || c->top_k <= 0 || c->top_k > 32 || c->top_k > c->n_experts) {
         set_error("gate: bad shape (E=%d H=%d top_k=%d; top_k<=32, H%%4==0)", c->n_experts, c->hidden_size, c->top_k);
         return KTB200_EINVAL;

@@ -118,46 +118,59 @@ __global__ void __launch_bounds__(kGemvThreads, MINB) rows_kernel(const RowsPara
     uint8_t* q8 = smem;                                                        // ncols
     float* dx = reinterpret_cast<float*>(smem + p.ncols);                      // nblk
     int16_t* bsums = reinterpret_cast<int16_t*>(smem + p.ncols + nblk * 4);    // ncols/16
-    cta_quantize_q8k_rows<4>(p.x, (long)t * p.ncols, 0, p.hidden_type, 1, p.ncols, 0u, q8, dx, bsums);
-    __syncthreads();
     const ActQ8K act{q8, dx, bsums};
     const typename Fmt::Lane L = Fmt::lane(lane);
 
     const int nslots = p.slots + (p.x0 ? 1 : 0);
-    const long total = (long)nslots * p.rows;
-    const long u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int total = nslots * p.rows;   // < 2^31 (launcher checks): keep the per-unit index math 32-bit
+    const int u0 = (int)((long)total * blockIdx.x / gridDim.x), u1 = (int)((long)total * (blockIdx.x + 1) / gridDim.x);
     constexpr int NM = PAIR ? 2 : 1;
 
-    for (long ub = u0 + (long)warp * RW; ub < u1; ub += (long)nwarps * RW) {
+    // rows of unit u (one per matrix); returns false for skipped experts / out-of-range units
+    auto unit_rows = [&](int u, typename Fmt::Row (&r)[NM]) -> bool {
+        if (u >= u1) return false;
+        const int s = u / p.rows, rr = u - s * p.rows;
+        if (s == p.slots) {  // the fused extra slot
+            r[0] = Fmt::row(p.x0, rr, p.ncols, p.type0);
+            if (PAIR) r[NM - 1] = Fmt::row(p.x1, rr, p.ncols, p.type1);
+            return true;
+        }
+        const long e = p.ids ? (long)p.ids[(long)t * p.slots + s] - p.id_offset : 0;
+        if (e < 0 || e >= p.n_experts) return false;
+        r[0] = Fmt::row(p.w0, e * p.rows + rr, p.ncols, p.type0);
+        if (PAIR) r[NM - 1] = Fmt::row(p.w1, e * p.rows + rr, p.ncols, p.type1);
+        return true;
+    };
+    // L2 prefetch of the rows a warp will stream NEXT: one lane, one instruction per row, no registers held.
+    auto prefetch_units = [&](int ub) {
+        if (lane < RW) {
+            typename Fmt::Row r[NM];
+            if (unit_rows(ub + lane, r)) {
+#pragma unroll
+                for (int m = 0; m < NM; m++) Fmt::prefetch(r[m], nblk);
+            }
+        }
+    };
+
+    prefetch_units(u0 + warp * RW);   // first units go to L2 while the activation row is quantised
+    cta_quantize_q8k_rows<4>(p.x, (long)t * p.ncols, 0, p.hidden_type, 1, p.ncols, 0u, q8, dx, bsums);
+    __syncthreads();
+
+    for (int ub = u0 + warp * RW; ub < u1; ub += nwarps * RW) {
+        prefetch_units(ub + nwarps * RW);
         typename Fmt::Row rp[RW][NM];
         bool valid[RW];
         float acc[RW][NM];
 #pragma unroll
         for (int rw = 0; rw < RW; rw++) {
-            const long u = ub + rw;
-            valid[rw] = false;
 #pragma unroll
             for (int m = 0; m < NM; m++) acc[rw][m] = 0.f;
-            if (u < u1) {
-                const int s = (int)(u / p.rows), r = (int)(u - (long)s * p.rows);
-                if (s == p.slots) {  // the fused extra slot
-                    valid[rw] = true;
-                    rp[rw][0] = Fmt::row(p.x0, r, p.ncols, p.type0);
-                    if (PAIR) rp[rw][NM - 1] = Fmt::row(p.x1, r, p.ncols, p.type1);
-                } else {
-                    const long e = p.ids ? (long)p.ids[(long)t * p.slots + s] - p.id_offset : 0;
-                    if (e >= 0 && e < p.n_experts) {
-                        valid[rw] = true;
-                        rp[rw][0] = Fmt::row(p.w0, e * p.rows + r, p.ncols, p.type0);
-                        if (PAIR) rp[rw][NM - 1] = Fmt::row(p.w1, e * p.rows + r, p.ncols, p.type1);
-                    }
-                }
-            }
+            valid[rw] = unit_rows(ub + rw, rp[rw]);
         }
         gemv_rows<Fmt, RW, NM, NB>(rp, valid, act, nblk, L, acc);
 #pragma unroll
         for (int rw = 0; rw < RW; rw++) {
-            const long u = ub + rw;
+            const int u = ub + rw;
             if (u >= u1) continue;
             float g = warp_sum(acc[rw][0]);
             float uu = PAIR ? warp_sum(acc[rw][NM - 1]) : 0.f;
@@ -220,13 +233,31 @@ __global__ void __launch_bounds__(kGemvThreads, MINB) reduce_kernel(const Reduce
         const long e = p.ids ? (long)p.ids[(long)t * k + j] - p.id_offset : 0;
         if (e < 0 || e >= p.n_experts) skip |= 1u << j;
     }
-    cta_quantize_q8k_rows<4>(p.a, (long)t * ns * p.ncols, p.ncols, KTB200_TYPE_F32, ns, p.ncols, skip, q8, dx, bsums);
-    __syncthreads();
-
     const typename Fmt::Lane L = Fmt::lane(lane);
     const int ngroups = (nrows + RW - 1) / RW;
     const int total = ngroups * ns;
+    auto item_base = [&](int item, const void*& wbase, long& row0, int& j, int& hl0) -> bool {
+        if (item >= total) return false;
+        j = item / ngroups;
+        hl0 = (item - j * ngroups) * RW;
+        wbase = p.w;
+        row0 = r0 + hl0;
+        if (j == k) { wbase = p.xw; return true; }
+        if ((skip >> j) & 1u) return false;
+        const long e = p.ids ? (long)p.ids[(long)t * k + j] - p.id_offset : 0;
+        row0 += e * p.rows;
+        return true;
+    };
+    auto prefetch_item = [&](int item) {
+        const void* wb; long row0; int j, hl0;
+        if (lane < RW && item_base(item, wb, row0, j, hl0) && hl0 + lane < nrows)
+            Fmt::prefetch(Fmt::row(wb, row0 + lane, p.ncols, p.type), nblk);
+    };
+    prefetch_item(warp);   // weights do not depend on phase 1: pull the first rows into L2 during the prologue
+    cta_quantize_q8k_rows<4>(p.a, (long)t * ns * p.ncols, p.ncols, KTB200_TYPE_F32, ns, p.ncols, skip, q8, dx, bsums);
+    __syncthreads();
     for (int item = warp; item < total; item += nwarps) {
+        prefetch_item(item + nwarps);
         const int j = item / ngroups, hl0 = (item - j * ngroups) * RW;
         float res = 0.f;
         if (j == k || !((skip >> j) & 1u)) {   // warp-uniform

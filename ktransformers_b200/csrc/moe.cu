@@ -89,7 +89,7 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 static int cfg_minb() { static int v = env_int("KTB200_MINB", 2); return v == 3 ? 3 : 2; }
-static int cfg_nb() { static int v = env_int("KTB200_NB", 4); return v == 2 ? 2 : 4; }
+static int cfg_nb() { static int v = env_int("KTB200_NB", 2); return v == 4 ? 4 : 2; }
 
 template <class Fmt, bool PAIR>
 static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t stream, bool tunable) {
@@ -99,6 +99,7 @@ static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t 
     const int minb = tunable ? cfg_minb() : 2;
     int gx = (minb * num_sms(device) + T - 1) / T;
     const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
+    if (total >= (1L << 31) / 2) { set_error("rows kernel: slots x rows too large"); return KTB200_EINVAL; }
     if (gx > total) gx = (int)total;
     if (gx < 1) gx = 1;
     dim3 grid(gx, T);
