@@ -44,6 +44,7 @@ __device__ __forceinline__ void k4_pair(uint32_t w0, uint32_t w1, uint32_t w2, i
 struct FmtQ4K {
     static constexpr int kType = KTB200_TYPE_Q4_K;
     static constexpr int kBlocksPerStep = 4;
+    static constexpr int kBlockBytes = SZ_Q4_K;
     struct Lane { int blk, qs_off, act_off, bs_off, sh; bool big, half; };
     struct Row { const uint8_t* p; };
     struct Regs { uint4 hdr, qs; };
@@ -61,6 +62,12 @@ struct FmtQ4K {
         const uint8_t* b = r.p + blk * SZ_Q4_K;
         R.hdr = ldg_stream16(b);
         R.qs = ldg_stream16(b + L.qs_off);
+    }
+    // the same slice from a row staged in shared memory (gemv_pipe.cuh)
+    __device__ static __forceinline__ void load_smem(const uint8_t* row, int blk, const Lane& L, Regs& R) {
+        const uint8_t* b = row + blk * SZ_Q4_K;
+        R.hdr = *reinterpret_cast<const uint4*>(b);
+        R.qs = *reinterpret_cast<const uint4*>(b + L.qs_off);
     }
     __device__ static __forceinline__ void load_act(const ActQ8K& a, int blk, const Lane& L, Act& A) {
         const uint8_t* q = a.q8 + blk * QK_K + L.act_off;
@@ -126,6 +133,14 @@ struct FmtQ6K8 {
         R.s = ldg_stream16(r.sc + blk * 16);
         R.d = ldg_u16(r.d + blk * 2);
     }
+    // the same slices from an item staged in shared memory (gemv_pipe.cuh): Row pointers point into smem
+    __device__ static __forceinline__ void load_smem(const Row& r, int blk, const Lane& L, Regs& R) {
+        R.a = *reinterpret_cast<const uint4*>(r.ql + blk * 128 + L.ql_off);
+        R.b = *reinterpret_cast<const uint4*>(r.ql + blk * 128 + L.ql_off + 32);
+        R.h = *reinterpret_cast<const uint4*>(r.qh + blk * 64 + L.qh_off);
+        R.s = *reinterpret_cast<const uint4*>(r.sc + blk * 16);
+        R.d = *reinterpret_cast<const uint16_t*>(r.d + blk * 2);
+    }
     __device__ static __forceinline__ void load_act(const ActQ8K& a, int blk, const Lane& L, Act& A) {
         const uint8_t* q = a.q8 + blk * QK_K + L.act_off;
         A.x0 = *reinterpret_cast<const uint4*>(q);
@@ -169,6 +184,7 @@ struct FmtQ6K8 {
 struct FmtQ5K {
     static constexpr int kType = KTB200_TYPE_Q5_K;
     static constexpr int kBlocksPerStep = 4;
+    static constexpr int kBlockBytes = SZ_Q5_K;
     struct Lane { int blk, qs_off, qh_off, act_off, bs_off, sh, hsh; bool big, half; };
     struct Row { const uint8_t* p; };
     struct Regs { uint4 hdr, qh, qs; };
@@ -182,6 +198,12 @@ struct FmtQ5K {
         return Row{reinterpret_cast<const uint8_t*>(base) + row_idx * (long)(ncols / QK_K) * SZ_Q5_K};
     }
     __device__ static __forceinline__ void prefetch(const Row& r, int nblk) { prefetch_l2_bulk(r.p, nblk * SZ_Q5_K); }
+    __device__ static __forceinline__ void load_smem(const uint8_t* row, int blk, const Lane& L, Regs& R) {
+        const uint8_t* b = row + blk * SZ_Q5_K;
+        R.hdr = *reinterpret_cast<const uint4*>(b);
+        R.qh = *reinterpret_cast<const uint4*>(b + L.qh_off);
+        R.qs = *reinterpret_cast<const uint4*>(b + L.qs_off);
+    }
     __device__ static __forceinline__ void load(const Row& r, int blk, const Lane& L, Regs& R) {
         const uint8_t* b = r.p + blk * SZ_Q5_K;
         R.hdr = ldg_stream16(b);

@@ -5,7 +5,7 @@
 #include <cstring>
 #include <new>
 
-#include "gemv.cuh"
+#include "gemv_pipe.cuh"
 
 namespace ktb {
 
@@ -89,6 +89,7 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 static int cfg_minb() { static int v = env_int("KTB200_MINB", 2); return v == 3 ? 3 : 2; }
+static int cfg_pipe() { static int v = env_int("KTB200_PIPE", 1); return v; }
 static int cfg_nb() { static int v = env_int("KTB200_NB", 2); return v == 4 ? 4 : 2; }
 
 template <class Fmt, bool PAIR>
@@ -120,8 +121,43 @@ static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t 
     return KTB200_OK;
 }
 
+// cp.async-pipelined variant (gemv_pipe.cuh): one CTA per SM, a private 2-slot ring per warp.
+// Returns 1 when the shape does not suit it (caller falls back to rows_kernel).
+template <class Fmt, bool PAIR>
+static int launch_rows_pipe(const RowsParams& p, int T, int device, cudaStream_t stream) {
+    if (!cfg_pipe()) return 1;
+    const int nblk = p.ncols / QK_K;
+    const int row_bytes = nblk * Fmt::kBlockBytes;
+    const int slot = row_bytes * (PAIR ? 2 : 1);
+    const int act = (p.ncols + nblk * 4 + p.ncols / 8 + 15) & ~15;
+    if (slot < 4096) return 1;                          // short rows: the register-staged kernel batches better
+    int warps = 0;
+    for (int w : {12, 8}) if ((size_t)act + (size_t)w * 2 * slot <= 220 * 1024) { warps = w; break; }
+    if (!warps) return 1;
+    const size_t smem = (size_t)act + (size_t)warps * 2 * slot;
+    const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
+    if (total >= (1L << 30)) return 1;
+    int gx = (num_sms(device) + T - 1) / T;
+    if (gx > total) gx = (int)total;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, T);
+    if (warps == 12) {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_kernel<Fmt, PAIR, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_pipe_kernel<Fmt, PAIR, 12><<<grid, 12 * 32, smem, stream>>>(p, act, slot);
+    } else {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_kernel<Fmt, PAIR, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_pipe_kernel<Fmt, PAIR, 8><<<grid, 8 * 32, smem, stream>>>(p, act, slot);
+    }
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
 template <bool PAIR>
 static int launch_rows(FmtId f, const RowsParams& p, int T, int device, cudaStream_t stream) {
+    if (f == FMT_Q4K || f == FMT_Q5K) {
+        const int rc = (f == FMT_Q4K) ? launch_rows_pipe<FmtQ4K, PAIR>(p, T, device, stream) : launch_rows_pipe<FmtQ5K, PAIR>(p, T, device, stream);
+        if (rc != 1) return rc;
+    }
     switch (f) {
         case FMT_Q4K: return launch_rows_fmt<FmtQ4K, PAIR>(p, T, device, stream, true);
         case FMT_Q5K: return launch_rows_fmt<FmtQ5K, PAIR>(p, T, device, stream, false);
@@ -164,7 +200,35 @@ static int launch_reduce_fmt(const ReduceParams& p, int T, int device, cudaStrea
     return KTB200_OK;
 }
 
+// cp.async-pipelined Q6_K (SoA) reduce: returns 1 when the shape does not suit it
+static int launch_reduce_pipe_q6k8(const ReduceParams& p, int T, int device, cudaStream_t stream) {
+    if (!cfg_pipe()) return 1;
+    const int nb = p.ncols / QK_K;
+    if (p.rows % 4 || nb % 2) return 1;
+    const int ns = p.slots + (p.xw ? 1 : 0);
+    const int slot = 840 * nb;     // 4 rows x 210 nb
+    if (slot < 4096) return 1;
+    const int quads = p.rows / 4;
+    int gx = (num_sms(device) + T - 1) / T;
+    if (gx > quads) gx = quads;
+    if (gx < 1) gx = 1;
+    const int nrows_max = ((quads + gx - 1) / gx + 1) * 4;
+    size_t base = (size_t)ns * p.ncols + (size_t)ns * nb * 4 + (size_t)ns * (p.ncols / 16) * 2 + (size_t)nrows_max * ns * 4 + 16;
+    const int warps = 12;
+    const size_t smem = base + (size_t)warps * 2 * slot;
+    if (smem > 220 * 1024) return 1;
+    dim3 grid(gx, T);
+    KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k8_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reduce_pipe_q6k8_kernel<12><<<grid, warps * 32, smem, stream>>>(p, slot);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
 static int launch_reduce(FmtId f, const ReduceParams& p, int T, int device, cudaStream_t stream) {
+    if (f == FMT_Q6K8) {
+        const int rc = launch_reduce_pipe_q6k8(p, T, device, stream);
+        if (rc != 1) return rc;
+    }
     switch (f) {
         case FMT_Q4K: return launch_reduce_fmt<FmtQ4K, 2>(p, T, device, stream, true);
         case FMT_Q5K: return launch_reduce_fmt<FmtQ5K, 1>(p, T, device, stream, false);
