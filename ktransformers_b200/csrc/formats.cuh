@@ -99,6 +99,67 @@ struct FmtQ4K {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Q4_K with 32-byte units (one whole 64-value group per lane: both nibble planes, both sub-blocks), used when
+// the row is staged in shared memory (gemv_pipe.cuh).  4 lanes per block, 8 blocks per step: the 6-bit scale
+// decode, the fp16 conversions and the fp32 scale application are paid once per 64 weights instead of once
+// per 32, which is what the issue-bound gate/up kernel needs (ncu: ~1200 warp instructions per row pair).
+struct FmtQ4K32 {
+    static constexpr int kType = KTB200_TYPE_Q4_K;
+    static constexpr int kBlocksPerStep = 8;
+    static constexpr int kBlockBytes = SZ_Q4_K;
+    struct Lane { int blk, qs_off, act_off, bs_off, sh; bool big; };
+    struct Regs { uint4 hdr, q0, q1; };
+    struct Act { uint4 l0, l1, h0, h1; float dx; int bs_lo, bs_hi; };
+
+    __device__ static __forceinline__ Lane lane(int l) {
+        const int j = l & 3;
+        return Lane{l >> 2, 16 + 32 * j, 64 * j, 4 * j, 16 * (j & 1), j >= 2};
+    }
+    __device__ static __forceinline__ void load_smem(const uint8_t* row, int blk, const Lane& L, Regs& R) {
+        const uint8_t* b = row + blk * SZ_Q4_K;
+        R.hdr = *reinterpret_cast<const uint4*>(b);
+        R.q0 = *reinterpret_cast<const uint4*>(b + L.qs_off);
+        R.q1 = *reinterpret_cast<const uint4*>(b + L.qs_off + 16);
+    }
+    __device__ static __forceinline__ void load_act(const ActQ8K& a, int blk, const Lane& L, Act& A) {
+        const uint8_t* q = a.q8 + blk * QK_K + L.act_off;
+        A.l0 = *reinterpret_cast<const uint4*>(q);
+        A.l1 = *reinterpret_cast<const uint4*>(q + 16);
+        A.h0 = *reinterpret_cast<const uint4*>(q + 32);
+        A.h1 = *reinterpret_cast<const uint4*>(q + 48);
+        A.dx = a.dx[blk];
+        const uint2 w = *reinterpret_cast<const uint2*>(a.bsums + blk * 16 + L.bs_off);   // 4 x int16
+        A.bs_lo = (int)(int16_t)(w.x & 0xffff) + (int)(int16_t)(w.x >> 16);
+        A.bs_hi = (int)(int16_t)(w.y & 0xffff) + (int)(int16_t)(w.y >> 16);
+    }
+    __device__ static __forceinline__ float dot(const Regs& R, const Act& A, const Lane& L) {
+        uint32_t sc, mn;
+        k4_pair(R.hdr.y, R.hdr.z, R.hdr.w, L.sh, L.big, sc, mn);
+        int slo = 0, shi = 0;
+        slo = dp4a_s8s8(R.q0.x & 0x0f0f0f0fu, A.l0.x, slo);
+        slo = dp4a_s8s8(R.q0.y & 0x0f0f0f0fu, A.l0.y, slo);
+        slo = dp4a_s8s8(R.q0.z & 0x0f0f0f0fu, A.l0.z, slo);
+        slo = dp4a_s8s8(R.q0.w & 0x0f0f0f0fu, A.l0.w, slo);
+        slo = dp4a_s8s8(R.q1.x & 0x0f0f0f0fu, A.l1.x, slo);
+        slo = dp4a_s8s8(R.q1.y & 0x0f0f0f0fu, A.l1.y, slo);
+        slo = dp4a_s8s8(R.q1.z & 0x0f0f0f0fu, A.l1.z, slo);
+        slo = dp4a_s8s8(R.q1.w & 0x0f0f0f0fu, A.l1.w, slo);
+        shi = dp4a_u8s8(R.q0.x & 0xf0f0f0f0u, A.h0.x, shi);
+        shi = dp4a_u8s8(R.q0.y & 0xf0f0f0f0u, A.h0.y, shi);
+        shi = dp4a_u8s8(R.q0.z & 0xf0f0f0f0u, A.h0.z, shi);
+        shi = dp4a_u8s8(R.q0.w & 0xf0f0f0f0u, A.h0.w, shi);
+        shi = dp4a_u8s8(R.q1.x & 0xf0f0f0f0u, A.h1.x, shi);
+        shi = dp4a_u8s8(R.q1.y & 0xf0f0f0f0u, A.h1.y, shi);
+        shi = dp4a_u8s8(R.q1.z & 0xf0f0f0f0u, A.h1.z, shi);
+        shi = dp4a_u8s8(R.q1.w & 0xf0f0f0f0u, A.h1.w, shi);
+        const int isum = (int)(sc & 0xff) * slo + (int)(sc >> 8) * (shi >> 4);
+        const int msum = (int)(mn & 0xff) * A.bs_lo + (int)(mn >> 8) * A.bs_hi;
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2*>(&R.hdr.x));
+        return (dm.x * A.dx) * (float)isum - (dm.y * A.dx) * (float)msum;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Q6_K in the 8-row SoA layout produced by repack_q6k (moe.cu).  For a group of 8 consecutive rows,
 // each of nb = ncols/256 blocks:  [ql: 8 x nb x 128][qh: 8 x nb x 64][scales: 8 x nb x 16][d: 8 x nb x 2]
 // (= 8 * nb * 210 bytes, same as raw).  Every ql/qh/scales slice a lane touches is 16-byte aligned.

@@ -9,8 +9,8 @@
 //            expert rows x one column split; each warp streams its row slice with 16-byte loads (8 in flight
 //            per lane) against the token slice staged in shared memory, and writes one partial sum per
 //            (token, expert, split).  Partials are added in fixed split order: deterministic, no float atomics.
-//   phase 2  the LAST CTA to finish (atomic ticket, self-resetting, graph-replay safe) selects: one warp per
-//            token — scoring, bias, group top-2 / max, group top-k, expert top-k by iterative arg-max with
+//   phase 2  the LAST CTA to finish (atomic ticket, self-resetting, graph-replay safe) selects, all 128 threads
+//            per token — scoring, bias, group top-2 / max, group top-k, expert top-k by iterative arg-max with
 //            REDUX max/min (ties -> lowest index), gather, normalise, scale.
 #include "common.cuh"
 
@@ -41,52 +41,72 @@ __device__ __forceinline__ unsigned fkey(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-constexpr int kGateEPL = 16;   // experts per lane held in registers (E <= 512)
+constexpr int kGateEPT = 4;   // experts per thread of the selecting CTA (E <= 512)
 
-__device__ void gate_select_token(const GateParams& p, int t, int lane, float* scores, float* choice) {
-    const int E = p.E;
-    // logits = sum of the S partials (fixed order), lane owns experts e = lane + 32*i
-    float v[kGateEPL];
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Selection for ONE token by the whole CTA (kGateThreads threads).  Shared scratch (floats):
+//   scores[E] | choice[E] | gsc[32] | wbest[2*kGateWarps] | red[2*kGateWarps]
+__device__ void gate_select_token_cta(const GateParams& p, int t, float* sm) {
+    const int E = p.E, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* scores = sm;
+    float* choice = sm + E;
+    float* gsc = choice + E;
+    unsigned* wbest = reinterpret_cast<unsigned*>(gsc + 32);
+    float* red = reinterpret_cast<float*>(wbest + 2 * kGateWarps);
+
+    // logits = sum of the S partials in fixed order; thread owns experts e = tid + 128*i
+    float v[kGateEPT];
 #pragma unroll
-    for (int i = 0; i < kGateEPL; i++) v[i] = 0.f;
+    for (int i = 0; i < kGateEPT; i++) v[i] = 0.f;
     for (int s = 0; s < p.S; s++) {
         const float* pp = p.partial + ((long)t * p.S + s) * E;
 #pragma unroll
-        for (int i = 0; i < kGateEPL; i++) {
-            const int e = lane + 32 * i;
+        for (int i = 0; i < kGateEPT; i++) {
+            const int e = tid + kGateThreads * i;
             if (e < E) v[i] += __ldcg(pp + e);   // written by other SMs in this launch: read at L2
         }
     }
-    float lmax = -INFINITY;
+    if (p.logits_out) {
 #pragma unroll
-    for (int i = 0; i < kGateEPL; i++) {
-        const int e = lane + 32 * i;
-        if (e < E) {
-            if (p.logits_out) p.logits_out[(long)t * E + e] = v[i];
-            lmax = fmaxf(lmax, v[i]);
+        for (int i = 0; i < kGateEPT; i++) {
+            const int e = tid + kGateThreads * i;
+            if (e < E) p.logits_out[(long)t * E + e] = v[i];
         }
     }
     if (p.scoring == 0) {  // sigmoid
 #pragma unroll
-        for (int i = 0; i < kGateEPL; i++) v[i] = __fdiv_rn(1.0f, 1.0f + expf(-v[i]));
-    } else {               // softmax(dim=-1, fp32)
+        for (int i = 0; i < kGateEPT; i++) v[i] = __fdiv_rn(1.0f, 1.0f + expf(-v[i]));
+    } else {               // softmax(dim=-1, fp32): block max, block sum
+        float m = -INFINITY;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        for (int i = 0; i < kGateEPT; i++) if (tid + kGateThreads * i < E) m = fmaxf(m, v[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        m = red[0];
+        for (int w = 1; w < kGateWarps; w++) m = fmaxf(m, red[w]);
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < kGateEPL; i++) {
-            const int e = lane + 32 * i;
-            v[i] = (e < E) ? expf(v[i] - lmax) : 0.f;
+        for (int i = 0; i < kGateEPT; i++) {
+            v[i] = (tid + kGateThreads * i < E) ? expf(v[i] - m) : 0.f;
             sum += v[i];
         }
         sum = warp_sum(sum);
+        if (lane == 0) red[kGateWarps + warp] = sum;
+        __syncthreads();
+        sum = 0.f;
+        for (int w = 0; w < kGateWarps; w++) sum += red[kGateWarps + w];
 #pragma unroll
-        for (int i = 0; i < kGateEPL; i++) v[i] = __fdiv_rn(v[i], sum);
+        for (int i = 0; i < kGateEPT; i++) v[i] = __fdiv_rn(v[i], sum);
     }
-    float c[kGateEPL];   // selection scores
+    float c[kGateEPT];   // selection scores
 #pragma unroll
-    for (int i = 0; i < kGateEPL; i++) {
-        const int e = lane + 32 * i;
+    for (int i = 0; i < kGateEPT; i++) {
+        const int e = tid + kGateThreads * i;
         c[i] = -INFINITY;
         if (e < E) {
             c[i] = v[i] + ((p.topk_method == 0 && p.bias) ? p.bias[e] : 0.f);
@@ -94,88 +114,87 @@ __device__ void gate_select_token(const GateParams& p, int t, int lane, float* s
             choice[e] = c[i];
         }
     }
-    __syncwarp();
+    __syncthreads();
 
     // group selection (noaux_tc: sum of the group's top-2 biased scores; group_limited_greedy: group max)
     if (p.n_group > 1 && p.topk_method != 1) {
         const int gs = E / p.n_group;
-        float gscore = -INFINITY;
-        const bool pow2 = (p.n_group & (p.n_group - 1)) == 0;
-        if (pow2) {
-            // 32/n_group lanes cooperate on one group, then merge their (max1, max2) pairs
-            const int lpg = 32 / p.n_group, g = lane / lpg, sub = lane % lpg;
-            float m1 = -INFINITY, m2 = -INFINITY;
-            for (int i = sub; i < gs; i += lpg) {
+        for (int g = warp; g < p.n_group; g += kGateWarps) {   // one warp per group
+            float a1 = -INFINITY, a2 = -INFINITY;
+            for (int i = lane; i < gs; i += 32) {
                 const float x = choice[g * gs + i];
-                if (x > m1) { m2 = m1; m1 = x; } else if (x > m2) { m2 = x; }
+                if (x > a1) { a2 = a1; a1 = x; } else if (x > a2) { a2 = x; }
             }
-            for (int o = 1; o < lpg; o <<= 1) {
-                const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
-                const float hi = fmaxf(m1, o1), lo = fminf(m1, o1);
-                m2 = fmaxf(lo, fmaxf(m2, o2));
-                m1 = hi;
-            }
-            const float gsc = (p.topk_method == 0) ? (m1 + m2) : m1;
-            gscore = __shfl_sync(0xffffffffu, gsc, (lane % p.n_group) * lpg);   // lane g (< n_group) gets group g's score
-            if (lane >= p.n_group) gscore = -INFINITY;
-        } else if (lane < p.n_group) {
-            float m1 = -INFINITY, m2 = -INFINITY;
-            for (int i = 0; i < gs; i++) {
-                const float x = choice[lane * gs + i];
-                if (x > m1) { m2 = m1; m1 = x; } else if (x > m2) { m2 = x; }
-            }
-            gscore = (p.topk_method == 0) ? (m1 + m2) : m1;
+            const unsigned k1 = fkey(a1);
+            const unsigned mx1 = __reduce_max_sync(0xffffffffu, k1);
+            const int wl = __ffs(__ballot_sync(0xffffffffu, k1 == mx1)) - 1;
+            const unsigned mx2 = __reduce_max_sync(0xffffffffu, lane == wl ? fkey(a2) : k1);
+            if (lane == 0) gsc[g] = (p.topk_method == 0) ? (fkey_inv(mx1) + fkey_inv(mx2)) : fkey_inv(mx1);
         }
-        int rank = 0;  // higher first, ties -> lower index
-        for (int g = 0; g < p.n_group; g++) {
-            const float og = __shfl_sync(0xffffffffu, gscore, g);
-            if (lane < p.n_group && (og > gscore || (og == gscore && g < lane))) rank++;
-        }
-        const unsigned sel = __ballot_sync(0xffffffffu, lane < p.n_group && rank < p.topk_group);
+        __syncthreads();
         const float fill = (p.topk_method == 0) ? -INFINITY : 0.0f;  // V3 masks with -inf, V2 with 0.0
 #pragma unroll
-        for (int i = 0; i < kGateEPL; i++) {
-            const int e = lane + 32 * i;
-            if (e < E && !((sel >> (e / gs)) & 1u)) c[i] = fill;
+        for (int i = 0; i < kGateEPT; i++) {
+            const int e = tid + kGateThreads * i;
+            if (e < E) {
+                const int g = e / gs;
+                const float mine = gsc[g];
+                int rank = 0;  // higher first, ties -> lower index
+                for (int o = 0; o < p.n_group; o++) {
+                    const float og = gsc[o];
+                    rank += (og > mine || (og == mine && o < g)) ? 1 : 0;
+                }
+                if (rank >= p.topk_group) { c[i] = fill; choice[e] = fill; }
+            }
         }
+        __syncthreads();
     }
 
-    // top-k by iterative arg-max over the register-resident scores; ties -> lowest expert index
+    // top-k by iterative arg-max; ties -> lowest expert index
     float wsum = 0.f, myw = 0.f;
     long myidx = 0;
     for (int it = 0; it < p.top_k; it++) {
         unsigned bk = 0;
         int bi = 0x7fffffff;
 #pragma unroll
-        for (int i = 0; i < kGateEPL; i++) {
-            const int e = lane + 32 * i;
+        for (int i = 0; i < kGateEPT; i++) {
+            const int e = tid + kGateThreads * i;
             const unsigned kk = (e < E) ? fkey(c[i]) : 0u;
             if (kk > bk) { bk = kk; bi = e; }
         }
         const unsigned mx = __reduce_max_sync(0xffffffffu, bk);
-        int win = __reduce_min_sync(0xffffffffu, (bk == mx) ? bi : 0x7fffffff);
-        if (win == 0x7fffffff) win = 0;  // degenerate (all NaN)
-        // the winner's owner broadcasts its selection score; V3 gathers the weight from the un-biased scores,
-        // V2 group_limited takes the (masked) score itself
-        float cw = 0.f;
+        const int wi = __reduce_min_sync(0xffffffffu, (bk == mx) ? bi : 0x7fffffff);
+        if (lane == 0) { wbest[2 * warp] = mx; wbest[2 * warp + 1] = (unsigned)wi; }
+        __syncthreads();
+        unsigned gk = wbest[0];
+        int win = (int)wbest[1];
 #pragma unroll
-        for (int i = 0; i < kGateEPL; i++)
-            if (lane + 32 * i == win) { cw = c[i]; c[i] = -INFINITY; }
-        cw = __shfl_sync(0xffffffffu, cw, win & 31);
-        const float wv = (p.topk_method == 2) ? cw : scores[win];
-        if (lane == it) { myw = wv; myidx = win; }
+        for (int w = 1; w < kGateWarps; w++) {
+            const unsigned kk = wbest[2 * w];
+            const int ii = (int)wbest[2 * w + 1];
+            if (kk > gk || (kk == gk && ii < win)) { gk = kk; win = ii; }
+        }
+        if (win == 0x7fffffff || win < 0 || win >= E) win = 0;  // degenerate (all NaN)
+        // V3 gathers the weight from the un-biased scores; V2 group_limited takes the (masked) score itself
+        const float wv = (p.topk_method == 2) ? choice[win] : scores[win];
+#pragma unroll
+        for (int i = 0; i < kGateEPT; i++)
+            if (tid + kGateThreads * i == win) c[i] = -INFINITY;
+        if (tid == it) { myw = wv; myidx = win; }
         wsum += wv;
+        __syncthreads();   // wbest is rewritten in the next iteration
     }
     // V3 (modeling_deepseek_v3.py:474-479): normalise (if top_k>1 && norm_topk_prob) THEN always scale;
     // V2 (modeling_deepseek.py:455-459): normalise XOR scale.
-    if (lane < p.top_k) {
+    if (tid < p.top_k) {
         float w = myw;
         const bool do_norm = p.top_k > 1 && p.norm_topk_prob;
         if (do_norm) w = __fdiv_rn(w, wsum + 1e-20f);
         if (p.topk_method == 0 || !do_norm) w = w * p.routed_scaling_factor;
-        p.idx[(long)t * p.top_k + lane] = myidx;
-        p.w[(long)t * p.top_k + lane] = w;
+        p.idx[(long)t * p.top_k + tid] = myidx;
+        p.w[(long)t * p.top_k + tid] = w;
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) {
@@ -249,8 +268,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    float* sc = xs;                 // per warp: scores[E] | choice[E]
-    for (int t = warp; t < Teff; t += kGateWarps) gate_select_token(p, t, lane, sc + (size_t)warp * 2 * p.E, sc + (size_t)warp * 2 * p.E + p.E);
+    for (int t = 0; t < Teff; t++) gate_select_token_cta(p, t, xs);
 }
 
 // per-device scratch: partial sums + ticket
@@ -265,7 +283,7 @@ extern "C" int ktb200_moe_gate_forward(const ktb200_gate_config* c, int qlen, co
     using namespace ktb;
     if (!c || !x || !idx || !w) { set_error("null pointer"); return KTB200_EINVAL; }
     if (qlen <= 0) return KTB200_OK;
-    if (c->n_experts > 32 * kGateEPL) { set_error("gate: at most %d experts", 32 * kGateEPL); return KTB200_EINVAL; }
+    if (c->n_experts > kGateThreads * kGateEPT) { set_error("gate: at most %d experts", kGateThreads * kGateEPT); return KTB200_EINVAL; }
     if (c->n_experts <= 0 || c->hidden_size <= 0 || c->hidden_size % 4 || c->top_k <= 0 || c->top_k > 32 || c->top_k > c->n_experts) {
         set_error("gate: bad shape (E=%d H=%d top_k=%d; top_k<=32, H%%4==0)", c->n_experts, c->hidden_size, c->top_k);
         return KTB200_EINVAL;
@@ -303,7 +321,7 @@ extern "C" int ktb200_moe_gate_forward(const ktb200_gate_config* c, int qlen, co
     const int nc4_max = c->hidden_size / 4 / S + 1;
     const int nt = qlen < kGateTokTile ? qlen : kGateTokTile;
     size_t smem = (size_t)nt * nc4_max * 16;
-    const size_t smem_sel = (size_t)kGateWarps * 2 * c->n_experts * sizeof(float);
+    const size_t smem_sel = ((size_t)2 * c->n_experts + 32 + 4 * kGateWarps) * sizeof(float);
     if (smem_sel > smem) smem = smem_sel;
     if (smem > 48 * 1024) KTB_CUDA_CHECK(cudaFuncSetAttribute(gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gate_kernel<<<dim3(row_ctas, S), kGateThreads, smem, s>>>(p);

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rows_pipe_kernel(const RowsPara
     constexpr int NM = PAIR ? 2 : 1;
     uint8_t* q8 = smem;
     float* dx = reinterpret_cast<float*>(smem + p.ncols);
-    int16_t* bsums = reinterpret_cast<int16_t*>(smem + p.ncols + nblk * 4);
+    int16_t* bsums = reinterpret_cast<int16_t*>(smem + p.ncols + ((nblk * 4 + 15) & ~15));   // 16-byte aligned
     uint8_t* ring = smem + act_bytes + (size_t)warp * 2 * slot_bytes;
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
     const ActQ8K act{q8, dx, bsums};

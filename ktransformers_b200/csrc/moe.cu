@@ -129,7 +129,7 @@ static int launch_rows_pipe(const RowsParams& p, int T, int device, cudaStream_t
     const int nblk = p.ncols / QK_K;
     const int row_bytes = nblk * Fmt::kBlockBytes;
     const int slot = row_bytes * (PAIR ? 2 : 1);
-    const int act = (p.ncols + nblk * 4 + p.ncols / 8 + 15) & ~15;
+    const int act = (p.ncols + ((nblk * 4 + 15) & ~15) + p.ncols / 8 + 15) & ~15;
     if (slot < 4096) return 1;                          // short rows: the register-staged kernel batches better
     int warps = 0;
     for (int w : {12, 8}) if ((size_t)act + (size_t)w * 2 * slot <= 220 * 1024) { warps = w; break; }
@@ -155,7 +155,7 @@ static int launch_rows_pipe(const RowsParams& p, int T, int device, cudaStream_t
 template <bool PAIR>
 static int launch_rows(FmtId f, const RowsParams& p, int T, int device, cudaStream_t stream) {
     if (f == FMT_Q4K || f == FMT_Q5K) {
-        const int rc = (f == FMT_Q4K) ? launch_rows_pipe<FmtQ4K, PAIR>(p, T, device, stream) : launch_rows_pipe<FmtQ5K, PAIR>(p, T, device, stream);
+        const int rc = (f == FMT_Q4K) ? launch_rows_pipe<FmtQ4K32, PAIR>(p, T, device, stream) : launch_rows_pipe<FmtQ5K, PAIR>(p, T, device, stream);
         if (rc != 1) return rc;
     }
     switch (f) {
