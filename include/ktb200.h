@@ -222,6 +222,12 @@ int ktb200_mla_decode(const ktb200_mla_params* p, void* stream);
 int ktb200_mla_kv_write(void* kv_cache, int page_size, const void* ckv, const void* k_pe, const int* page_idx,
                         const int* page_offset, int n_tokens, void* stream);
 
+/* Diagnostics (bench.py --probe): time a plain read-only stream over `bytes` of device memory.
+ * mode 0 = grid-stride coalesced 16-byte loads; mode 1 = every warp reads chunk_bytes pieces at hashed offsets
+ * (the access shape of the expert GEMV).  Establishes the practical read ceiling next to MEASURED_PEAKS' copy figure. */
+int ktb200_debug_stream_read(const void* src_dev, long bytes, int mode, int unroll, int ctas_per_sm, int chunk_bytes,
+                             void* stream, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,3 +38,68 @@ long ktb200_type_size(int t) { return ktb::type_size(t); }
 long ktb200_blck_size(int t) { return ktb::blck_size(t); }
 unsigned long long ktb200_launch_count(void) { return ktb::g_launches.load(); }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Diagnostics: what does a plain read-only stream achieve on this part?  (bench.py --probe; profiles/)
+//   mode 0: grid-stride coalesced 16-byte loads, U loads in flight per thread
+//   mode 1: every warp reads `chunk`-byte pieces at pseudo-random (hashed) offsets — the access shape of the
+//           expert GEMV (one 4 KB weight row per warp at a time)
+namespace ktb {
+template <int U>
+__global__ void __launch_bounds__(256) stream_read_kernel(const uint4* __restrict__ src, long n16, int mode, int chunk16,
+                                                          unsigned* sink) {
+    unsigned acc = 0;
+    if (mode == 0) {
+        const long stride = (long)gridDim.x * blockDim.x;
+        long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + (U - 1) * stride < n16; i += U * stride) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = ldg_stream16(src + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < U; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        const long nwarps = (long)gridDim.x * (blockDim.x >> 5), w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const long nchunks = n16 / chunk16;
+        for (long c = w; c < nchunks; c += nwarps) {
+            const long pc = (c * 2654435761L) % nchunks;   // scatter the chunks
+            const uint4* p = src + pc * chunk16;
+            for (int i = lane; i < chunk16; i += 32 * U) {
+                uint4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) if (i + 32 * u < chunk16) v[u] = ldg_stream16(p + i + 32 * u); else v[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < U; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+            }
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;   // never true in practice: keeps the loads alive
+}
+}  // namespace ktb
+
+extern "C" int ktb200_debug_stream_read(const void* src, long bytes, int mode, int unroll, int ctas_per_sm, int chunk_bytes,
+                                        void* stream, float* ms_out) {
+    using namespace ktb;
+    int dev = 0;
+    KTB_CUDA_CHECK(cudaGetDevice(&dev));
+    static unsigned* sink = nullptr;
+    if (!sink) KTB_CUDA_CHECK(cudaMalloc(&sink, 4));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    KTB_CUDA_CHECK(cudaEventCreate(&e0));
+    KTB_CUDA_CHECK(cudaEventCreate(&e1));
+    const int grid = num_sms(dev) * (ctas_per_sm > 0 ? ctas_per_sm : 2);
+    const long n16 = bytes / 16;
+    KTB_CUDA_CHECK(cudaEventRecord(e0, s));
+    if (unroll >= 8) stream_read_kernel<8><<<grid, 256, 0, s>>>((const uint4*)src, n16, mode, chunk_bytes / 16, sink);
+    else if (unroll >= 4) stream_read_kernel<4><<<grid, 256, 0, s>>>((const uint4*)src, n16, mode, chunk_bytes / 16, sink);
+    else stream_read_kernel<2><<<grid, 256, 0, s>>>((const uint4*)src, n16, mode, chunk_bytes / 16, sink);
+    KTB_LAUNCH_CHECK();
+    KTB_CUDA_CHECK(cudaEventRecord(e1, s));
+    KTB_CUDA_CHECK(cudaEventSynchronize(e1));
+    if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return KTB200_OK;
+}
