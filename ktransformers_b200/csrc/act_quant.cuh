@@ -21,7 +21,7 @@ namespace ktb {
 //   * an all-zero block gives d = 0, q = 0 (bsums forced to 0; the reference leaves them stale but
 //     they are only ever multiplied by d == 0).
 __device__ __forceinline__ void warp_quantize_q8k_block(const float (&x)[8], int lane, uint32_t* q8_out,
-                                                        float* d_out, int16_t* bsums_out) {
+                                                        float* d_out, int16_t* bsums_out, int16_t* bs32_out = nullptr) {
     // local first-max scan
     float amax = 0.f, mx = 0.f;
     int midx = 0;
@@ -61,7 +61,11 @@ __device__ __forceinline__ void warp_quantize_q8k_block(const float (&x)[8], int
     q8_out[2 * lane] = w0;
     q8_out[2 * lane + 1] = w1;
     int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);
-    if ((lane & 1) == 0) bsums_out[lane >> 1] = (int16_t)s2;
+    if (bsums_out && (lane & 1) == 0) bsums_out[lane >> 1] = (int16_t)s2;
+    if (bs32_out) {   // sums of 32 consecutive q8 (one Q4_K/Q5_K sub-block each), |sum| <= 4064
+        const int s4 = s2 + __shfl_xor_sync(0xffffffffu, s2, 2);
+        if ((lane & 3) == 0) bs32_out[lane >> 2] = (int16_t)s4;
+    }
     if (lane == 0) *d_out = d;
 }
 

@@ -242,3 +242,166 @@ __global__ void __launch_bounds__(WARPS * 32, 1) reduce_pipe_q6k8_kernel(const R
 }
 
 }  // namespace ktb
+
+namespace ktb {
+
+// Q4_K gate/up, third generation: rows staged in shared memory (same warp-private cp.async ring as rows_pipe_kernel)
+// and consumed with ONE LANE PER SUPER-BLOCK.  A lane decodes its block's eight 6-bit (scale, min) pairs once
+// (the ggml kmask trick, ggml-quants.c:7494-7499), runs the 64 dp4a of the block against the int8 activations,
+// applies the sub-block scales as integers, folds the mins with 4 dp2a against pre-summed activations and touches
+// fp32 once per block — the same granularity as the reference's scalar loop (one `d * sumi` per block) and ~2.5x
+// fewer instructions than one lane per 16-byte chunk.  Bank-conflict-free by construction: weight blocks are 144 B
+// (36 words) apart, activation blocks are padded to 272 B (68 words), so 8 lanes x LDS.128 hit 32 distinct banks.
+constexpr int kActBlkStride = QK_K + 16;   // padded int8 activation block
+
+template <bool PAIR, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) rows_pipe_q4k_blk_kernel(const RowsParams p, int act_bytes, int slot_bytes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int t = blockIdx.y;
+    if (p.bsz && t >= *p.bsz) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nblk = p.ncols / QK_K;
+    const int row_bytes = nblk * SZ_Q4_K;
+    constexpr int NM = PAIR ? 2 : 1;
+    // activation staging: q8 [nblk][272] | bs32 [nblk][8] int16 | dx [nblk] float
+    uint8_t* q8 = smem;
+    int16_t* bs32 = reinterpret_cast<int16_t*>(smem + (size_t)nblk * kActBlkStride);
+    float* dx = reinterpret_cast<float*>(smem + (size_t)nblk * kActBlkStride + (size_t)nblk * 16);
+    uint8_t* ring = smem + act_bytes + (size_t)warp * 2 * slot_bytes;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+
+    const int nslots = p.slots + (p.x0 ? 1 : 0);
+    const int total = nslots * p.rows;
+    const int u0 = (int)((long)total * blockIdx.x / gridDim.x), u1 = (int)((long)total * (blockIdx.x + 1) / gridDim.x);
+
+    auto unit_rows = [&](int u, const uint8_t* (&r)[NM]) -> bool {
+        if (u >= u1) return false;
+        const int s = u / p.rows, rr = u - s * p.rows;
+        if (s == p.slots) {
+            r[0] = reinterpret_cast<const uint8_t*>(p.x0) + (long)rr * row_bytes;
+            if (PAIR) r[NM - 1] = reinterpret_cast<const uint8_t*>(p.x1) + (long)rr * row_bytes;
+            return true;
+        }
+        const long e = p.ids ? (long)p.ids[(long)t * p.slots + s] - p.id_offset : 0;
+        if (e < 0 || e >= p.n_experts) return false;
+        r[0] = reinterpret_cast<const uint8_t*>(p.w0) + (e * p.rows + rr) * row_bytes;
+        if (PAIR) r[NM - 1] = reinterpret_cast<const uint8_t*>(p.w1) + (e * p.rows + rr) * row_bytes;
+        return true;
+    };
+    auto issue = [&](int u, int slot) -> bool {
+        const uint8_t* r[NM];
+        const bool ok = unit_rows(u, r);
+        if (ok) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const uint32_t dst = ring_u32 + slot * slot_bytes + m * row_bytes;
+                for (int c = lane * 16; c < row_bytes; c += 32 * 16) cp_async16_cg(dst + c, r[m] + c);
+            }
+        }
+        cp_async_commit_group();
+        return ok;
+    };
+
+    int u = u0 + warp;
+    bool cur_ok = issue(u, 0);
+    {   // quantise the token's activation row into the padded layout (one warp per block, 4 blocks in flight)
+        const int nwarps = WARPS;
+        for (int g0 = warp; g0 < nblk; g0 += nwarps * 4) {
+            float x[4][8];
+            bool live[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int b = g0 + i * nwarps;
+                live[i] = b < nblk;
+                if (live[i]) load_block8(p.x, (long)t * p.ncols + (long)b * QK_K + lane * 8, p.hidden_type, x[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int b = g0 + i * nwarps;
+                if (live[i]) warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(q8 + (size_t)b * kActBlkStride), dx + b, nullptr, bs32 + b * 8);
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int it = 0; u < u1; u += WARPS, it++) {
+        const int slot = it & 1;
+        const bool next_ok = issue(u + WARPS, slot ^ 1);
+        cp_async_wait_group<1>();
+        __syncwarp();
+        float acc[NM];
+#pragma unroll
+        for (int m = 0; m < NM; m++) acc[m] = 0.f;
+        if (cur_ok) {
+            const uint8_t* row0 = ring + slot * slot_bytes;
+            for (int blk = lane; blk < nblk; blk += 32) {
+                const uint8_t* aq = q8 + (size_t)blk * kActBlkStride;
+                const uint4 bsv = *reinterpret_cast<const uint4*>(bs32 + blk * 8);
+                const float dxb = dx[blk];
+                uint32_t scl[NM], sch[NM], mnl[NM], mnh[NM];
+                float2 dm[NM];
+                int isum[NM];
+#pragma unroll
+                for (int m = 0; m < NM; m++) {
+                    const uint4 hdr = *reinterpret_cast<const uint4*>(row0 + m * row_bytes + blk * SZ_Q4_K);
+                    dm[m] = __half22float2(*reinterpret_cast<const __half2*>(&hdr.x));
+                    scl[m] = hdr.y & 0x3f3f3f3fu;                                             // scales 0..3
+                    mnl[m] = hdr.z & 0x3f3f3f3fu;                                             // mins   0..3
+                    sch[m] = (hdr.w & 0x0f0f0f0fu) | ((hdr.y >> 2) & 0x30303030u);            // scales 4..7
+                    mnh[m] = ((hdr.w >> 4) & 0x0f0f0f0fu) | ((hdr.z >> 2) & 0x30303030u);     // mins   4..7
+                    isum[m] = 0;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint4 a0 = *reinterpret_cast<const uint4*>(aq + 64 * g);
+                    const uint4 a1 = *reinterpret_cast<const uint4*>(aq + 64 * g + 16);
+                    const uint4 a2 = *reinterpret_cast<const uint4*>(aq + 64 * g + 32);
+                    const uint4 a3 = *reinterpret_cast<const uint4*>(aq + 64 * g + 48);
+#pragma unroll
+                    for (int m = 0; m < NM; m++) {
+                        const uint8_t* qs = row0 + m * row_bytes + blk * SZ_Q4_K + 16 + 32 * g;
+                        const uint4 q0 = *reinterpret_cast<const uint4*>(qs);
+                        const uint4 q1 = *reinterpret_cast<const uint4*>(qs + 16);
+                        int slo = 0, shi = 0;
+                        slo = dp4a_s8s8(q0.x & 0x0f0f0f0fu, a0.x, slo); slo = dp4a_s8s8(q0.y & 0x0f0f0f0fu, a0.y, slo);
+                        slo = dp4a_s8s8(q0.z & 0x0f0f0f0fu, a0.z, slo); slo = dp4a_s8s8(q0.w & 0x0f0f0f0fu, a0.w, slo);
+                        slo = dp4a_s8s8(q1.x & 0x0f0f0f0fu, a1.x, slo); slo = dp4a_s8s8(q1.y & 0x0f0f0f0fu, a1.y, slo);
+                        slo = dp4a_s8s8(q1.z & 0x0f0f0f0fu, a1.z, slo); slo = dp4a_s8s8(q1.w & 0x0f0f0f0fu, a1.w, slo);
+                        shi = dp4a_u8s8(q0.x & 0xf0f0f0f0u, a2.x, shi); shi = dp4a_u8s8(q0.y & 0xf0f0f0f0u, a2.y, shi);
+                        shi = dp4a_u8s8(q0.z & 0xf0f0f0f0u, a2.z, shi); shi = dp4a_u8s8(q0.w & 0xf0f0f0f0u, a2.w, shi);
+                        shi = dp4a_u8s8(q1.x & 0xf0f0f0f0u, a3.x, shi); shi = dp4a_u8s8(q1.y & 0xf0f0f0f0u, a3.y, shi);
+                        shi = dp4a_u8s8(q1.z & 0xf0f0f0f0u, a3.z, shi); shi = dp4a_u8s8(q1.w & 0xf0f0f0f0u, a3.w, shi);
+                        const uint32_t scw = (g < 2) ? scl[m] : sch[m];
+                        const int sc0 = (int)((scw >> (16 * (g & 1))) & 0xff), sc1 = (int)((scw >> (16 * (g & 1) + 8)) & 0xff);
+                        isum[m] += sc0 * slo + sc1 * (shi >> 4);
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < NM; m++) {
+                    int msum = __dp2a_lo((int)bsv.x, (int)mnl[m], 0);
+                    msum = __dp2a_hi((int)bsv.y, (int)mnl[m], msum);
+                    msum = __dp2a_lo((int)bsv.z, (int)mnh[m], msum);
+                    msum = __dp2a_hi((int)bsv.w, (int)mnh[m], msum);
+                    acc[m] += (dm[m].x * dxb) * (float)isum[m] - (dm[m].y * dxb) * (float)msum;
+                }
+            }
+        }
+        float g = warp_sum(acc[0]);
+        const float uu = PAIR ? warp_sum(acc[NM - 1]) : 0.f;
+        if (lane == 0) {
+            if (PAIR) {
+                p.out_f32[(long)t * total + u] = cur_ok ? (p.use_silu ? act_silu(g) : act_relu(g)) * uu : 0.f;
+            } else {
+                if (!cur_ok) g = 0.f;
+                if (p.bias) g += p.bias[u % p.rows];
+                if (p.out_f32) p.out_f32[(long)t * total + u] = g;
+                if (p.out_hidden) store_hidden(p.out_hidden, (long)t * total + u, p.hidden_type, g);
+            }
+        }
+        __syncwarp();
+        cur_ok = next_ok;
+    }
+    cp_async_wait_group<0>();
+}
+
+}  // namespace ktb

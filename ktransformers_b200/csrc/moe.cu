@@ -89,7 +89,7 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 static int cfg_minb() { static int v = env_int("KTB200_MINB", 2); return v == 3 ? 3 : 2; }
-static int cfg_pipe() { static int v = env_int("KTB200_PIPE", 1); return v; }
+static int cfg_pipe() { static int v = env_int("KTB200_PIPE", 2); return v; }   // 0 off, 1 chunk-per-lane, 2 block-per-lane
 static int cfg_nb() { static int v = env_int("KTB200_NB", 2); return v == 4 ? 4 : 2; }
 
 template <class Fmt, bool PAIR>
@@ -152,8 +152,42 @@ static int launch_rows_pipe(const RowsParams& p, int T, int device, cudaStream_t
     return KTB200_OK;
 }
 
+// Q4_K, one lane per super-block (rows_pipe_q4k_blk_kernel).  Returns 1 when the shape does not suit it.
+template <bool PAIR>
+static int launch_rows_pipe_q4k_blk(const RowsParams& p, int T, int device, cudaStream_t stream) {
+    if (cfg_pipe() < 2) return 1;
+    const int nblk = p.ncols / QK_K;
+    const int row_bytes = nblk * SZ_Q4_K;
+    const int slot = row_bytes * (PAIR ? 2 : 1);
+    const int act = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
+    if (slot < 4096 || nblk < 16) return 1;             // needs >= 16 blocks per row to keep most lanes busy
+    int warps = 0;
+    for (int w : {12, 8}) if ((size_t)act + (size_t)w * 2 * slot <= 220 * 1024) { warps = w; break; }
+    if (!warps) return 1;
+    const size_t smem = (size_t)act + (size_t)warps * 2 * slot;
+    const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
+    if (total >= (1L << 30)) return 1;
+    int gx = (num_sms(device) + T - 1) / T;
+    if (gx > total) gx = (int)total;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, T);
+    if (warps == 12) {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_q4k_blk_kernel<PAIR, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_pipe_q4k_blk_kernel<PAIR, 12><<<grid, 12 * 32, smem, stream>>>(p, act, slot);
+    } else {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_q4k_blk_kernel<PAIR, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_pipe_q4k_blk_kernel<PAIR, 8><<<grid, 8 * 32, smem, stream>>>(p, act, slot);
+    }
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
 template <bool PAIR>
 static int launch_rows(FmtId f, const RowsParams& p, int T, int device, cudaStream_t stream) {
+    if (f == FMT_Q4K) {
+        const int rc = launch_rows_pipe_q4k_blk<PAIR>(p, T, device, stream);
+        if (rc != 1) return rc;
+    }
     if (f == FMT_Q4K || f == FMT_Q5K) {
         const int rc = (f == FMT_Q4K) ? launch_rows_pipe<FmtQ4K32, PAIR>(p, T, device, stream) : launch_rows_pipe<FmtQ5K, PAIR>(p, T, device, stream);
         if (rc != 1) return rc;
