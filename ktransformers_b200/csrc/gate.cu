@@ -197,6 +197,41 @@ __device__ void gate_select_token_cta(const GateParams& p, int t, float* sm) {
     __syncthreads();
 }
 
+template <int NT>
+__device__ __forceinline__ void gate_dot(const GateParams& p, const float4* wrow, const float* xs, int nc4, int lane, int t0, int e,
+                                         int s, int S, int nt = NT) {
+    float acc[NT];
+#pragma unroll
+    for (int i = 0; i < NT; i++) acc[i] = 0.f;
+    for (int cb = lane; cb < nc4; cb += 32 * 8) {
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int c = cb + 32 * u;
+            if (c < nc4) w[u] = __ldg(wrow + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int c = cb + 32 * u;
+            if (c < nc4) {
+#pragma unroll
+                for (int i = 0; i < NT; i++) {
+                    const float4 xv = reinterpret_cast<const float4*>(xs + (size_t)(i < nt ? i : 0) * nc4 * 4)[c];
+                    acc[i] = fmaf(w[u].x, xv.x, acc[i]);
+                    acc[i] = fmaf(w[u].y, xv.y, acc[i]);
+                    acc[i] = fmaf(w[u].z, xv.z, acc[i]);
+                    acc[i] = fmaf(w[u].w, xv.w, acc[i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+        const float v = warp_sum(acc[i]);
+        if (i < nt && lane == 0) p.partial[((long)(t0 + i) * S + s) * p.E + e] = v;
+    }
+}
+
 __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);   // [tok tile][slice cols]  (phase 1) / scores+choice (phase 2)
@@ -218,39 +253,11 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
                 xs[tt * nc4 * 4 + c] = load_hidden(p.x, (long)(t0 + tt) * p.H + 4L * c0 + c, p.hidden_type);
         __syncthreads();
         if (e < p.E) {
-            float acc[kGateTokTile];
-#pragma unroll
-            for (int i = 0; i < kGateTokTile; i++) acc[i] = 0.f;
-            for (int cb = lane; cb < nc4; cb += 32 * 8) {
-                float4 w[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int c = cb + 32 * u;
-                    if (c < nc4) w[u] = __ldg(wrow + c);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int c = cb + 32 * u;
-                    if (c < nc4) {
-#pragma unroll
-                        for (int i = 0; i < kGateTokTile; i++) {
-                            if (i < nt) {
-                                const float4 xv = reinterpret_cast<const float4*>(xs + (size_t)i * nc4 * 4)[c];
-                                acc[i] = fmaf(w[u].x, xv.x, acc[i]);
-                                acc[i] = fmaf(w[u].y, xv.y, acc[i]);
-                                acc[i] = fmaf(w[u].z, xv.z, acc[i]);
-                                acc[i] = fmaf(w[u].w, xv.w, acc[i]);
-                            }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kGateTokTile; i++) {
-                if (i < nt) {
-                    const float v = warp_sum(acc[i]);
-                    if (lane == 0) p.partial[((long)(t0 + i) * S + s) * p.E + e] = v;
-                }
+            switch (nt) {   // compile-time token counts: no predicated-off FMAs for the common bs=1 decode
+                case 1: gate_dot<1>(p, wrow, xs, nc4, lane, t0, e, s, S); break;
+                case 2: gate_dot<2>(p, wrow, xs, nc4, lane, t0, e, s, S); break;
+                case 3: case 4: gate_dot<4>(p, wrow, xs, nc4, lane, t0, e, s, S, nt); break;
+                default: gate_dot<kGateTokTile>(p, wrow, xs, nc4, lane, t0, e, s, S, nt); break;
             }
         }
     }

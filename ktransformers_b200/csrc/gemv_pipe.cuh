@@ -124,7 +124,7 @@ namespace ktb {
 // in the SoA layout the item is four contiguous pieces (ql 4x128nb | qh 4x64nb | scales 4x16nb | d 4x2nb),
 // streamed into a warp-private 2-slot ring with cp.async while the previous item is reduced from shared memory.
 // CTA row ranges are multiples of 4 rows; requires rows % 4 == 0 and nb even.
-template <int WARPS>
+template <int WARPS, int SLOTS>
 __global__ void __launch_bounds__(WARPS * 32, 1) reduce_pipe_q6k8_kernel(const ReduceParams p, int slot_bytes) {
     using Fmt = FmtQ6K8;
     constexpr int RW = 4;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) reduce_pipe_q6k8_kernel(const R
     const int nquads = q1 - q0;
     size_t off = (size_t)ns * p.ncols + (size_t)ns * nb * 4 + (size_t)ns * (p.ncols / 16) * 2 + (size_t)(nrows > 0 ? nrows : 1) * ns * 4;
     off = (off + 15) & ~(size_t)15;
-    uint8_t* ring = smem + off + (size_t)warp * 2 * slot_bytes;
+    uint8_t* ring = smem + off + (size_t)warp * SLOTS * slot_bytes;
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
 
     unsigned skip = 0;
@@ -192,9 +192,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) reduce_pipe_q6k8_kernel(const R
     const Fmt::Lane L = Fmt::lane(lane);
     const int nsteps = (nb + Fmt::kBlocksPerStep - 1) / Fmt::kBlocksPerStep;
     for (int it = 0; item < total; item += WARPS, it++) {
-        const int slot = it & 1;
-        const bool next_ok = issue(item + WARPS, slot ^ 1);
-        cp_async_wait_group<1>();
+        const int slot = (SLOTS == 2) ? (it & 1) : 0;
+        bool next_ok = false;
+        if (SLOTS == 2) {
+            next_ok = issue(item + WARPS, slot ^ 1);
+            cp_async_wait_group<1>();
+        } else {
+            cp_async_wait_group<0>();
+        }
         __syncwarp();
         const int j = item / nquads, quad = item - j * nquads;
         float res = 0.f;
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) reduce_pipe_q6k8_kernel(const R
         }
         if ((lane & 7) == 0) partial[(quad * RW + (lane >> 3)) * ns + j] = res;
         __syncwarp();
-        cur_ok = next_ok;
+        if (SLOTS == 2) cur_ok = next_ok;
+        else cur_ok = issue(item + WARPS, 0);
     }
     cp_async_wait_group<0>();
     __syncthreads();
@@ -254,7 +260,9 @@ namespace ktb {
 // (36 words) apart, activation blocks are padded to 272 B (68 words), so 8 lanes x LDS.128 hit 32 distinct banks.
 constexpr int kActBlkStride = QK_K + 16;   // padded int8 activation block
 
-template <bool PAIR, int WARPS>
+// SLOTS = 2: every warp prefetches its next unit while it computes (12 warps fit); SLOTS = 1: no intra-warp overlap
+// but twice the warps (24) — more eligible warps per scheduler, the in-flight bytes come from the warps that wait.
+template <bool PAIR, int WARPS, int SLOTS>
 __global__ void __launch_bounds__(WARPS * 32, 1) rows_pipe_q4k_blk_kernel(const RowsParams p, int act_bytes, int slot_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int t = blockIdx.y;
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rows_pipe_q4k_blk_kernel(const 
     uint8_t* q8 = smem;
     int16_t* bs32 = reinterpret_cast<int16_t*>(smem + (size_t)nblk * kActBlkStride);
     float* dx = reinterpret_cast<float*>(smem + (size_t)nblk * kActBlkStride + (size_t)nblk * 16);
-    uint8_t* ring = smem + act_bytes + (size_t)warp * 2 * slot_bytes;
+    uint8_t* ring = smem + act_bytes + (size_t)warp * SLOTS * slot_bytes;
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
 
     const int nslots = p.slots + (p.x0 ? 1 : 0);
@@ -325,9 +333,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rows_pipe_q4k_blk_kernel(const 
     __syncthreads();
 
     for (int it = 0; u < u1; u += WARPS, it++) {
-        const int slot = it & 1;
-        const bool next_ok = issue(u + WARPS, slot ^ 1);
-        cp_async_wait_group<1>();
+        const int slot = (SLOTS == 2) ? (it & 1) : 0;
+        bool next_ok = false;
+        if (SLOTS == 2) {
+            next_ok = issue(u + WARPS, slot ^ 1);
+            cp_async_wait_group<1>();
+        } else {
+            cp_async_wait_group<0>();
+        }
         __syncwarp();
         float acc[NM];
 #pragma unroll
@@ -399,7 +412,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rows_pipe_q4k_blk_kernel(const 
             }
         }
         __syncwarp();
-        cur_ok = next_ok;
+        if (SLOTS == 2) cur_ok = next_ok;
+        else cur_ok = issue(u + WARPS, 0);   // refill the single slot for the next round
     }
     cp_async_wait_group<0>();
 }

@@ -161,23 +161,27 @@ static int launch_rows_pipe_q4k_blk(const RowsParams& p, int T, int device, cuda
     const int slot = row_bytes * (PAIR ? 2 : 1);
     const int act = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
     if (slot < 4096 || nblk < 16) return 1;             // needs >= 16 blocks per row to keep most lanes busy
-    int warps = 0;
-    for (int w : {12, 8}) if ((size_t)act + (size_t)w * 2 * slot <= 220 * 1024) { warps = w; break; }
-    if (!warps) return 1;
-    const size_t smem = (size_t)act + (size_t)warps * 2 * slot;
+    // (warps, slots): 24 x 1 by default (more eligible warps per scheduler), 12 x 2 with KTB200_PIPE_SLOTS=2
+    static const int want_slots = env_int("KTB200_PIPE_SLOTS", 1);
     const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
     if (total >= (1L << 30)) return 1;
     int gx = (num_sms(device) + T - 1) / T;
     if (gx > total) gx = (int)total;
     if (gx < 1) gx = 1;
     dim3 grid(gx, T);
-    if (warps == 12) {
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_q4k_blk_kernel<PAIR, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rows_pipe_q4k_blk_kernel<PAIR, 12><<<grid, 12 * 32, smem, stream>>>(p, act, slot);
-    } else {
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_q4k_blk_kernel<PAIR, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rows_pipe_q4k_blk_kernel<PAIR, 8><<<grid, 8 * 32, smem, stream>>>(p, act, slot);
-    }
+#define KTB_BLK(W, S)                                                                                                  \
+    do {                                                                                                               \
+        const size_t smem = (size_t)act + (size_t)(W) * (S) * slot;                                                    \
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_q4k_blk_kernel<PAIR, W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rows_pipe_q4k_blk_kernel<PAIR, W, S><<<grid, (W) * 32, smem, stream>>>(p, act, slot);                        \
+    } while (0)
+    const size_t cap = 220 * 1024;
+    if (want_slots != 2 && (size_t)act + (size_t)24 * slot <= cap) KTB_BLK(24, 1);
+    else if ((size_t)act + (size_t)12 * 2 * slot <= cap) KTB_BLK(12, 2);
+    else if ((size_t)act + (size_t)16 * slot <= cap) KTB_BLK(16, 1);
+    else if ((size_t)act + (size_t)8 * 2 * slot <= cap) KTB_BLK(8, 2);
+    else return 1;
+#undef KTB_BLK
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
 }
@@ -248,12 +252,19 @@ static int launch_reduce_pipe_q6k8(const ReduceParams& p, int T, int device, cud
     if (gx < 1) gx = 1;
     const int nrows_max = ((quads + gx - 1) / gx + 1) * 4;
     size_t base = (size_t)ns * p.ncols + (size_t)ns * nb * 4 + (size_t)ns * (p.ncols / 16) * 2 + (size_t)nrows_max * ns * 4 + 16;
-    const int warps = 12;
-    const size_t smem = base + (size_t)warps * 2 * slot;
-    if (smem > 220 * 1024) return 1;
+    static const int want_slots = env_int("KTB200_PIPE_SLOTS", 1);
     dim3 grid(gx, T);
-    KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k8_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reduce_pipe_q6k8_kernel<12><<<grid, warps * 32, smem, stream>>>(p, slot);
+    if (want_slots != 2 && base + (size_t)24 * slot <= 220 * 1024) {
+        const size_t smem = base + (size_t)24 * slot;
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k8_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_pipe_q6k8_kernel<24, 1><<<grid, 24 * 32, smem, stream>>>(p, slot);
+    } else if (base + (size_t)12 * 2 * slot <= 220 * 1024) {
+        const size_t smem = base + (size_t)12 * 2 * slot;
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k8_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_pipe_q6k8_kernel<12, 2><<<grid, 12 * 32, smem, stream>>>(p, slot);
+    } else {
+        return 1;
+    }
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
 }
