@@ -162,7 +162,7 @@ static int launch_rows_pipe_q4k_blk(const RowsParams& p, int T, int device, cuda
     const int act = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
     if (slot < 4096 || nblk < 16) return 1;             // needs >= 16 blocks per row to keep most lanes busy
     // (warps, slots): 24 x 1 by default (more eligible warps per scheduler), 12 x 2 with KTB200_PIPE_SLOTS=2
-    static const int want_slots = env_int("KTB200_PIPE_SLOTS", 1);
+    static const int want_slots = env_int("KTB200_PIPE_SLOTS", 2);
     const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
     if (total >= (1L << 30)) return 1;
     int gx = (num_sms(device) + T - 1) / T;
@@ -252,7 +252,7 @@ static int launch_reduce_pipe_q6k8(const ReduceParams& p, int T, int device, cud
     if (gx < 1) gx = 1;
     const int nrows_max = ((quads + gx - 1) / gx + 1) * 4;
     size_t base = (size_t)ns * p.ncols + (size_t)ns * nb * 4 + (size_t)ns * (p.ncols / 16) * 2 + (size_t)nrows_max * ns * 4 + 16;
-    static const int want_slots = env_int("KTB200_PIPE_SLOTS", 1);
+    static const int want_slots = env_int("KTB200_PIPE_SLOTS", 2);
     dim3 grid(gx, T);
     if (want_slots != 2 && base + (size_t)24 * slot <= 220 * 1024) {
         const size_t smem = base + (size_t)24 * slot;
