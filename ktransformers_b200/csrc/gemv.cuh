@@ -42,6 +42,7 @@ struct RowsParams {
     void* out_hidden;       // !PAIR: [T][rows] hidden_type (slots must be 1) or null
     const float* bias;      // !PAIR optional [rows]
     const int* bsz;         // optional device batch size
+    int ntokens;            // T (used by the token-looping kernels; the (gx, T)-grid kernels read blockIdx.y)
     // optional extra slot (index == slots) served from separate tensors: the shared expert fused into
     // the routed launch (KDeepseekV3MoE: y = experts(x) + shared_experts(x), experts.py:984-1011)
     const void* x0;
@@ -203,6 +204,7 @@ struct ReduceParams {
     int hidden_type;
     int accumulate;         // out = round(out + round(result)) in hidden_type (torch `y += y_` semantics)
     const int* bsz;
+    int ntokens;            // T
     const void* xw;         // optional extra slot (shared expert down_proj); its result is rounded to
                             // hidden_type separately and added like `y += y_` (experts.py:1011)
 };

@@ -164,11 +164,11 @@ static int launch_rows_pipe_q4k_blk(const RowsParams& p, int T, int device, cuda
     // (warps, slots): 24 x 1 by default (more eligible warps per scheduler), 12 x 2 with KTB200_PIPE_SLOTS=2
     static const int want_slots = env_int("KTB200_PIPE_SLOTS", 2);
     const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
-    if (total >= (1L << 30)) return 1;
-    int gx = (num_sms(device) + T - 1) / T;
+    if (total >= (1L << 30) || p.slots + 1 > 36) return 1;
+    int gx = num_sms(device);            // one CTA per SM walks all T tokens
     if (gx > total) gx = (int)total;
     if (gx < 1) gx = 1;
-    dim3 grid(gx, T);
+    dim3 grid(gx, 1);
 #define KTB_BLK(W, S)                                                                                                  \
     do {                                                                                                               \
         const size_t smem = (size_t)act + (size_t)(W) * (S) * slot;                                                    \
@@ -187,7 +187,9 @@ static int launch_rows_pipe_q4k_blk(const RowsParams& p, int T, int device, cuda
 }
 
 template <bool PAIR>
-static int launch_rows(FmtId f, const RowsParams& p, int T, int device, cudaStream_t stream) {
+static int launch_rows(FmtId f, const RowsParams& p_in, int T, int device, cudaStream_t stream) {
+    RowsParams p = p_in;
+    p.ntokens = T;
     if (f == FMT_Q4K) {
         const int rc = launch_rows_pipe_q4k_blk<PAIR>(p, T, device, stream);
         if (rc != 1) return rc;
@@ -269,9 +271,45 @@ static int launch_reduce_pipe_q6k8(const ReduceParams& p, int T, int device, cud
     return KTB200_OK;
 }
 
-static int launch_reduce(FmtId f, const ReduceParams& p, int T, int device, cudaStream_t stream) {
+// Q6_K, one lane per super-block (reduce_pipe_q6k_blk_kernel).  Returns 1 when the shape does not suit it.
+static int launch_reduce_pipe_q6k_blk(const ReduceParams& p, int T, int device, cudaStream_t stream) {
+    if (cfg_pipe() < 2) return 1;
+    const int nb = p.ncols / QK_K;
+    if (p.rows % 4 || nb % 2 || (4 * nb) % 8) return 1;
+    const int ns = p.slots + (p.xw ? 1 : 0);
+    const int nrb = 4 * nb;
+    const int slot = (nrb * (kQ6QlStride + kQ6QhStride + 16) + nrb * 2 + 15) & ~15;
+    if (slot < 4096) return 1;
+    const int quads = p.rows / 4;
+    if (ns > 36) return 1;
+    int gx = num_sms(device);            // one CTA per SM walks all T tokens
+    if (gx > quads) gx = quads;
+    if (gx < 1) gx = 1;
+    const int nrows_max = ((quads + gx - 1) / gx + 1) * 4;
+    const size_t base = (size_t)ns * nb * (kActBlkStride + 32 + 4) + (size_t)nrows_max * ns * 4 + 16;
+    int warps = 0;
+    for (int w : {12, 8}) if (base + (size_t)w * 2 * slot <= 220 * 1024) { warps = w; break; }
+    if (!warps) return 1;
+    const size_t smem = base + (size_t)warps * 2 * slot;
+    dim3 grid(gx, 1);
+    if (warps == 12) {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k_blk_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_pipe_q6k_blk_kernel<12><<<grid, 12 * 32, smem, stream>>>(p, slot);
+    } else {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k_blk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_pipe_q6k_blk_kernel<8><<<grid, 8 * 32, smem, stream>>>(p, slot);
+    }
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+static int launch_reduce(FmtId f, const ReduceParams& p_in, int T, int device, cudaStream_t stream) {
+    ReduceParams p = p_in;
+    p.ntokens = T;
     if (f == FMT_Q6K8) {
-        const int rc = launch_reduce_pipe_q6k8(p, T, device, stream);
+        int rc = launch_reduce_pipe_q6k_blk(p, T, device, stream);
+        if (rc != 1) return rc;
+        rc = launch_reduce_pipe_q6k8(p, T, device, stream);
         if (rc != 1) return rc;
     }
     switch (f) {
