@@ -467,7 +467,10 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        # tearing NCCL down with captured graphs alive can hang in destroy_process_group: leave by the fast door
+        os._exit(0)
 
 
 if __name__ == "__main__":
