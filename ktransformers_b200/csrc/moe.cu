@@ -5,7 +5,7 @@
 #include <cstring>
 #include <new>
 
-#include "gemv_pipe.cuh"
+#include "gemv_bulk.cuh"
 
 namespace ktb {
 
@@ -64,13 +64,71 @@ static int repack_q6k(void* w, long rows_total, int ncols, int device, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel dispatch
-enum FmtId { FMT_Q4K, FMT_Q5K, FMT_Q6K8, FMT_GENK, FMT_NONE };
+// Q6_K "4-row chunk-major tile" re-layout, in place (consumed by reduce_bulk_kernel<BulkQ6K4T>, gemv_bulk.cuh).
+// Item = 4 consecutive rows x nb blocks (f = rw*nb + blk is also the raw block index inside the item):
+//   raw : block f at f*210 : {ql[128] qh[64] scales[16] d[2]}
+//   t4  : [ql: c=0..7][f][16] | [qh: c=0..3][f][16] | [scales: f][16] | [d: f][2]
+// Same bytes; the item is one contiguous, 16-byte aligned range (nb even) = one bulk copy, and consecutive
+// lanes read consecutive 16-byte words of a chunk.
+__global__ void __launch_bounds__(256) repack_q6k4t_kernel(uint8_t* w, long n_items, int nb) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const long nrb = 4L * nb, ibytes = nrb * SZ_Q6_K;  // multiple of 16 (nb even)
+    for (long it = blockIdx.x; it < n_items; it += gridDim.x) {
+        uint8_t* base = w + it * ibytes;
+        for (long i = threadIdx.x; i < ibytes / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(base)[i];
+        __syncthreads();
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(smem);
+        uint16_t* dst = reinterpret_cast<uint16_t*>(base);
+        const long s_qh = nrb * 128, s_sc = nrb * 192, s_d = nrb * 208;
+        for (long i = threadIdx.x; i < ibytes / 2; i += blockDim.x) {
+            const long off = 2 * i;
+            long f, sect, x;
+            if (off < s_qh) {
+                const long c = off / (nrb * 16), o = off % (nrb * 16);
+                f = o / 16; x = c * 16 + o % 16; sect = 0;
+            } else if (off < s_sc) {
+                const long o2 = off - s_qh, c = o2 / (nrb * 16), o = o2 % (nrb * 16);
+                f = o / 16; x = c * 16 + o % 16; sect = 128;
+            } else if (off < s_d) {
+                const long o = off - s_sc;
+                f = o / 16; x = o % 16; sect = 192;
+            } else {
+                f = (off - s_d) / 2; x = 0; sect = 208;
+            }
+            dst[i] = src[(f * SZ_Q6_K + sect + x) / 2];
+        }
+        __syncthreads();
+    }
+}
 
-static FmtId pick_fmt(int type, bool soa) {
+static int repack_q6k4t(void* w, long rows_total, int ncols, int device, cudaStream_t stream) {
+    const int nb = ncols / QK_K;
+    const long n_items = rows_total / 4;
+    const size_t smem = (size_t)4 * SZ_Q6_K * nb;
+    if (smem > 200 * 1024 || nb % 2 || rows_total % 4) {
+        set_error("Q6_K tile repack: unsupported shape (%ld rows x %d cols)", rows_total, ncols);
+        return KTB200_EINVAL;
+    }
+    KTB_CUDA_CHECK(cudaFuncSetAttribute(repack_q6k4t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long grid = n_items < (long)num_sms(device) * 8 ? n_items : (long)num_sms(device) * 8;
+    if (grid < 1) grid = 1;
+    repack_q6k4t_kernel<<<(unsigned)grid, 256, smem, stream>>>(reinterpret_cast<uint8_t*>(w), n_items, nb);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+enum FmtId { FMT_Q4K, FMT_Q5K, FMT_Q6K8, FMT_Q6K4T, FMT_GENK, FMT_NONE };
+// how a Q6_K tensor was re-laid at load time
+enum Q6Layout { LAYOUT_RAW = 0, LAYOUT_SOA8 = 1, LAYOUT_T4 = 2 };
+
+static FmtId pick_fmt(int type, int layout) {
     if (type == KTB200_TYPE_Q4_K) return FMT_Q4K;
     if (type == KTB200_TYPE_Q5_K) return FMT_Q5K;
-    if (type == KTB200_TYPE_Q6_K && soa) return FMT_Q6K8;
+    if (type == KTB200_TYPE_Q6_K && layout == LAYOUT_SOA8) return FMT_Q6K8;
+    if (type == KTB200_TYPE_Q6_K && layout == LAYOUT_T4) return FMT_Q6K4T;
     if (is_kquant(type)) return FMT_GENK;
     return FMT_NONE;
 }
@@ -91,6 +149,12 @@ static int env_int(const char* name, int dflt) {
 static int cfg_minb() { static int v = env_int("KTB200_MINB", 2); return v == 3 ? 3 : 2; }
 static int cfg_pipe() { static int v = env_int("KTB200_PIPE", 2); return v; }   // 0 off, 1 chunk-per-lane, 2 block-per-lane
 static int cfg_nb() { static int v = env_int("KTB200_NB", 2); return v == 4 ? 4 : 2; }
+// bulk-copy generation (gemv_bulk.cuh): KTB200_BULK=0 disables it, *_SLOTS_* = ring depth, KTB200_BULK_WARPS caps the CTA
+static int cfg_bulk() { static int v = env_int("KTB200_BULK", 1); return v; }
+static int cfg_bulk_slots_up() { static int v = env_int("KTB200_BULK_SLOTS_UP", 3); return v == 2 ? 2 : (v == 4 ? 4 : 3); }
+static int cfg_bulk_slots_down() { static int v = env_int("KTB200_BULK_SLOTS_DOWN", 2); return v == 3 ? 3 : 2; }
+static int cfg_bulk_warps() { static int v = env_int("KTB200_BULK_WARPS", kBulkMaxWarps); return v < 1 ? 1 : (v > kBulkMaxWarps ? kBulkMaxWarps : v); }
+constexpr size_t kSmemCap = 232448 - 512;   // 227 KB opt-in limit minus the kernels' static shared variables
 
 template <class Fmt, bool PAIR>
 static int launch_rows_fmt(const RowsParams& p, int T, int device, cudaStream_t stream, bool tunable) {
@@ -186,11 +250,42 @@ static int launch_rows_pipe_q4k_blk(const RowsParams& p, int T, int device, cuda
     return KTB200_OK;
 }
 
+// Q4_K rows through the bulk-copy ring (rows_bulk_q4k_kernel).  Returns 1 when the shape does not suit it.
+template <bool PAIR>
+static int launch_rows_bulk_q4k(const RowsParams& p, int T, int device, cudaStream_t stream) {
+    if (!cfg_bulk()) return 1;
+    const int nblk = p.ncols / QK_K;
+    const int row_bytes = nblk * SZ_Q4_K;
+    if (nblk < 16) return 1;                             // needs >= 16 blocks per row to keep most lanes busy
+    const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
+    if (total >= (1L << 30) || p.slots + 1 > 36) return 1;
+    const int act = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
+    const int S = cfg_bulk_slots_up();
+    int W = (int)((kSmemCap - act - 16) / ((size_t)S * (row_bytes + 8)));
+    if (W > cfg_bulk_warps()) W = cfg_bulk_warps();
+    if (W < 4) return 1;
+    const size_t smem = (size_t)act + (((size_t)W * S * 8 + 15) & ~(size_t)15) + (size_t)W * S * row_bytes;
+    int gx = num_sms(device);            // one CTA per SM walks all T tokens
+    if (gx > total) gx = (int)total;
+    if (gx < 1) gx = 1;
+#define KTB_BULK_ROWS(SL)                                                                                              \
+    do {                                                                                                               \
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_bulk_q4k_kernel<PAIR, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rows_bulk_q4k_kernel<PAIR, SL><<<gx, W * 32, smem, stream>>>(p, act);                                          \
+    } while (0)
+    if (S == 2) KTB_BULK_ROWS(2); else if (S == 4) KTB_BULK_ROWS(4); else KTB_BULK_ROWS(3);
+#undef KTB_BULK_ROWS
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
 template <bool PAIR>
 static int launch_rows(FmtId f, const RowsParams& p_in, int T, int device, cudaStream_t stream) {
     RowsParams p = p_in;
     p.ntokens = T;
     if (f == FMT_Q4K) {
+        const int rcb = launch_rows_bulk_q4k<PAIR>(p, T, device, stream);
+        if (rcb != 1) return rcb;
         const int rc = launch_rows_pipe_q4k_blk<PAIR>(p, T, device, stream);
         if (rc != 1) return rc;
     }
@@ -303,9 +398,73 @@ static int launch_reduce_pipe_q6k_blk(const ReduceParams& p, int T, int device, 
     return KTB200_OK;
 }
 
+// Shared-memory plan of reduce_bulk_kernel<Fmt, S>: returns the warp count (0 = does not fit)
+template <class Fmt>
+static int reduce_bulk_plan(int rows, int ncols, int ns, int S, int device, int* gx_out, int* nrows_max_out, size_t* smem_out) {
+    const int nb = ncols / QK_K;
+    if (rows % 4 || nb < 1 || ns > 36) return 0;
+    const size_t item = (size_t)4 * nb * Fmt::kBlockBytes;
+    if (item % 16) return 0;
+    const int quads = rows / 4;
+    int gx = num_sms(device);
+    if (gx > quads) gx = quads;
+    if (gx < 1) gx = 1;
+    const int nrows_max = ((quads + gx - 1) / gx) * 4;
+    size_t base = (size_t)ns * nb * (kActBlkStride + 2 * Fmt::kBs + 4) + (size_t)nrows_max * ns * 4;
+    base = (base + 15) & ~(size_t)15;
+    if (base + 16 >= kSmemCap) return 0;
+    int W = (int)((kSmemCap - base - 16) / ((size_t)S * (item + 8)));
+    if (W > cfg_bulk_warps()) W = cfg_bulk_warps();
+    if (W > kBulkMaxWarpsDown) W = kBulkMaxWarpsDown;
+    if (W < 2) return 0;
+    if (gx_out) *gx_out = gx;
+    if (nrows_max_out) *nrows_max_out = nrows_max;
+    if (smem_out) *smem_out = base + (((size_t)W * S * 8 + 15) & ~(size_t)15) + (size_t)W * S * item;
+    return W;
+}
+
+// Down projection through the bulk-copy ring.  Returns 1 when the shape does not suit it.
+template <class Fmt>
+static int launch_reduce_bulk(const ReduceParams& p, int T, int device, cudaStream_t stream) {
+    if (!cfg_bulk()) return 1;
+    const int ns = p.slots + (p.xw ? 1 : 0);
+    const int S = cfg_bulk_slots_down();
+    int gx = 0, nrows_max = 0;
+    size_t smem = 0;
+    const int W = reduce_bulk_plan<Fmt>(p.rows, p.ncols, ns, S, device, &gx, &nrows_max, &smem);
+    if (!W) return 1;
+    if (S == 3) {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_bulk_kernel<Fmt, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_bulk_kernel<Fmt, 3><<<gx, W * 32, smem, stream>>>(p, nrows_max);
+    } else {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_bulk_kernel<Fmt, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_bulk_kernel<Fmt, 2><<<gx, W * 32, smem, stream>>>(p, nrows_max);
+    }
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+// Load-time decision: can a Q6_K down tensor [rows][ncols] take the T4 tile layout (and therefore ONLY the bulk
+// kernel) for up to ns_max slots per token?
+static bool q6k4t_eligible(int rows, int ncols, int ns_max, int device) {
+    if (!cfg_bulk()) return false;
+    const int nb = ncols / QK_K;
+    if (nb % 2 || rows % 4) return false;
+    return reduce_bulk_plan<BulkQ6K4T>(rows, ncols, ns_max, 3, device, nullptr, nullptr, nullptr) >= 4;
+}
+
 static int launch_reduce(FmtId f, const ReduceParams& p_in, int T, int device, cudaStream_t stream) {
     ReduceParams p = p_in;
     p.ntokens = T;
+    if (f == FMT_Q6K4T) {
+        const int rc = launch_reduce_bulk<BulkQ6K4T>(p, T, device, stream);
+        if (rc == 1) { set_error("Q6_K tile layout: k=%d x ncols=%d does not fit the bulk kernel", p.slots, p.ncols); return KTB200_EINVAL; }
+        return rc;
+    }
+    if (f == FMT_Q4K) {
+        const int rc = launch_reduce_bulk<BulkQ4K>(p, T, device, stream);
+        if (rc != 1) return rc;
+    }
     if (f == FMT_Q6K8) {
         int rc = launch_reduce_pipe_q6k_blk(p, T, device, stream);
         if (rc != 1) return rc;
@@ -353,7 +512,8 @@ using namespace ktb;
 struct ktb200_mlp {
     int H, I, gate_type, up_type, down_type, hidden_type, group_max_len, device;
     const void *gate, *up, *down;
-    bool loaded, gu_soa, down_soa;
+    bool loaded, gu_soa;
+    int down_layout;   // Q6Layout of the down tensor
     float* inter;
 };
 
@@ -361,7 +521,8 @@ struct ktb200_moe {
     ktb200_moe_config cfg;
     int device;
     bool loaded;
-    bool gu_soa, down_soa;
+    bool gu_soa;
+    int down_layout;   // Q6Layout of the down tensor
     float* inter;      // [group_max_len * k][I]
     // host-call staging
     int64_t* ids_d;
@@ -404,7 +565,8 @@ int ktb200_moe_create(const ktb200_moe_config* c, int device, ktb200_moe** out) 
     m->cfg = *c;
     m->device = device;
     m->loaded = false;
-    m->gu_soa = m->down_soa = false;
+    m->gu_soa = false;
+    m->down_layout = LAYOUT_RAW;
     m->inter = nullptr; m->ids_d = nullptr; m->w_d = nullptr; m->in_d = nullptr; m->out_d = nullptr;
     const size_t slots = (size_t)c->group_max_len * c->routed_expert_num;
     const size_t hid = (size_t)c->group_max_len * c->hidden_size * type_size(c->hidden_type);
@@ -443,10 +605,14 @@ int ktb200_moe_load_weights(ktb200_moe* m, void* stream) {
         if (rc) return rc;
         m->gu_soa = true;
     }
-    if (c.down_type == KTB200_TYPE_Q6_K && c.hidden_size % 8 == 0) {
+    if (c.down_type == KTB200_TYPE_Q6_K && q6k4t_eligible(c.hidden_size, c.intermediate_size, c.routed_expert_num + 1, m->device)) {
+        int rc = repack_q6k4t(const_cast<void*>(c.down_proj), (long)c.expert_num * c.hidden_size, c.intermediate_size, m->device, s);
+        if (rc) return rc;
+        m->down_layout = LAYOUT_T4;
+    } else if (c.down_type == KTB200_TYPE_Q6_K && c.hidden_size % 8 == 0) {
         int rc = repack_q6k(const_cast<void*>(c.down_proj), (long)c.expert_num * c.hidden_size, c.intermediate_size, m->device, s);
         if (rc) return rc;
-        m->down_soa = true;
+        m->down_layout = LAYOUT_SOA8;
     }
     m->loaded = true;
     return KTB200_OK;
@@ -472,12 +638,12 @@ static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, 
     rp.n_experts = c.expert_num; rp.rows = c.intermediate_size; rp.ncols = c.hidden_size; rp.slots = k;
     rp.ids = ids; rp.id_offset = c.expert_id_offset; rp.x = input; rp.hidden_type = c.hidden_type;
     rp.use_silu = c.use_silu; rp.out_f32 = m->inter; rp.out_hidden = nullptr; rp.bias = nullptr; rp.bsz = bsz;
-    const FmtId fd = pick_fmt(c.down_type, m->down_soa);
+    const FmtId fd = pick_fmt(c.down_type, m->down_layout);
     // the shared expert rides in the same two launches as slot k when its tensors have the routed experts'
     // shapes and layouts (DeepSeek-V3: n_shared_experts = 1, same quant types); otherwise it runs separately
     const bool fuse = sh && sh->loaded && sh->H == c.hidden_size && sh->I == c.intermediate_size && c.use_silu &&
                       sh->hidden_type == c.hidden_type && sh->gate_type == c.gate_type && sh->up_type == c.up_type &&
-                      sh->down_type == c.down_type && sh->gu_soa == m->gu_soa && sh->down_soa == m->down_soa;
+                      sh->down_type == c.down_type && sh->gu_soa == m->gu_soa && sh->down_layout == m->down_layout;
     if (fuse) { rp.x0 = sh->gate; rp.x1 = sh->up; }
     int rc = launch_rows<true>(fg, rp, qlen, m->device, s);
     if (rc) return rc;
@@ -629,7 +795,7 @@ int ktb200_mlp_create(int H, int I, const void* gate, const void* up, const void
     if (!m) return KTB200_ENOMEM;
     m->H = H; m->I = I; m->gate = gate; m->up = up; m->down = down; m->gate_type = gate_type; m->up_type = up_type;
     m->down_type = down_type; m->hidden_type = hidden_type; m->group_max_len = group_max_len; m->device = device;
-    m->loaded = m->gu_soa = m->down_soa = false; m->inter = nullptr;
+    m->loaded = m->gu_soa = false; m->down_layout = LAYOUT_RAW; m->inter = nullptr;
     if (cudaMalloc(&m->inter, (size_t)group_max_len * I * sizeof(float)) != cudaSuccess) {
         set_error("cudaMalloc failed");
         delete m;
@@ -656,10 +822,15 @@ int ktb200_mlp_load_weights(ktb200_mlp* m, void* stream) {
         if (rc) return rc;
         m->gu_soa = true;
     }
-    if (m->down_type == KTB200_TYPE_Q6_K && m->H % 8 == 0 && (size_t)8 * SZ_Q6_K * (m->I / QK_K) <= 200 * 1024) {
+    // 17 slots: a shared expert stays fusable with up to 16 routed experts per token (ktb200_moe_forward_shared)
+    if (m->down_type == KTB200_TYPE_Q6_K && q6k4t_eligible(m->H, m->I, 17, m->device)) {
+        int rc = repack_q6k4t(const_cast<void*>(m->down), m->H, m->I, m->device, s);
+        if (rc) return rc;
+        m->down_layout = LAYOUT_T4;
+    } else if (m->down_type == KTB200_TYPE_Q6_K && m->H % 8 == 0 && (size_t)8 * SZ_Q6_K * (m->I / QK_K) <= 200 * 1024) {
         int rc = repack_q6k(const_cast<void*>(m->down), m->H, m->I, m->device, s);
         if (rc) return rc;
-        m->down_soa = true;
+        m->down_layout = LAYOUT_SOA8;
     }
     m->loaded = true;
     return KTB200_OK;
@@ -682,7 +853,7 @@ int ktb200_mlp_forward(ktb200_mlp* m, int qlen, const void* input, void* output,
     ReduceParams dp{};
     dp.w = m->down; dp.type = m->down_type; dp.n_experts = 1; dp.rows = m->H; dp.ncols = m->I; dp.slots = 1; dp.ids = nullptr;
     dp.weights = nullptr; dp.a = m->inter; dp.out = output; dp.hidden_type = m->hidden_type; dp.accumulate = accumulate; dp.bsz = bsz;
-    return launch_reduce(pick_fmt(m->down_type, m->down_soa), dp, qlen, m->device, s);
+    return launch_reduce(pick_fmt(m->down_type, m->down_layout), dp, qlen, m->device, s);
 }
 
 // ------------------------------------------------------------------------------------------ quantize API

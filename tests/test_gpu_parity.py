@@ -112,6 +112,10 @@ COMBOS = [
     (Q4_K, Q4_K, Q6_K, 8, 4, 1024, 512), (Q4_K, Q4_K, Q4_K, 8, 4, 1024, 512), (Q6_K, Q6_K, Q6_K, 4, 2, 512, 256),
     (Q5_K, Q5_K, Q5_K, 4, 2, 512, 512), (Q2_K, Q2_K, Q3_K, 4, 2, 512, 256), (IQ4_XS, IQ4_XS, IQ4_XS, 4, 2, 256, 256),
     (Q4_K, Q5_K, Q6_K, 4, 3, 768, 256), (Q3_K, Q3_K, Q2_K, 4, 2, 256, 512), (Q4_K, Q4_K, Q6_K, 6, 6, 2048, 1536),
+    # shapes that take the bulk-copy kernels (gemv_bulk.cuh): >= 16 blocks per gate/up row (16 / 40 / 32 lanes-worth),
+    # down items of 8, 32 and 64 (row, block) pairs, Q4_K down
+    (Q4_K, Q4_K, Q6_K, 4, 3, 4096, 512), (Q4_K, Q4_K, Q4_K, 3, 2, 10240, 256), (Q4_K, Q4_K, Q6_K, 3, 2, 512, 4096),
+    (Q4_K, Q4_K, Q6_K, 4, 2, 4096, 2048), (Q4_K, Q4_K, Q4_K, 2, 2, 8192, 256),
 ]
 
 
@@ -136,8 +140,9 @@ def test_moe_forward_vs_oracle(oracle, gt, ut, dt, E, k, H, I, hid):
     m.close()
 
 
-def test_moe_edge_cases(oracle):
-    E, k, H, I = 8, 4, 512, 256
+@pytest.mark.parametrize("H,I", [(512, 256), (4096, 512)])   # register-staged kernels / bulk-copy kernels
+def test_moe_edge_cases(oracle, H, I):
+    E, k = 8, 4
     gate, up, down = _synth(Q4_K, E * I * H, 11), _synth(Q4_K, E * I * H, 12), _synth(Q6_K, E * H * I, 13)
     g_np, u_np, d_np = gate.cpu().numpy(), up.cpu().numpy(), down.cpu().numpy()
     m = G.Moe(E, k, H, I, gate, up, down, Q4_K, Q4_K, Q6_K, F32, max_tokens=16)
@@ -169,8 +174,9 @@ def test_moe_edge_cases(oracle):
     m.close()
 
 
-def test_moe_expert_parallel_shards_sum_to_full():
-    E, k, H, I = 8, 4, 512, 512
+@pytest.mark.parametrize("H", [512, 4096])
+def test_moe_expert_parallel_shards_sum_to_full(H):
+    E, k, I = 8, 4, 512
     gate, up, down = _synth(Q4_K, E * I * H, 21), _synth(Q4_K, E * I * H, 22), _synth(Q6_K, E * H * I, 23)
     gbytes, dbytes = gate.numel() // E, down.numel() // E
     rng = np.random.default_rng(9)
@@ -187,12 +193,13 @@ def test_moe_expert_parallel_shards_sum_to_full():
     assert relmax(acc, full) < 1e-5
 
 
+@pytest.mark.parametrize("H", [1024, 4096])
 @pytest.mark.parametrize("sgt,sdt,fused", [(Q4_K, Q6_K, True), (Q5_K, Q4_K, False)])
-def test_moe_with_shared_expert_matches_two_rounded_terms(oracle, sgt, sdt, fused):
+def test_moe_with_shared_expert_matches_two_rounded_terms(oracle, sgt, sdt, fused, H):
     """KDeepseekV3MoE: y = experts(x); y += shared_experts(x) on bf16 tensors — each term rounded, then the sum.
     Same quant types as the routed experts -> the shared expert is an extra slot inside the two routed launches;
     different types -> it runs as a separate MLP.  Both must give the reference's two-rounding result."""
-    E, k, H, I = 8, 4, 1024, 512
+    E, k, I = 8, 4, 512
     gate, up, down = _synth(Q4_K, E * I * H, 71), _synth(Q4_K, E * I * H, 72), _synth(Q6_K, E * H * I, 73)
     sg, su, sd = _synth(sgt, I * H, 74), _synth(sgt, I * H, 75), _synth(sdt, H * I, 76)
     g_np, u_np, d_np, sg_np, su_np, sd_np = (t.cpu().numpy() for t in (gate, up, down, sg, su, sd))
