@@ -24,6 +24,7 @@
 namespace ktb {
 
 constexpr int kBulkMaxWarps = 18;        // gate/up kernel (<= 96 registers per thread)
+constexpr int kBulkMaxWarpsAreg = 16;    // gate/up kernel with register-resident activations (128 registers)
 constexpr int kBulkMaxWarpsDown = 16;    // down kernel: 128 registers per thread, and shared memory caps it at 15 anyway
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -59,7 +60,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------------------------------
 // One Q4_K super-block (144 B at `wb`, shared memory, 16-byte aligned) against one padded int8 activation block.
 // bsv = the block's eight 32-value activation sums (int16), dxb = the activation block scale.
-__device__ __forceinline__ float q4k_block_dot(const uint8_t* wb, const uint8_t* aq, const uint4 bsv, const float dxb) {
+// `act4(i)` returns the i-th 16-byte word of the block's 256 int8 activations (from shared memory or from registers).
+template <class ActFn>
+__device__ __forceinline__ float q4k_block_dot_t(const uint8_t* wb, ActFn&& act4, const uint4 bsv, const float dxb) {
     const uint4 hdr = *reinterpret_cast<const uint4*>(wb);
     const float2 dm = __half22float2(*reinterpret_cast<const __half2*>(&hdr.x));
     const uint32_t scl = hdr.y & 0x3f3f3f3fu;                                          // scales 0..3
@@ -69,10 +72,7 @@ __device__ __forceinline__ float q4k_block_dot(const uint8_t* wb, const uint8_t*
     int isum = 0;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        const uint4 a0 = *reinterpret_cast<const uint4*>(aq + 64 * g);
-        const uint4 a1 = *reinterpret_cast<const uint4*>(aq + 64 * g + 16);
-        const uint4 a2 = *reinterpret_cast<const uint4*>(aq + 64 * g + 32);
-        const uint4 a3 = *reinterpret_cast<const uint4*>(aq + 64 * g + 48);
+        const uint4 a0 = act4(4 * g), a1 = act4(4 * g + 1), a2 = act4(4 * g + 2), a3 = act4(4 * g + 3);
         const uint4 q0 = *reinterpret_cast<const uint4*>(wb + 16 + 32 * g);
         const uint4 q1 = *reinterpret_cast<const uint4*>(wb + 32 + 32 * g);
         int slo = 0, shi = 0, slo2 = 0, shi2 = 0;
@@ -95,13 +95,19 @@ __device__ __forceinline__ float q4k_block_dot(const uint8_t* wb, const uint8_t*
     msum = __dp2a_hi((int)bsv.w, (int)mnh, msum);
     return (dm.x * dxb) * (float)isum - (dm.y * dxb) * (float)msum;
 }
+__device__ __forceinline__ float q4k_block_dot(const uint8_t* wb, const uint8_t* aq, const uint4 bsv, const float dxb) {
+    return q4k_block_dot_t(wb, [&](int i) { return *reinterpret_cast<const uint4*>(aq + 16 * i); }, bsv, dxb);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Gate/up (PAIR) or dense (PAIR = false) rows of Q4_K tensors.  Per warp: a private ring of SLOTS row slots; the
 // warp's stream of sub-units is g(u0), u(u0), g(u0+W), u(u0+W), ... (PAIR) and at any time SLOTS-1 rows are in
 // flight behind the one being consumed.
-template <bool PAIR, int SLOTS>
-__global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) rows_bulk_q4k_kernel(const RowsParams p, int act_bytes) {
+// AREG (rows of <= 32 super-blocks, i.e. ncols <= 8192): lane b always meets activation block b, so the block's 256
+// int8 + sums + scale live in 69 REGISTERS for the whole token and the dot product reads only weights from shared
+// memory (9 instead of 27 LDS.128 per row); costs registers -> 16 warps instead of 18.
+template <bool PAIR, int SLOTS, bool AREG>
+__global__ void __launch_bounds__((AREG ? kBulkMaxWarpsAreg : kBulkMaxWarps) * 32, 1) rows_bulk_q4k_kernel(const RowsParams p, int act_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_vs[36];   // compacted list of the slots this launch computes for the current token
     __shared__ int s_nv;
@@ -198,15 +204,28 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) rows_bulk_q4k_kernel(co
     }
     __syncthreads();
 
+    uint4 areg[AREG ? 16 : 1];
+    if (AREG) {
+        const int b = lane < nblk ? lane : 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) areg[i] = *reinterpret_cast<const uint4*>(q8 + (size_t)b * kActBlkStride + 16 * i);
+    }
+
     float acc_first = 0.f;
     for (int n = 0; n < nsub; n++) {
         mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
         phase ^= 1u << slot_u;
         const uint8_t* row0 = ring + slot_u * row_bytes;
         float acc = 0.f;
-        for (int blk = lane; blk < nblk; blk += 32)
-            acc += q4k_block_dot(row0 + blk * SZ_Q4_K, q8 + (size_t)blk * kActBlkStride,
-                                 *reinterpret_cast<const uint4*>(bs32 + blk * 8), dx[blk]);
+        if (AREG) {
+            // (sums and scale are re-read per row: two LDS are cheaper than five more live registers)
+            if (lane < nblk) acc = q4k_block_dot_t(row0 + lane * SZ_Q4_K, [&](int i) { return areg[i]; },
+                                                   *reinterpret_cast<const uint4*>(bs32 + lane * 8), dx[lane]);
+        } else {
+            for (int blk = lane; blk < nblk; blk += 32)
+                acc += q4k_block_dot(row0 + blk * SZ_Q4_K, q8 + (size_t)blk * kActBlkStride,
+                                     *reinterpret_cast<const uint4*>(bs32 + blk * 8), dx[blk]);
+        }
         __syncwarp();                       // every lane is done reading the slot: hand it back to the copy engine
         slot_u = (slot_u + 1 == SLOTS) ? 0 : slot_u + 1;
         issue_one();

@@ -261,19 +261,23 @@ static int launch_rows_bulk_q4k(const RowsParams& p, int T, int device, cudaStre
     if (total >= (1L << 30) || p.slots + 1 > 36) return 1;
     const int act = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
     const int S = cfg_bulk_slots_up();
+    static const int want_areg = env_int("KTB200_BULK_AREG", 1);
+    const bool areg = want_areg && nblk <= 32;
     int W = (int)((kSmemCap - act - 16) / ((size_t)S * (row_bytes + 8)));
     if (W > cfg_bulk_warps()) W = cfg_bulk_warps();
+    if (areg && W > kBulkMaxWarpsAreg) W = kBulkMaxWarpsAreg;
     if (W < 4) return 1;
     const size_t smem = (size_t)act + (((size_t)W * S * 8 + 15) & ~(size_t)15) + (size_t)W * S * row_bytes;
     int gx = num_sms(device);            // one CTA per SM walks all T tokens
     if (gx > total) gx = (int)total;
     if (gx < 1) gx = 1;
-#define KTB_BULK_ROWS(SL)                                                                                              \
+#define KTB_BULK_ROWS(SL, AR)                                                                                          \
     do {                                                                                                               \
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_bulk_q4k_kernel<PAIR, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rows_bulk_q4k_kernel<PAIR, SL><<<gx, W * 32, smem, stream>>>(p, act);                                          \
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_bulk_q4k_kernel<PAIR, SL, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rows_bulk_q4k_kernel<PAIR, SL, AR><<<gx, W * 32, smem, stream>>>(p, act);                                      \
     } while (0)
-    if (S == 2) KTB_BULK_ROWS(2); else if (S == 4) KTB_BULK_ROWS(4); else KTB_BULK_ROWS(3);
+    if (areg) { if (S == 2) KTB_BULK_ROWS(2, true); else if (S == 4) KTB_BULK_ROWS(4, true); else KTB_BULK_ROWS(3, true); }
+    else { if (S == 2) KTB_BULK_ROWS(2, false); else if (S == 4) KTB_BULK_ROWS(4, false); else KTB_BULK_ROWS(3, false); }
 #undef KTB_BULK_ROWS
     KTB_LAUNCH_CHECK();
     return KTB200_OK;

@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <atomic>
 
-#include "common.cuh"
+#include "gemv_bulk.cuh"
 
 namespace ktb {
 
@@ -77,6 +77,51 @@ __global__ void __launch_bounds__(256) stream_read_kernel(const uint4* __restric
     }
     if (acc == 0x12345678u) *sink = acc;   // never true in practice: keeps the loads alive
 }
+
+// mode 2: the access shape of the bulk-copy kernels without their arithmetic — one CTA per SM, W warps, each with a
+// private ring of S slots filled by cp.async.bulk and "consumed" by one 16-byte LDS per lane.  Upper bound for what
+// the ring structure itself can stream in a launch of this size.
+template <int S>
+__global__ void __launch_bounds__(1024, 1) stream_bulk_kernel(const uint8_t* __restrict__ src, long nchunks, int chunk, unsigned* sink) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(smem) + warp * S * 8;
+    const int bar_bytes = (W * S * 8 + 15) & ~15;
+    uint8_t* ring = smem + bar_bytes + (size_t)warp * S * chunk;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+    if (lane == 0) {
+        for (int s = 0; s < S; s++) mbar_init(bar_u32 + 8 * s, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+    const long c0 = nchunks * blockIdx.x / gridDim.x, c1 = nchunks * (blockIdx.x + 1) / gridDim.x;
+    long ci = c0 + warp;
+    int slot_i = 0, slot_u = 0;
+    uint32_t phase = 0;
+    unsigned acc = 0;
+    auto issue = [&]() {
+        if (ci < c1) {
+            if (lane == 0) {
+                mbar_expect_tx(bar_u32 + 8 * slot_i, (uint32_t)chunk);
+                bulk_g2s(ring_u32 + slot_i * chunk, src + ci * chunk, (uint32_t)chunk, bar_u32 + 8 * slot_i);
+            }
+            ci += W;
+            slot_i = (slot_i + 1 == S) ? 0 : slot_i + 1;
+        }
+    };
+    for (int s = 0; s < S; s++) issue();
+    for (long c = c0 + warp; c < c1; c += W) {
+        mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
+        phase ^= 1u << slot_u;
+        const uint4 v = *reinterpret_cast<const uint4*>(ring + slot_u * chunk + lane * 16);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+        __syncwarp();
+        slot_u = (slot_u + 1 == S) ? 0 : slot_u + 1;
+        issue();
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
 }  // namespace ktb
 
 extern "C" int ktb200_debug_stream_read(const void* src, long bytes, int mode, int unroll, int ctas_per_sm, int chunk_bytes,
@@ -92,6 +137,22 @@ extern "C" int ktb200_debug_stream_read(const void* src, long bytes, int mode, i
     KTB_CUDA_CHECK(cudaEventCreate(&e1));
     const int grid = num_sms(dev) * (ctas_per_sm > 0 ? ctas_per_sm : 2);
     const long n16 = bytes / 16;
+    if (mode == 2) {   // unroll = ring slots, ctas_per_sm = warps per CTA
+        const int W = ctas_per_sm > 0 ? (ctas_per_sm > 32 ? 32 : ctas_per_sm) : 16, S = unroll >= 4 ? 4 : (unroll == 3 ? 3 : 2);
+        const size_t smem = (((size_t)W * S * 8 + 15) & ~(size_t)15) + (size_t)W * S * chunk_bytes;
+        if (chunk_bytes % 16 || smem > 232448 - 256) { set_error("stream probe: ring does not fit"); cudaEventDestroy(e0); cudaEventDestroy(e1); return KTB200_EINVAL; }
+        const long nchunks = bytes / chunk_bytes;
+        auto k = S == 4 ? stream_bulk_kernel<4> : (S == 3 ? stream_bulk_kernel<3> : stream_bulk_kernel<2>);
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KTB_CUDA_CHECK(cudaEventRecord(e0, s));
+        k<<<num_sms(dev), W * 32, smem, s>>>(reinterpret_cast<const uint8_t*>(src), nchunks, chunk_bytes, sink);
+        KTB_LAUNCH_CHECK();
+        KTB_CUDA_CHECK(cudaEventRecord(e1, s));
+        KTB_CUDA_CHECK(cudaEventSynchronize(e1));
+        if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return KTB200_OK;
+    }
     KTB_CUDA_CHECK(cudaEventRecord(e0, s));
     if (unroll >= 8) stream_read_kernel<8><<<grid, 256, 0, s>>>((const uint4*)src, n16, mode, chunk_bytes / 16, sink);
     else if (unroll >= 4) stream_read_kernel<4><<<grid, 256, 0, s>>>((const uint4*)src, n16, mode, chunk_bytes / 16, sink);
