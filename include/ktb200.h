@@ -199,6 +199,27 @@ int ktb200_moe_gate_forward(const ktb200_gate_config* cfg, int qlen, const void*
                             float* w_dev, float* logits_dev, const int* bsz_tensor_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The whole MoE block of a decoder layer in ONE call — KDeepseekV3MoE.forward
+ * (archive/ktransformers/operators/experts.py:972-1012):
+ *     topk_idx, topk_weight = self.gate(hidden_states)          (models/modeling_deepseek_v3.py:430-481)
+ *     y = self.experts(hidden_states, topk_idx, topk_weight)    (CPU MOE: operators/llamafile/moe.cpp:146-245)
+ *     y += self.shared_experts(identity)                        (n_shared_experts is not None)
+ * For decode batches (qlen <= 8) of Q4_K gate/up + Q6_K or Q4_K down experts with rows of 4096..8192 columns this is
+ * ONE persistent cooperative launch (router GEMV, grid barrier, top-k in every CTA, gate/up, grid barrier, down +
+ * combine; weights stream through the copy engine across the barriers); any other configuration runs as
+ * ktb200_moe_gate_forward + ktb200_moe_forward_shared.  Results are bit-identical between the two.
+ * idx_dev int64 [qlen][top_k] and w_dev fp32 [qlen][top_k] receive the routing (as from ktb200_moe_gate_forward).
+ * `shared` may be NULL.  The first call per device allocates scratch: make it before CUDA-graph capture.
+ * ------------------------------------------------------------------------------------------ */
+int ktb200_moe_block_forward(const ktb200_gate_config* gate, ktb200_moe* moe, ktb200_mlp* shared, int qlen,
+                             const void* input_dev, void* output_dev, int64_t* idx_dev, float* w_dev,
+                             const int* bsz_tensor_dev, void* stream);
+/* HOST-buffer form (pinned host tensors in / out like the reference's CPU operator, experts.py:293-318): copies the
+ * tokens up, runs the block, copies output (+ routing when idx_host / w_host are non-NULL) back, synchronises. */
+int ktb200_moe_block_forward_host(const ktb200_gate_config* gate, ktb200_moe* moe, ktb200_mlp* shared, int qlen,
+                                  const void* input_host, void* output_host, int64_t* idx_host, float* w_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Absorbed-MLA paged decode attention.  Replaces MLAWrapper.run / BatchMLAPagedAttentionWrapper
  * (archive/ktransformers/operators/flashinfer_wrapper.py:117-161; attention.py:419-447) and the
  * Triton split-KV decode (triton_attention.py:358-385).

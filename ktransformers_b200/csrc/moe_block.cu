@@ -1,0 +1,568 @@
+// The whole MoE block of one decoder layer in ONE persistent launch:
+//     router GEMV + grouped top-k  ->  gate/up of the selected (and the shared) experts  ->  down + weighted combine
+// Replaces KDeepseekV3MoE.forward (archive/ktransformers/operators/experts.py:972-1012): `topk_idx, topk_weight =
+// self.gate(x)` (models/modeling_deepseek_v3.py:430-481), `y = self.experts(x, topk_idx, topk_weight)` (the CPU MOE,
+// operators/llamafile/moe.cpp:146-245) and `y += self.shared_experts(identity)`.
+//
+// Why one kernel: a launch that streams ~100-150 MB lasts 25-30 us on a B200 of which ~6 us are fixed cost (launch
+// gap, pipeline ramp, activation prologue, tail) — profiles/probe_bulk.txt: the bare copy ring needs 27.3 us for the
+// gate/up bytes that take 21 us at the sustained rate.  Three launches per layer pay that three times.  Here the 148
+// CTAs (one per SM, cooperative launch) stay resident for the whole layer, separate the phases with two grid-wide
+// barriers, and keep the copy engine busy ACROSS them:
+//   * before the router's barrier every warp has already requested its first shared-expert rows (they do not depend
+//     on the routing), so the top-k selection and the barrier latency are covered by bytes in flight;
+//   * before the gate/up -> down barrier every warp has already requested its first down tiles (they depend on the
+//     expert ids only, not on the activations).
+// The selection runs redundantly in every CTA (128 threads, ~2 us, from the same partial sums in the same order):
+// no second barrier and no global round trip for the ids.
+//
+// Arithmetic, summation orders and rounding are exactly those of the separate kernels (gate.cuh, gemv_bulk.cuh):
+// the fused launch is bit-identical to ktb200_moe_gate_forward + ktb200_moe_forward_shared (tests/test_gpu_parity.py).
+#include <cstdlib>
+
+#include "gate.cuh"
+#include "gemv_bulk.cuh"
+#include "handles.cuh"
+
+namespace ktb {
+
+constexpr int kBlockWarps = 15;    // 480 threads -> 128 registers; 15 x 13440-byte rings + staging = 227 KB
+constexpr int kBlockMaxTokens = 8;
+
+struct BlockParams {
+    GateParams g;                        // router (W, bias, partial scratch, idx / w / logits outputs, x)
+    const void *w_gate, *w_up, *w_down;  // routed experts [n_local][...]
+    const void *s_gate, *s_up, *s_down;  // shared expert (null: none)
+    int n_local, id_offset;              // this shard owns expert ids [id_offset, id_offset + n_local)
+    int H, I, k;
+    int hidden_type, use_silu;
+    float* inter;                        // [T][ns][I] fp32
+    void* out;                           // [T][H]
+    unsigned* sync;                      // [0] barrier counter, [1] exit counter; both zero between launches
+    int nrows_max;                       // output rows per CTA (stride of the `partial` staging)
+    int region_a;                        // bytes of the aliased activation staging
+    int ring_bytes;                      // per-warp ring
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs of the (co-resident) grid; `gen` counts the barriers this CTA has passed
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& gen) {
+    __syncthreads();
+    gen++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = gen * gridDim.x;
+        while (ld_acquire_u32(counter) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 load_x4(const void* x, long i4, int type) {
+    if (type == KTB200_TYPE_F32) return reinterpret_cast<const float4*>(x)[i4];
+    const uint2 v = reinterpret_cast<const uint2*>(x)[i4];
+    if (type == KTB200_TYPE_BF16)
+        return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                           __uint_as_float(v.y & 0xffff0000u));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shared-memory layout (dynamic):
+//   [BlockShared]  ids / weights / work list of the current token
+//   [region A]     aliased over the phases:  {x int8 staging | selection scratch}  then  {a int8 staging}
+//   [partial]      [nrows_max][ns] fp32 down results before the weighted combine
+//   [mbarriers]    W x 3
+//   [rings]        W x ring_bytes   (3 gate/up rows or 2 down tiles per warp)
+struct BlockShared {
+    int64_t ids[32];
+    float w[32];
+    int vs[36];      // work list: slot indices this shard computes (the shared expert, slot k, first)
+    int nv;
+    unsigned skip;   // bit j: routed slot j is not owned by this shard
+};
+constexpr int kBlockSharedBytes = (sizeof(BlockShared) + 15) & ~15;
+
+struct BlockLay {
+    uint8_t *xq, *aq;
+    int16_t *xbs, *abs_;
+    float *xdx, *adx, *sel, *partial;
+    size_t ring_off;   // mbarriers, then the rings
+};
+template <int KBS>
+__device__ __forceinline__ BlockLay block_layout(const BlockParams& p, uint8_t* smem) {
+    const int nblk = p.H / QK_K, nb = p.I / QK_K, ns = p.k + (p.s_gate ? 1 : 0);
+    uint8_t* a = smem + kBlockSharedBytes;
+    BlockLay L;
+    L.xq = a;
+    L.xbs = reinterpret_cast<int16_t*>(a + (size_t)nblk * kActBlkStride);
+    L.xdx = reinterpret_cast<float*>(a + (size_t)nblk * (kActBlkStride + 16));
+    L.sel = reinterpret_cast<float*>(a + (((size_t)nblk * (kActBlkStride + 16 + 4) + 15) & ~(size_t)15));
+    L.aq = a;
+    L.abs_ = reinterpret_cast<int16_t*>(a + (size_t)ns * nb * kActBlkStride);
+    L.adx = reinterpret_cast<float*>(a + (size_t)ns * nb * (kActBlkStride + 2 * KBS));
+    L.partial = reinterpret_cast<float*>(a + p.region_a);
+    L.ring_off = ((size_t)kBlockSharedBytes + p.region_a + (size_t)p.nrows_max * ns * 4 + 15) & ~(size_t)15;
+    return L;
+}
+
+// ---- cold phases: their own register allocation, called once per token ------------------------------------------
+// x -> Q8_K (padded staging)
+__device__ __noinline__ void blk_quantize_x(const BlockParams& p, int t) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const BlockLay L = block_layout<8>(p, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5, nblk = p.H / QK_K;
+    for (int g0 = warp; g0 < nblk; g0 += W * 2) {
+        float x[2][8];
+        bool live[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int b = g0 + i * W;
+            live[i] = b < nblk;
+            if (live[i]) load_block8(p.g.x, (long)t * p.H + (long)b * QK_K + lane * 8, p.hidden_type, x[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int b = g0 + i * W;
+            if (live[i]) warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(L.xq + (size_t)b * kActBlkStride), L.xdx + b, nullptr, L.xbs + b * 8);
+        }
+    }
+}
+
+// router partial sums: unit = (expert row e, column split s); same loop and summation order as gate_dot<1> (gate.cuh)
+__device__ __noinline__ void blk_router(const BlockParams& p, int t) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int E = p.g.E, S = p.g.S, n4 = p.H / 4;
+    const int gw = blockIdx.x * W + warp, tw = gridDim.x * W;
+    for (int u = gw; u < E * S; u += tw) {
+        const int s = u / E, e = u - s * E;
+        const int c0 = (int)((long)n4 * s / S), nc4 = (int)((long)n4 * (s + 1) / S) - c0;
+        const float4* wrow = reinterpret_cast<const float4*>(p.g.W + (long)e * p.H) + c0;
+        const long xbase = (long)t * n4 + c0;
+        float acc = 0.f;
+        for (int cb = lane; cb < nc4; cb += 32 * 8) {
+            float4 w[8], xv[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int c = cb + 32 * q;
+                if (c < nc4) { w[q] = __ldg(wrow + c); xv[q] = load_x4(p.g.x, xbase + c, p.hidden_type); }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int c = cb + 32 * q;
+                if (c < nc4) {
+                    acc = fmaf(w[q].x, xv[q].x, acc);
+                    acc = fmaf(w[q].y, xv[q].y, acc);
+                    acc = fmaf(w[q].z, xv[q].z, acc);
+                    acc = fmaf(w[q].w, xv[q].w, acc);
+                }
+            }
+        }
+        const float v = warp_sum(acc);
+        if (lane == 0) p.g.partial[((long)t * S + s) * E + e] = v;
+    }
+}
+
+// top-k selection (first 4 warps of EVERY CTA, identical results), work-list compaction, routing outputs (CTA 0)
+__device__ __noinline__ void blk_select(const BlockParams& p, int t) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
+    const BlockLay L = block_layout<8>(p, smem);
+    const int k = p.k;
+    if ((threadIdx.x >> 5) < kGateWarps) {
+        GateParams gp = p.g;
+        if (blockIdx.x != 0) gp.logits_out = nullptr;
+        gate_select_token<1>(gp, t, L.sel, sh.ids, sh.w);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned sk = 0;
+        int nv = p.s_gate ? 1 : 0;
+        for (int j = 0; j < k; j++) {
+            const long e = (long)sh.ids[j] - p.id_offset;
+            if (e < 0 || e >= p.n_local) sk |= 1u << j; else sh.vs[nv++] = j;
+        }
+        sh.nv = nv;
+        sh.skip = sk;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < k) {
+        p.g.idx[(long)t * k + threadIdx.x] = sh.ids[threadIdx.x];
+        p.g.w[(long)t * k + threadIdx.x] = sh.w[threadIdx.x];
+    }
+    __syncthreads();
+}
+
+// a (fp32 phase-1 output, written by all CTAs) -> Q8_K
+template <int KBS>
+__device__ __noinline__ void blk_quantize_a(const BlockParams& p, int t) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const BlockShared& sh = *reinterpret_cast<const BlockShared*>(smem);
+    const BlockLay L = block_layout<KBS>(p, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int k = p.k, nb = p.I / QK_K, ns = k + (p.s_gate ? 1 : 0);
+    const unsigned skip = sh.skip;
+    const int totalb = ns * nb;
+    for (int g0 = warp; g0 < totalb; g0 += W * 5) {
+        float x[5][8];
+        bool live[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const int gb = g0 + i * W;
+            live[i] = gb < totalb;
+            if (live[i]) {
+                const int r = gb / nb, b = gb - r * nb;
+                live[i] = r == k || !((skip >> r) & 1u);
+                if (live[i]) {   // written by other SMs in this launch: read at L2
+                    const float4* src = reinterpret_cast<const float4*>(p.inter + ((long)t * ns + r) * p.I + (long)b * QK_K + lane * 8);
+                    const float4 v0 = __ldcg(src), v1 = __ldcg(src + 1);
+                    x[i][0] = v0.x; x[i][1] = v0.y; x[i][2] = v0.z; x[i][3] = v0.w;
+                    x[i][4] = v1.x; x[i][5] = v1.y; x[i][6] = v1.z; x[i][7] = v1.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const int gb = g0 + i * W;
+            if (live[i])
+                warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(L.aq + (size_t)gb * kActBlkStride), L.adx + gb,
+                                        KBS == 16 ? L.abs_ + gb * 16 : nullptr, KBS == 8 ? L.abs_ + gb * 8 : nullptr);
+        }
+    }
+}
+
+// weighted accumulation over the k experts IN expert_ids ORDER (moe.cpp:222-236), one FMA per expert; then the
+// shared expert as a second rounded term (experts.py:1011)
+template <int KBS>
+__device__ __noinline__ void blk_combine(const BlockParams& p, int t) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const BlockShared& sh = *reinterpret_cast<const BlockShared*>(smem);
+    const BlockLay L = block_layout<KBS>(p, smem);
+    const int k = p.k, ns = k + (p.s_gate ? 1 : 0);
+    const int quads = p.H / 4;
+    const int q0 = (int)((long)quads * blockIdx.x / gridDim.x), nrows = ((int)((long)quads * (blockIdx.x + 1) / gridDim.x) - q0) * 4;
+    const unsigned skip = sh.skip;
+    for (int hl = threadIdx.x; hl < nrows; hl += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < k; j++) {
+            if ((skip >> j) & 1u) continue;
+            acc = __fmaf_rn(L.partial[hl * ns + j], sh.w[j], acc);
+        }
+        if (p.s_gate) acc = round_hidden(acc, p.hidden_type) + round_hidden(L.partial[hl * ns + k], p.hidden_type);
+        store_hidden(p.out, (long)t * p.H + q0 * 4 + hl, p.hidden_type, acc);
+    }
+}
+
+template <class DownFmt>
+__global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __grid_constant__ BlockParams p) {
+    constexpr int RW = 4, SU = 3, SD = 2;   // rows per down item, ring depth in rows (gate/up) and in tiles (down)
+    extern __shared__ __align__(16) uint8_t smem[];
+    BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    int Teff = p.g.T;
+    if (p.g.bsz) Teff = min(Teff, *p.g.bsz);
+    const int k = p.k;
+    const bool has_shared = p.s_gate != nullptr;
+    uint32_t bar_u32, ring_u32;
+    {
+        const BlockLay L = block_layout<DownFmt::kBs>(p, smem);
+        const int bar_bytes = (W * SU * 8 + 15) & ~15;
+        bar_u32 = (uint32_t)__cvta_generic_to_shared(smem + L.ring_off) + warp * SU * 8;
+        ring_u32 = (uint32_t)__cvta_generic_to_shared(smem + L.ring_off + bar_bytes) + warp * p.ring_bytes;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < SU; s++) mbar_init(bar_u32 + 8 * s, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (threadIdx.x == 0 && has_shared) sh.vs[0] = k;   // the shared expert is always the first entry of the work list
+    uint32_t phase = 0;   // bit s = parity the next use of barrier s waits for
+    unsigned gen = 0;
+
+  for (int t = 0; t < Teff; t++) {
+    __syncthreads();   // previous token: region A, partial and the work list are free (first token: barriers initialised)
+    {
+        // ------------------------------------------------------------ gate/up: rows [ur0, ur0 + nr) of EVERY work-list entry
+        // unit u of this CTA (u = warp, warp + W, ...) = (entry u / nr, row ur0 + u % nr); 2 rows (gate, up) each
+        const int nblk = p.H / QK_K, row_bytes = nblk * SZ_Q4_K;
+        const int ur0 = (int)((long)p.I * blockIdx.x / gridDim.x), nr = (int)((long)p.I * (blockIdx.x + 1) / gridDim.x) - ur0;
+        int ivi = warp / nr, irr = warp - ivi * nr, isub = 0;   // issue cursor, rows requested
+        int cvi = ivi, crr = irr, csub = 0;                     // consume cursor, rows consumed
+        int vi_limit = has_shared ? 1 : 0;                      // entries of the work list known so far
+        int slot_i = 0, slot_u = 0;
+        auto issue_u = [&]() {
+            if (ivi < vi_limit && isub - csub < SU) {
+                if (lane == 0) {
+                    const int s = sh.vs[ivi];
+                    const bool second = isub & 1;
+                    const uint8_t* src;
+                    if (s == k) {
+                        src = reinterpret_cast<const uint8_t*>(second ? p.s_up : p.s_gate) + (long)(ur0 + irr) * row_bytes;
+                    } else {
+                        const long e = (long)sh.ids[s] - p.id_offset;
+                        src = reinterpret_cast<const uint8_t*>(second ? p.w_up : p.w_gate) + (e * p.I + ur0 + irr) * row_bytes;
+                    }
+                    const uint32_t bar = bar_u32 + 8 * slot_i;
+                    mbar_expect_tx(bar, (uint32_t)row_bytes);
+                    bulk_g2s(ring_u32 + slot_i * row_bytes, src, (uint32_t)row_bytes, bar);
+                }
+                isub++;
+                if (!(isub & 1)) {
+                    irr += W;
+                    while (irr >= nr) { irr -= nr; ivi++; }
+                }
+                slot_i = (slot_i + 1 == SU) ? 0 : slot_i + 1;
+            }
+        };
+        // the shared expert's rows do not depend on the routing: request them before the router's barrier
+#pragma unroll
+        for (int s = 0; s < SU; s++) issue_u();
+        blk_quantize_x(p, t);
+        blk_router(p, t);
+        grid_sync(p.sync, gen);
+        blk_select(p, t);
+        const int nv = sh.nv;
+        vi_limit = nv;
+#pragma unroll
+        for (int s = 0; s < SU; s++) issue_u();
+
+        const BlockLay L = block_layout<DownFmt::kBs>(p, smem);
+        const uint8_t* ring = smem + (ring_u32 - (uint32_t)__cvta_generic_to_shared(smem));
+        const int ns = k + (has_shared ? 1 : 0);
+        float acc_first = 0.f;
+        while (cvi < nv) {
+            mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
+            phase ^= 1u << slot_u;
+            const uint8_t* row0 = ring + slot_u * row_bytes;
+            float acc = 0.f;
+            if (lane < nblk)
+                acc = q4k_block_dot(row0 + lane * SZ_Q4_K, L.xq + (size_t)lane * kActBlkStride,
+                                    *reinterpret_cast<const uint4*>(L.xbs + lane * 8), L.xdx[lane]);
+            __syncwarp();
+            slot_u = (slot_u + 1 == SU) ? 0 : slot_u + 1;
+            csub++;
+            issue_u();
+            if (csub & 1) { acc_first = acc; continue; }
+            float g = acc_first, uu = acc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                g += __shfl_xor_sync(0xffffffffu, g, o);
+                uu += __shfl_xor_sync(0xffffffffu, uu, o);
+            }
+            if (lane == 0) p.inter[((long)t * ns + sh.vs[cvi]) * p.I + ur0 + crr] = (p.use_silu ? act_silu(g) : act_relu(g)) * uu;
+            crr += W;
+            while (crr >= nr) { crr -= nr; cvi++; }
+        }
+    }
+    {
+        // ------------------------------------------------------------ down: row quads [q0, q0 + nquads) of every entry
+        const int nb = p.I / QK_K, nrb = RW * nb, item_bytes = nrb * DownFmt::kBlockBytes;
+        const int quads = p.H / RW;
+        const int q0 = (int)((long)quads * blockIdx.x / gridDim.x), nquads = (int)((long)quads * (blockIdx.x + 1) / gridDim.x) - q0;
+        const int nv = sh.nv;
+        int ni = nquads * nv - warp;
+        ni = ni > 0 ? (ni + W - 1) / W : 0;
+        int dvi = 0, dq = 0, dss = 0;
+        if (ni > 0) { dvi = warp / nquads; dq = warp - dvi * nquads; }
+        int evi = dvi, eq = dq;
+        int dslot_i = 0, dslot_u = 0;
+        auto issue_d = [&]() {
+            if (dss < ni) {
+                if (lane == 0) {
+                    const int j = sh.vs[dvi];
+                    long row = (long)(q0 + dq) * RW;
+                    const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w_down);
+                    if (j == k) wbase = reinterpret_cast<const uint8_t*>(p.s_down);
+                    else row += ((long)sh.ids[j] - p.id_offset) * p.H;
+                    const uint32_t bar = bar_u32 + 8 * dslot_i;
+                    mbar_expect_tx(bar, (uint32_t)item_bytes);
+                    bulk_g2s(ring_u32 + dslot_i * item_bytes, wbase + (row >> 2) * item_bytes, (uint32_t)item_bytes, bar);
+                }
+                dss++;
+                dq += W;
+                while (dq >= nquads) { dq -= nquads; dvi++; }
+                dslot_i = (dslot_i + 1 == SD) ? 0 : dslot_i + 1;
+            }
+        };
+        // the first tiles depend on the expert ids only: request them before the barrier
+#pragma unroll
+        for (int s = 0; s < SD; s++) issue_d();
+        grid_sync(p.sync, gen);   // every row of `inter` is written and visible
+        blk_quantize_a<DownFmt::kBs>(p, t);
+        __syncthreads();
+
+        const BlockLay L = block_layout<DownFmt::kBs>(p, smem);
+        const uint8_t* ring = smem + (ring_u32 - (uint32_t)__cvta_generic_to_shared(smem));
+        const int ns = k + (has_shared ? 1 : 0);
+        for (int n = 0; n < ni; n++) {
+            mbar_wait(bar_u32 + 8 * dslot_u, (phase >> dslot_u) & 1u);
+            phase ^= 1u << dslot_u;
+            const uint8_t* sl = ring + dslot_u * item_bytes;
+            const int j = sh.vs[evi];
+            float res;
+            if (nrb == 32) {   // 4 rows x 8 blocks: lane = (rw, blk)
+                const int ab = j * nb + (lane & 7);
+                float v = DownFmt::dot(sl, lane, nrb, L.aq + (size_t)ab * kActBlkStride, L.abs_ + ab * DownFmt::kBs, L.adx[ab]);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                res = v;
+            } else {
+                float acc[RW] = {0.f, 0.f, 0.f, 0.f};
+                for (int f = lane; f < nrb; f += 32) {
+                    const int rw = f / nb, blk = f - rw * nb;
+                    const int ab = j * nb + blk;
+                    const float val = DownFmt::dot(sl, f, nrb, L.aq + (size_t)ab * kActBlkStride, L.abs_ + ab * DownFmt::kBs, L.adx[ab]);
+                    acc[0] += rw == 0 ? val : 0.f; acc[1] += rw == 1 ? val : 0.f; acc[2] += rw == 2 ? val : 0.f; acc[3] += rw == 3 ? val : 0.f;
+                }
+                res = warp_reduce4(acc[0], acc[1], acc[2], acc[3], lane);
+            }
+            __syncwarp();
+            dslot_u = (dslot_u + 1 == SD) ? 0 : dslot_u + 1;
+            issue_d();
+            if ((lane & 7) == 0) L.partial[(eq * RW + (lane >> 3)) * ns + j] = res;
+            eq += W;
+            while (eq >= nquads) { eq -= nquads; evi++; }
+        }
+        __syncthreads();
+        blk_combine<DownFmt::kBs>(p, t);
+    }
+  }  // tokens
+
+    // leave the barrier words zeroed for the next launch / graph replay: the last CTA to get here resets them
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(p.sync + 1, 1u);
+        if (prev == gridDim.x - 1) {
+            p.sync[0] = 0;
+            p.sync[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// per-device scratch: router partial sums [kBlockMaxTokens][S<=8][E<=512] + the two barrier words
+static float* g_bpartial[64] = {nullptr};
+static unsigned* g_bsync[64] = {nullptr};
+
+static int env_fused() {
+    static int v = [] { const char* e = getenv("KTB200_FUSED"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
+}  // namespace ktb
+
+using namespace ktb;
+
+extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe* m, ktb200_mlp* sh, int qlen, const void* input,
+                                        void* output, int64_t* idx, float* w, const int* bsz, void* stream) {
+    if (!gc || !m || !input || !output || !idx || !w) { set_error("null pointer"); return KTB200_EINVAL; }
+    if (!m->loaded) { set_error("Not Loaded"); return KTB200_ESTATE; }
+    if (sh && !sh->loaded) { set_error("shared expert: Not Loaded"); return KTB200_ESTATE; }
+    if (qlen <= 0) return KTB200_OK;
+    const ktb200_moe_config& c = m->cfg;
+    const int k = gc->top_k;
+    if (gc->hidden_size != c.hidden_size || gc->hidden_type != c.hidden_type) { set_error("moe_block: gate and experts disagree on the hidden size / type"); return KTB200_EINVAL; }
+    if (k <= 0 || k > c.routed_expert_num) { set_error("moe_block: top_k=%d outside (0, routed_expert_num=%d]", k, c.routed_expert_num); return KTB200_EINVAL; }
+    if (qlen > c.group_max_len) { set_error("forward: qlen=%d exceeds group_max_len=%d", qlen, c.group_max_len); return KTB200_EINVAL; }
+
+    // ---- can the fused kernel take it?  otherwise: the separate launches (same results)
+    const FmtId fd = pick_fmt(c.down_type, m->down_layout);
+    const bool sh_ok = !sh || (sh->H == c.hidden_size && sh->I == c.intermediate_size && sh->hidden_type == c.hidden_type &&
+                               sh->gate_type == c.gate_type && sh->up_type == c.up_type && sh->down_type == c.down_type &&
+                               sh->gu_soa == m->gu_soa && sh->down_layout == m->down_layout && c.use_silu);
+    const int nblk = c.hidden_size / QK_K, nb = c.intermediate_size / QK_K;
+    bool fused = env_fused() && qlen <= kBlockMaxTokens && sh_ok && c.gate_type == KTB200_TYPE_Q4_K && c.up_type == KTB200_TYPE_Q4_K &&
+                 (fd == FMT_Q6K4T || fd == FMT_Q4K) && nblk >= 16 && nblk <= 32 && c.hidden_size % 4 == 0 && k <= 31 &&
+                 gc->n_experts <= kGateThreads * kGateEPT && gc->n_experts > 0 && gc->n_group >= 1 && gc->n_group <= 32 &&
+                 gc->n_experts % gc->n_group == 0 && gc->topk_group >= 1 && gc->topk_group <= gc->n_group && gc->weight &&
+                 gc->scoring >= 0 && gc->scoring <= 1 && gc->topk_method >= 0 && gc->topk_method <= 2 && k <= gc->n_experts;
+    DeviceGuard guard(m->device);
+    const int dev = m->device, d = dev & 63;
+    cudaStream_t s = (cudaStream_t)stream;
+    BlockParams p{};
+    size_t smem = 0;
+    int W = 0, G = 0;
+    if (fused) {
+        const int ns = k + (sh ? 1 : 0);
+        const int kbs = fd == FMT_Q6K4T ? 16 : 8, bbytes = fd == FMT_Q6K4T ? SZ_Q6_K : SZ_Q4_K;
+        const size_t item = (size_t)4 * nb * bbytes, row = (size_t)nblk * SZ_Q4_K;
+        G = num_sms(dev);
+        if (G > c.intermediate_size) G = c.intermediate_size;
+        if (G > c.hidden_size / 4) G = c.hidden_size / 4;
+        const int quads = c.hidden_size / 4;
+        p.nrows_max = ((quads + G - 1) / G) * 4;
+        const size_t xq = (((size_t)nblk * (kActBlkStride + 16 + 4) + 15) & ~(size_t)15) + ((size_t)2 * gc->n_experts + 32 + 4 * kGateWarps) * 4;
+        const size_t aqb = (size_t)ns * nb * (kActBlkStride + 2 * kbs + 4);
+        p.region_a = (int)(((xq > aqb ? xq : aqb) + 15) & ~(size_t)15);
+        size_t ring = 3 * row > 2 * item ? 3 * row : 2 * item;
+        p.ring_bytes = (int)ring;
+        size_t base = (size_t)kBlockSharedBytes + p.region_a + (size_t)p.nrows_max * ns * 4;
+        base = (base + 15) & ~(size_t)15;
+        W = base + 64 < 232448 - 1024 ? (int)((232448 - 1024 - base - 16) / (ring + 24)) : 0;
+        if (W > kBlockWarps) W = kBlockWarps;
+        smem = base + (((size_t)W * 3 * 8 + 15) & ~(size_t)15) + (size_t)W * ring;
+        if (W < 8 || c.hidden_size % 4 || item % 16 || c.intermediate_size < 1) fused = false;
+    }
+    if (!fused) {
+        int rc = ktb200_moe_gate_forward(gc, qlen, input, idx, w, nullptr, bsz, stream);
+        if (rc) return rc;
+        return ktb200_moe_forward_shared(m, sh, qlen, k, idx, w, input, output, bsz, stream);
+    }
+
+    // router split: the same S as ktb200_moe_gate_forward so that the partial sums (and the routing) are bit-identical
+    const int row_ctas = (gc->n_experts + kGateWarps - 1) / kGateWarps;
+    int S = (2 * num_sms(dev) + row_ctas - 1) / row_ctas;
+    if (S < 1) S = 1;
+    if (S > 8) S = 8;
+    while (S > 1 && gc->hidden_size / 4 / S < 64) S--;
+    if (!g_bpartial[d]) {   // not capturable: call once before graph capture (the first call allocates)
+        KTB_CUDA_CHECK(cudaMalloc(&g_bpartial[d], (size_t)kBlockMaxTokens * 8 * kGateThreads * kGateEPT * sizeof(float)));
+        KTB_CUDA_CHECK(cudaMalloc(&g_bsync[d], 2 * sizeof(unsigned)));
+        KTB_CUDA_CHECK(cudaMemset(g_bsync[d], 0, 2 * sizeof(unsigned)));
+    }
+    p.g = GateParams{gc->weight, input, gc->hidden_type, gc->n_experts, gc->hidden_size, qlen, S, k, gc->n_group, gc->topk_group,
+                     gc->scoring, gc->topk_method, gc->norm_topk_prob, gc->routed_scaling_factor, gc->bias, g_bpartial[d], nullptr,
+                     idx, w, bsz, nullptr};
+    p.w_gate = c.gate_proj; p.w_up = c.up_proj; p.w_down = c.down_proj;
+    p.s_gate = sh ? sh->gate : nullptr; p.s_up = sh ? sh->up : nullptr; p.s_down = sh ? sh->down : nullptr;
+    p.n_local = c.expert_num; p.id_offset = c.expert_id_offset;
+    p.H = c.hidden_size; p.I = c.intermediate_size; p.k = k; p.hidden_type = c.hidden_type; p.use_silu = c.use_silu;
+    p.inter = m->inter; p.out = output; p.sync = g_bsync[d];
+
+    void* args[] = {&p};
+    const void* fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T> : (const void*)moe_block_kernel<BulkQ4K>;
+    KTB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KTB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(W * 32), args, smem, s));
+    count_launch(1);
+    return KTB200_OK;
+}
+
+// Host-buffer form of the same call (the shape of the reference's CPU operator: pinned host tensors in, host tensors
+// out, cpuinfer.submit + sync — experts.py:293-318): H2D of the tokens, the block, D2H of the result and the routing.
+extern "C" int ktb200_moe_block_forward_host(const ktb200_gate_config* gc, ktb200_moe* m, ktb200_mlp* sh, int qlen, const void* input,
+                                             void* output, int64_t* idx, float* w, void* stream) {
+    if (!gc || !m || !input || !output) { set_error("null pointer"); return KTB200_EINVAL; }
+    if (qlen <= 0) return KTB200_OK;
+    const ktb200_moe_config& c = m->cfg;
+    const int k = gc->top_k;
+    if (qlen > c.group_max_len || k <= 0 || k > c.routed_expert_num) { set_error("forward_host: qlen/k out of range"); return KTB200_EINVAL; }
+    DeviceGuard guard(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t hid = (size_t)qlen * c.hidden_size * type_size(c.hidden_type);
+    KTB_CUDA_CHECK(cudaMemcpyAsync(m->in_d, input, hid, cudaMemcpyHostToDevice, s));
+    int rc = ktb200_moe_block_forward(gc, m, sh, qlen, m->in_d, m->out_d, m->ids_d, m->w_d, nullptr, stream);
+    if (rc) return rc;
+    KTB_CUDA_CHECK(cudaMemcpyAsync(output, m->out_d, hid, cudaMemcpyDeviceToHost, s));
+    if (idx) KTB_CUDA_CHECK(cudaMemcpyAsync(idx, m->ids_d, (size_t)qlen * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    if (w) KTB_CUDA_CHECK(cudaMemcpyAsync(w, m->w_d, (size_t)qlen * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    KTB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return KTB200_OK;
+}

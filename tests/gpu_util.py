@@ -170,6 +170,48 @@ def gate_forward(x, W, bias, top_k, n_group, topk_group, scoring=0, topk_method=
     return idx.cpu().numpy(), w.cpu().numpy(), (logits.cpu().numpy() if logits is not None else None)
 
 
+class Gate:
+    """ktb200_gate_config with device-resident router weights."""
+
+    def __init__(self, W, bias, top_k, n_group, topk_group, scoring=0, topk_method=0, norm=1, scale=2.5, hidden_type=0):
+        self.Wd = dev(W.astype(np.float32))
+        self.bd = dev(bias.astype(np.float32)) if bias is not None else None
+        self.top_k, self.E = top_k, W.shape[0]
+        self.cfg = native.GateConfig(W.shape[0], W.shape[1], top_k, n_group, topk_group, scoring, topk_method, norm, scale,
+                                     self.Wd.data_ptr(), self.bd.data_ptr() if self.bd is not None else None, hidden_type)
+
+
+def moe_block_forward(gate: "Gate", moe: "Moe", mlp, x, repeats=1, graph=False):
+    """ktb200_moe_block_forward -> (out, idx, w) as numpy; `repeats` back-to-back calls (the barrier words must reset),
+    optionally captured in a CUDA graph and replayed."""
+    lib = native.lib()
+    qlen = x.shape[0]
+    x_d = dev(x, TORCH_HID[moe.hidden_type] if moe.hidden_type == 30 else None)
+    out_d = torch.zeros((qlen, moe.H), dtype=TORCH_HID[moe.hidden_type], device="cuda")
+    idx = torch.zeros((qlen, gate.top_k), dtype=torch.int64, device="cuda")
+    w = torch.zeros((qlen, gate.top_k), dtype=torch.float32, device="cuda")
+
+    def call(st):
+        native.check(lib.ktb200_moe_block_forward(C.byref(gate.cfg), moe.h, mlp.h if mlp is not None else None, qlen, x_d.data_ptr(),
+                                                  out_d.data_ptr(), idx.data_ptr(), w.data_ptr(), None, st))
+    call(stream())
+    torch.cuda.synchronize()
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.graph(g, stream=side):
+            call(torch.cuda.current_stream().cuda_stream)
+        for _ in range(repeats):
+            g.replay()
+    else:
+        for _ in range(repeats - 1):
+            call(stream())
+    torch.cuda.synchronize()
+    o = out_d.cpu()
+    o = o.view(torch.int16).numpy().view(np.uint16) if moe.hidden_type == 30 else o.numpy()
+    return o, idx.cpu().numpy(), w.cpu().numpy()
+
+
 def mla_decode(q_nope, q_pe, kv_cache, page_table, kv_len, sm_scale, num_kv_splits=0):
     """numpy float32 arrays holding bf16 values -> (out [B,H,512] float32, lse [B,H])"""
     lib = native.lib()

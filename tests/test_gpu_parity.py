@@ -300,6 +300,51 @@ def test_gate_vs_oracle_full_shapes(E, H, k, ng, tg, scoring, method, norm, scal
     assert idx_b.shape == idx.shape and (idx_b >= 0).all() and (idx_b < E).all()
 
 
+# ------------------------------------------------------------------------------------------ fused MoE block
+@pytest.mark.parametrize("dt,hid,shared,offset,H,I", [
+    (Q6_K, BF16, True, 0, 4096, 512),      # V3-like: Q4_K gate/up, Q6_K (tile layout) down, shared expert fused as slot k
+    (Q6_K, F32, False, 0, 4096, 2048),     # no shared expert; 4 rows x 8 blocks down tiles
+    (Q4_K, BF16, True, 0, 8192, 512),      # Q4_K down, 32 blocks per gate/up row
+    (Q6_K, BF16, True, 8, 4096, 512),      # expert-parallel shard: owns ids 8..15 of 16, everything else is skipped
+    (Q6_K, BF16, True, 0, 1024, 512),      # rows too short for the persistent kernel -> separate launches behind the same call
+])
+def test_moe_block_single_launch_is_bit_identical_to_separate_launches(dt, hid, shared, offset, H, I):
+    """ktb200_moe_block_forward (router + experts + shared expert in ONE cooperative launch) must give exactly the bits
+    of ktb200_moe_gate_forward followed by ktb200_moe_forward_shared — which are the calls checked against the oracle."""
+    Eg, k, ng, tg = 16, 4, 4, 2
+    El = Eg - offset if offset else Eg
+    gate_w, up_w, down_w = _synth(Q4_K, El * I * H, 81), _synth(Q4_K, El * I * H, 82), _synth(dt, El * H * I, 83)
+    m = G.Moe(El, k, H, I, gate_w, up_w, down_w, Q4_K, Q4_K, dt, hid, offset=offset)
+    mlp = G.Mlp(H, I, _synth(Q4_K, I * H, 84), _synth(Q4_K, I * H, 85), _synth(dt, H * I, 86), Q4_K, Q4_K, dt, hid) if shared else None
+    rng = np.random.default_rng(H + I)
+    W = rng.standard_normal((Eg, H)).astype(np.float32)
+    bias = rng.standard_normal(Eg).astype(np.float32)
+    gate = G.Gate(W, bias, k, ng, tg, hidden_type=hid)
+    for qlen in (1, 3, 8, 9):      # 9 > 8 tokens: the call falls back to the separate launches
+        x = (rng.standard_normal((qlen, H)) / 10).astype(np.float32)
+        xin = x if hid == F32 else f32_to_bf16_bits(x)
+        n0 = native.launch_count()
+        out, idx, w = G.moe_block_forward(gate, m, mlp, xin)
+        fused = native.launch_count() - n0 == 1
+        assert fused == (H >= 4096 and qlen <= 8)
+        ridx, rw, _ = G.gate_forward(xin, W, bias, k, ng, tg, hidden_type=hid)
+        assert np.array_equal(idx, ridx) and np.array_equal(w, rw)
+        want = G.moe_forward_shared(m, mlp, ridx, rw, xin)
+        assert np.array_equal(out, want), f"qlen={qlen}"
+        if offset:
+            assert ((ridx < offset).any(axis=1)).any()          # some slots really are skipped in this case
+    # the barrier words reset themselves: repeated launches and CUDA-graph replays give the same bits
+    x = f32_to_bf16_bits((rng.standard_normal((2, H)) / 10).astype(np.float32)) if hid == BF16 else (rng.standard_normal((2, H)) / 10).astype(np.float32)
+    once = G.moe_block_forward(gate, m, mlp, x)
+    again = G.moe_block_forward(gate, m, mlp, x, repeats=5)
+    replay = G.moe_block_forward(gate, m, mlp, x, repeats=4, graph=True)
+    for a, b, c in zip(once, again, replay):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    m.close()
+    if mlp is not None:
+        mlp.close()
+
+
 # ------------------------------------------------------------------------------------------ MLA decode
 def _mla_case(rng, B, Hq, page_size, lens, shuffle_pages=True):
     from oracle.mla_oracle import bf16_round
