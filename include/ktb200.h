@@ -248,6 +248,11 @@ int ktb200_mla_kv_write(void* kv_cache, int page_size, const void* ckv, const vo
  * (the access shape of the expert GEMV).  Establishes the practical read ceiling next to MEASURED_PEAKS' copy figure. */
 int ktb200_debug_stream_read(const void* src_dev, long bytes, int mode, int unroll, int ctas_per_sm, int chunk_bytes,
                              void* stream, float* ms_out);
+/* mode 2 of the probe above: the bulk-copy ring of the expert kernels without arithmetic (unroll = ring slots,
+ * ctas_per_sm = warps per CTA).
+ * Phase trace of ktb200_moe_block_forward (profiles/block_trace.py): while trace_dev != NULL, thread 0 of every CTA
+ * writes %globaltimer at the phase boundaries into trace_dev[cta][16] (uint64, >= num_SMs * 16 entries). */
+void ktb200_debug_block_trace(unsigned long long* trace_dev);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,7 @@ __device__ __forceinline__ float fkey_inv(unsigned k) {
 // idx_out / w_out: where token t's top_k (id, weight) pairs go ([top_k] each; global or shared memory).
 template <int BAR>
 __device__ __forceinline__ void gate_sync() {
-    if (BAR == 0) gate_sync<BAR>();
+    if (BAR == 0) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(kGateThreads) : "memory");
 }
 template <int BAR>

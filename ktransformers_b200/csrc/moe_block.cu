@@ -42,6 +42,7 @@ struct BlockParams {
     int nrows_max;                       // output rows per CTA (stride of the `partial` staging)
     int region_a;                        // bytes of the aliased activation staging
     int ring_bytes;                      // per-warp ring
+    unsigned long long* trace;           // debug: [grid][16] globaltimer stamps of the phase boundaries (null: off)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -62,6 +63,14 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& gen) {
         __threadfence();
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void block_stamp(const BlockParams& p, int i) {
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[blockIdx.x * 16 + i] = t;
+    }
 }
 
 __device__ __forceinline__ float4 load_x4(const void* x, long i4, int type) {
@@ -285,6 +294,7 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
     if (threadIdx.x == 0 && has_shared) sh.vs[0] = k;   // the shared expert is always the first entry of the work list
     uint32_t phase = 0;   // bit s = parity the next use of barrier s waits for
     unsigned gen = 0;
+    block_stamp(p, 0);
 
   for (int t = 0; t < Teff; t++) {
     __syncthreads();   // previous token: region A, partial and the work list are free (first token: barriers initialised)
@@ -325,9 +335,13 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
 #pragma unroll
         for (int s = 0; s < SU; s++) issue_u();
         blk_quantize_x(p, t);
+        block_stamp(p, 1);
         blk_router(p, t);
+        block_stamp(p, 2);
         grid_sync(p.sync, gen);
+        block_stamp(p, 3);
         blk_select(p, t);
+        block_stamp(p, 4);
         const int nv = sh.nv;
         vi_limit = nv;
 #pragma unroll
@@ -360,6 +374,7 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
             crr += W;
             while (crr >= nr) { crr -= nr; cvi++; }
         }
+        if (p.trace) { __syncthreads(); block_stamp(p, 5); }
     }
     {
         // ------------------------------------------------------------ down: row quads [q0, q0 + nquads) of every entry
@@ -395,8 +410,10 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
 #pragma unroll
         for (int s = 0; s < SD; s++) issue_d();
         grid_sync(p.sync, gen);   // every row of `inter` is written and visible
+        block_stamp(p, 6);
         blk_quantize_a<DownFmt::kBs>(p, t);
         __syncthreads();
+        block_stamp(p, 7);
 
         const BlockLay L = block_layout<DownFmt::kBs>(p, smem);
         const uint8_t* ring = smem + (ring_u32 - (uint32_t)__cvta_generic_to_shared(smem));
@@ -432,7 +449,9 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
             while (eq >= nquads) { eq -= nquads; evi++; }
         }
         __syncthreads();
+        block_stamp(p, 8);
         blk_combine<DownFmt::kBs>(p, t);
+        block_stamp(p, 9);
     }
   }  // tokens
 
@@ -451,6 +470,8 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
 // per-device scratch: router partial sums [kBlockMaxTokens][S<=8][E<=512] + the two barrier words
 static float* g_bpartial[64] = {nullptr};
 static unsigned* g_bsync[64] = {nullptr};
+
+static unsigned long long* g_btrace = nullptr;
 
 static int env_fused() {
     static int v = [] { const char* e = getenv("KTB200_FUSED"); return e ? atoi(e) : 1; }();
@@ -535,7 +556,7 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     p.s_gate = sh ? sh->gate : nullptr; p.s_up = sh ? sh->up : nullptr; p.s_down = sh ? sh->down : nullptr;
     p.n_local = c.expert_num; p.id_offset = c.expert_id_offset;
     p.H = c.hidden_size; p.I = c.intermediate_size; p.k = k; p.hidden_type = c.hidden_type; p.use_silu = c.use_silu;
-    p.inter = m->inter; p.out = output; p.sync = g_bsync[d];
+    p.inter = m->inter; p.out = output; p.sync = g_bsync[d]; p.trace = g_btrace;
 
     void* args[] = {&p};
     const void* fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T> : (const void*)moe_block_kernel<BulkQ4K>;
@@ -566,3 +587,7 @@ extern "C" int ktb200_moe_block_forward_host(const ktb200_gate_config* gc, ktb20
     KTB_CUDA_CHECK(cudaStreamSynchronize(s));
     return KTB200_OK;
 }
+
+// Diagnostics (profiles/block_trace.py): when set, thread 0 of every CTA of the following ktb200_moe_block_forward
+// launches writes %globaltimer at the phase boundaries into trace[cta][16] (device memory, >= 148*16 u64).
+extern "C" void ktb200_debug_block_trace(unsigned long long* trace_dev) { g_btrace = trace_dev; }
