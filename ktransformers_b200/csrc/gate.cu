@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int t = 0; t < Teff; t++) gate_select_token<0>(p, t, xs, p.idx + (long)t * p.top_k, p.w + (long)t * p.top_k);
+    for (int t = 0; t < Teff; t++) gate_select_token<0>(p, t, xs, p.idx + (long)t * p.top_k, p.w + (long)t * p.top_k, p.logits_out);
 }
 
 // per-device scratch: partial sums + ticket

@@ -46,7 +46,7 @@ __device__ __forceinline__ void gate_sync() {
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(kGateThreads) : "memory");
 }
 template <int BAR>
-__device__ void gate_select_token(const GateParams& p, int t, float* sm, int64_t* idx_out, float* w_out) {
+__device__ void gate_select_token(const GateParams& p, int t, float* sm, int64_t* idx_out, float* w_out, float* logits_out) {
     const int E = p.E, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* scores = sm;
     float* choice = sm + E;
@@ -55,22 +55,29 @@ __device__ void gate_select_token(const GateParams& p, int t, float* sm, int64_t
     float* red = reinterpret_cast<float*>(wbest + 2 * kGateWarps);
 
     // logits = sum of the S partials in fixed order; thread owns experts e = tid + 128*i
-    float v[kGateEPT];
+    // (all S <= 8 loads are issued before the first add: one L2 round trip instead of S)
+    float v[kGateEPT], pv[8][kGateEPT];
 #pragma unroll
-    for (int i = 0; i < kGateEPT; i++) v[i] = 0.f;
-    for (int s = 0; s < p.S; s++) {
+    for (int s = 0; s < 8; s++) {
         const float* pp = p.partial + ((long)t * p.S + s) * E;
 #pragma unroll
         for (int i = 0; i < kGateEPT; i++) {
             const int e = tid + kGateThreads * i;
-            if (e < E) v[i] += __ldcg(pp + e);   // written by other SMs in this launch: read at L2
+            pv[s][i] = (s < p.S && e < E) ? __ldcg(pp + e) : 0.f;   // written by other SMs in this launch: read at L2
         }
     }
-    if (p.logits_out) {
+#pragma unroll
+    for (int i = 0; i < kGateEPT; i++) {
+        v[i] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            if (s < p.S) v[i] += pv[s][i];
+    }
+    if (logits_out) {
 #pragma unroll
         for (int i = 0; i < kGateEPT; i++) {
             const int e = tid + kGateThreads * i;
-            if (e < E) p.logits_out[(long)t * E + e] = v[i];
+            if (e < E) logits_out[(long)t * E + e] = v[i];
         }
     }
     if (p.scoring == 0) {  // sigmoid

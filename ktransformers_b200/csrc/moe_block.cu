@@ -42,6 +42,7 @@ struct BlockParams {
     int nrows_max;                       // output rows per CTA (stride of the `partial` staging)
     int region_a;                        // bytes of the aliased activation staging
     int ring_bytes;                      // per-warp ring
+    int prime_u, prime_d;                // rows / tiles every warp requests BEFORE the router's / the second grid barrier
     unsigned long long* trace;           // debug: [grid][16] globaltimer stamps of the phase boundaries (null: off)
 };
 
@@ -186,9 +187,7 @@ __device__ __noinline__ void blk_select(const BlockParams& p, int t) {
     const BlockLay L = block_layout<8>(p, smem);
     const int k = p.k;
     if ((threadIdx.x >> 5) < kGateWarps) {
-        GateParams gp = p.g;
-        if (blockIdx.x != 0) gp.logits_out = nullptr;
-        gate_select_token<1>(gp, t, L.sel, sh.ids, sh.w);
+        gate_select_token<1>(p.g, t, L.sel, sh.ids, sh.w, blockIdx.x == 0 ? p.g.logits_out : nullptr);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -331,11 +330,13 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
                 slot_i = (slot_i + 1 == SU) ? 0 : slot_i + 1;
             }
         };
-        // the shared expert's rows do not depend on the routing: request them before the router's barrier
-#pragma unroll
-        for (int s = 0; s < SU; s++) issue_u();
         blk_quantize_x(p, t);
         block_stamp(p, 1);
+        // the shared expert's rows do not depend on the routing: request a few before the router's barrier.  Only a
+        // few: everything requested here queues in front of the latency-critical loads of the next phases.
+#pragma unroll
+        for (int s = 0; s < SU; s++)
+            if (s < p.prime_u) issue_u();
         blk_router(p, t);
         block_stamp(p, 2);
         grid_sync(p.sync, gen);
@@ -384,12 +385,12 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
         const int nv = sh.nv;
         int ni = nquads * nv - warp;
         ni = ni > 0 ? (ni + W - 1) / W : 0;
-        int dvi = 0, dq = 0, dss = 0;
+        int dvi = 0, dq = 0, dss = 0, dcons = 0;   // issue cursor, tiles requested, tiles consumed
         if (ni > 0) { dvi = warp / nquads; dq = warp - dvi * nquads; }
         int evi = dvi, eq = dq;
         int dslot_i = 0, dslot_u = 0;
         auto issue_d = [&]() {
-            if (dss < ni) {
+            if (dss < ni && dss - dcons < SD) {
                 if (lane == 0) {
                     const int j = sh.vs[dvi];
                     long row = (long)(q0 + dq) * RW;
@@ -406,12 +407,15 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
                 dslot_i = (dslot_i + 1 == SD) ? 0 : dslot_i + 1;
             }
         };
-        // the first tiles depend on the expert ids only: request them before the barrier
+        // the first tiles depend on the expert ids only: some can be requested before the barrier
 #pragma unroll
-        for (int s = 0; s < SD; s++) issue_d();
+        for (int s = 0; s < SD; s++)
+            if (s < p.prime_d) issue_d();
         grid_sync(p.sync, gen);   // every row of `inter` is written and visible
         block_stamp(p, 6);
         blk_quantize_a<DownFmt::kBs>(p, t);
+#pragma unroll
+        for (int s = 0; s < SD; s++) issue_d();
         __syncthreads();
         block_stamp(p, 7);
 
@@ -443,6 +447,7 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
             }
             __syncwarp();
             dslot_u = (dslot_u + 1 == SD) ? 0 : dslot_u + 1;
+            dcons++;
             issue_d();
             if ((lane & 7) == 0) L.partial[(eq * RW + (lane >> 3)) * ns + j] = res;
             eq += W;
@@ -557,6 +562,9 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     p.n_local = c.expert_num; p.id_offset = c.expert_id_offset;
     p.H = c.hidden_size; p.I = c.intermediate_size; p.k = k; p.hidden_type = c.hidden_type; p.use_silu = c.use_silu;
     p.inter = m->inter; p.out = output; p.sync = g_bsync[d]; p.trace = g_btrace;
+    static const int prime_u = [] { const char* e = getenv("KTB200_BLK_PRIME_U"); return e ? atoi(e) : 1; }();
+    static const int prime_d = [] { const char* e = getenv("KTB200_BLK_PRIME_D"); return e ? atoi(e) : 1; }();
+    p.prime_u = prime_u; p.prime_d = prime_d;
 
     void* args[] = {&p};
     const void* fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T> : (const void*)moe_block_kernel<BulkQ4K>;
