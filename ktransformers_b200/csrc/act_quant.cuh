@@ -24,20 +24,19 @@ __device__ __forceinline__ void warp_quantize_q8k_block(const float (&x)[8], int
                                                         float* d_out, int16_t* bsums_out, int16_t* bs32_out = nullptr) {
     // local first-max scan
     float amax = 0.f, mx = 0.f;
-    int midx = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         float ax = fabsf(x[i]);
-        if (ax > amax) { amax = ax; mx = x[i]; midx = i; }
+        if (ax > amax) { amax = ax; mx = x[i]; }
     }
-    int gidx = lane * 8 + midx;
-    // warp arg-max: larger |x| wins, ties -> smaller index (== first in scan order)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-        float om = __shfl_xor_sync(0xffffffffu, mx, o);
-        int oi = __shfl_xor_sync(0xffffffffu, gidx, o);
-        if (oa > amax || (oa == amax && oi < gidx)) { amax = oa; mx = om; gidx = oi; }
+    // warp arg-max, first occurrence: |x| >= 0 orders like its bit pattern, so one REDUX finds the largest magnitude;
+    // the lowest lane holding it owns the earliest element (a lane owns 8 consecutive elements and its own scan kept
+    // the first), and one shuffle fetches that element's signed value.
+    {
+        const unsigned gmax = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+        const int src = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(amax) == gmax)) - 1;
+        mx = __shfl_sync(0xffffffffu, mx, src);
+        amax = __uint_as_float(gmax);
     }
     uint32_t w0 = 0, w1 = 0;
     int s = 0;

@@ -90,10 +90,7 @@ extern "C" int ktb200_moe_gate_forward(const ktb200_gate_config* c, int qlen, co
     const int d = dev & 63;
     cudaStream_t s = (cudaStream_t)stream;
     const int row_ctas = (c->n_experts + kGateWarps - 1) / kGateWarps;
-    int S = (2 * num_sms(dev) + row_ctas - 1) / row_ctas;   // ~2 CTAs per SM
-    if (S < 1) S = 1;
-    if (S > 8) S = 8;
-    while (S > 1 && c->hidden_size / 4 / S < 64) S--;
+    const int S = gate_splits(c->n_experts, c->hidden_size, num_sms(dev));
     const size_t need = (size_t)qlen * c->n_experts * S * sizeof(float);
     if (need > g_partial_cap[d] || !g_ticket[d]) {
         // grow-only scratch; allocation is NOT capturable: call once with the largest qlen before graph capture

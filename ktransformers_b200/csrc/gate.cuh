@@ -23,6 +23,16 @@ struct GateParams {
     unsigned* ticket;
 };
 
+// Column splits of the router GEMV: enough (row, split) units for ~15 warps on every SM, at least 64 float4 per unit.
+// ktb200_moe_gate_forward and the fused MoE-block kernel use the SAME S: their partial sums are bit-identical.
+static inline int gate_splits(int E, int H, int nsms) {
+    int S = (nsms * 15 + E - 1) / E;
+    if (S < 1) S = 1;
+    if (S > 8) S = 8;
+    while (S > 1 && H / 4 / S < 64) S--;
+    return S;
+}
+
 // order-preserving float -> uint32 key
 __device__ __forceinline__ unsigned fkey(float f) {
     const unsigned u = __float_as_uint(f);
@@ -45,8 +55,18 @@ __device__ __forceinline__ void gate_sync() {
     if (BAR == 0) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(kGateThreads) : "memory");
 }
+// (the fields the selection reads, copied into registers once: the named barriers below are memory clobbers, and a
+// params struct reached through a pointer would be re-read from memory after every one of them)
+struct GateSel {
+    int E, S, top_k, n_group, topk_group, scoring, topk_method, norm_topk_prob;
+    float routed_scaling_factor;
+    const float* bias;
+    const float* partial;
+};
 template <int BAR>
-__device__ void gate_select_token(const GateParams& p, int t, float* sm, int64_t* idx_out, float* w_out, float* logits_out) {
+__device__ void gate_select_token(const GateParams& pin, int t, float* sm, int64_t* idx_out, float* w_out, float* logits_out) {
+    const GateSel p{pin.E, pin.S, pin.top_k, pin.n_group, pin.topk_group, pin.scoring, pin.topk_method, pin.norm_topk_prob,
+                    pin.routed_scaling_factor, pin.bias, pin.partial};
     const int E = p.E, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* scores = sm;
     float* choice = sm + E;

@@ -92,6 +92,8 @@ __device__ __forceinline__ float4 load_x4(const void* x, long i4, int type) {
 //   [mbarriers]    W x 3
 //   [rings]        W x ring_bytes   (3 gate/up rows or 2 down tiles per warp)
 struct BlockShared {
+    BlockParams prm;   // the launch parameters, copied once: the cold phases read them with LDS instead of going through
+                       // a pointer to the kernel-parameter space after every barrier
     int64_t ids[32];
     float w[32];
     int vs[36];      // work list: slot indices this shard computes (the shared expert, slot k, first)
@@ -125,8 +127,9 @@ __device__ __forceinline__ BlockLay block_layout(const BlockParams& p, uint8_t* 
 
 // ---- cold phases: their own register allocation, called once per token ------------------------------------------
 // x -> Q8_K (padded staging)
-__device__ __noinline__ void blk_quantize_x(const BlockParams& p, int t) {
+__device__ __noinline__ void blk_quantize_x(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
+    const BlockParams& p = reinterpret_cast<const BlockShared*>(smem)->prm;
     const BlockLay L = block_layout<8>(p, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5, nblk = p.H / QK_K;
     for (int g0 = warp; g0 < nblk; g0 += W * 2) {
@@ -147,7 +150,9 @@ __device__ __noinline__ void blk_quantize_x(const BlockParams& p, int t) {
 }
 
 // router partial sums: unit = (expert row e, column split s); same loop and summation order as gate_dot<1> (gate.cuh)
-__device__ __noinline__ void blk_router(const BlockParams& p, int t) {
+__device__ __noinline__ void blk_router(int t) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const BlockParams& p = reinterpret_cast<const BlockShared*>(smem)->prm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int E = p.g.E, S = p.g.S, n4 = p.H / 4;
     const int gw = blockIdx.x * W + warp, tw = gridDim.x * W;
@@ -181,9 +186,10 @@ __device__ __noinline__ void blk_router(const BlockParams& p, int t) {
 }
 
 // top-k selection (first 4 warps of EVERY CTA, identical results), work-list compaction, routing outputs (CTA 0)
-__device__ __noinline__ void blk_select(const BlockParams& p, int t) {
+__device__ __noinline__ void blk_select(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
+    const BlockParams& p = sh.prm;
     const BlockLay L = block_layout<8>(p, smem);
     const int k = p.k;
     if ((threadIdx.x >> 5) < kGateWarps) {
@@ -209,9 +215,10 @@ __device__ __noinline__ void blk_select(const BlockParams& p, int t) {
 
 // a (fp32 phase-1 output, written by all CTAs) -> Q8_K
 template <int KBS>
-__device__ __noinline__ void blk_quantize_a(const BlockParams& p, int t) {
+__device__ __noinline__ void blk_quantize_a(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockShared& sh = *reinterpret_cast<const BlockShared*>(smem);
+    const BlockParams& p = sh.prm;
     const BlockLay L = block_layout<KBS>(p, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int k = p.k, nb = p.I / QK_K, ns = k + (p.s_gate ? 1 : 0);
@@ -248,9 +255,10 @@ __device__ __noinline__ void blk_quantize_a(const BlockParams& p, int t) {
 // weighted accumulation over the k experts IN expert_ids ORDER (moe.cpp:222-236), one FMA per expert; then the
 // shared expert as a second rounded term (experts.py:1011)
 template <int KBS>
-__device__ __noinline__ void blk_combine(const BlockParams& p, int t) {
+__device__ __noinline__ void blk_combine(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockShared& sh = *reinterpret_cast<const BlockShared*>(smem);
+    const BlockParams& p = sh.prm;
     const BlockLay L = block_layout<KBS>(p, smem);
     const int k = p.k, ns = k + (p.s_gate ? 1 : 0);
     const int quads = p.H / 4;
@@ -268,7 +276,7 @@ __device__ __noinline__ void blk_combine(const BlockParams& p, int t) {
 }
 
 template <class DownFmt>
-__global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __grid_constant__ BlockParams p) {
+__global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const BlockParams p) {
     constexpr int RW = 4, SU = 3, SD = 2;   // rows per down item, ring depth in rows (gate/up) and in tiles (down)
     extern __shared__ __align__(16) uint8_t smem[];
     BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
@@ -289,6 +297,11 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
         for (int s = 0; s < SU; s++) mbar_init(bar_u32 + 8 * s, 1);
         mbar_fence_init();
         fence_proxy_async_smem();
+    }
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&p);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.prm);
+        for (int i = threadIdx.x; i < (int)(sizeof(BlockParams) / 4); i += blockDim.x) dst[i] = src[i];
     }
     if (threadIdx.x == 0 && has_shared) sh.vs[0] = k;   // the shared expert is always the first entry of the work list
     uint32_t phase = 0;   // bit s = parity the next use of barrier s waits for
@@ -330,18 +343,18 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
                 slot_i = (slot_i + 1 == SU) ? 0 : slot_i + 1;
             }
         };
-        blk_quantize_x(p, t);
+        blk_quantize_x(t);
         block_stamp(p, 1);
         // the shared expert's rows do not depend on the routing: request a few before the router's barrier.  Only a
         // few: everything requested here queues in front of the latency-critical loads of the next phases.
 #pragma unroll
         for (int s = 0; s < SU; s++)
             if (s < p.prime_u) issue_u();
-        blk_router(p, t);
+        blk_router(t);
         block_stamp(p, 2);
         grid_sync(p.sync, gen);
         block_stamp(p, 3);
-        blk_select(p, t);
+        blk_select(t);
         block_stamp(p, 4);
         const int nv = sh.nv;
         vi_limit = nv;
@@ -413,7 +426,7 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
             if (s < p.prime_d) issue_d();
         grid_sync(p.sync, gen);   // every row of `inter` is written and visible
         block_stamp(p, 6);
-        blk_quantize_a<DownFmt::kBs>(p, t);
+        blk_quantize_a<DownFmt::kBs>(t);
 #pragma unroll
         for (int s = 0; s < SD; s++) issue_d();
         __syncthreads();
@@ -455,7 +468,7 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const __
         }
         __syncthreads();
         block_stamp(p, 8);
-        blk_combine<DownFmt::kBs>(p, t);
+        blk_combine<DownFmt::kBs>(t);
         block_stamp(p, 9);
     }
   }  // tokens
@@ -543,12 +556,7 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
         return ktb200_moe_forward_shared(m, sh, qlen, k, idx, w, input, output, bsz, stream);
     }
 
-    // router split: the same S as ktb200_moe_gate_forward so that the partial sums (and the routing) are bit-identical
-    const int row_ctas = (gc->n_experts + kGateWarps - 1) / kGateWarps;
-    int S = (2 * num_sms(dev) + row_ctas - 1) / row_ctas;
-    if (S < 1) S = 1;
-    if (S > 8) S = 8;
-    while (S > 1 && gc->hidden_size / 4 / S < 64) S--;
+    const int S = gate_splits(gc->n_experts, gc->hidden_size, num_sms(dev));
     if (!g_bpartial[d]) {   // not capturable: call once before graph capture (the first call allocates)
         KTB_CUDA_CHECK(cudaMalloc(&g_bpartial[d], (size_t)kBlockMaxTokens * 8 * kGateThreads * kGateEPT * sizeof(float)));
         KTB_CUDA_CHECK(cudaMalloc(&g_bsync[d], 2 * sizeof(unsigned)));
