@@ -86,6 +86,12 @@ __device__ void gate_select_token(const GateParams& pin, int t, float* sm, int64
             pv[s][i] = (s < p.S && e < E) ? __ldcg(pp + e) : 0.f;   // written by other SMs in this launch: read at L2
         }
     }
+    float bv[kGateEPT];   // e_score_correction_bias, requested together with the partial sums
+#pragma unroll
+    for (int i = 0; i < kGateEPT; i++) {
+        const int e = tid + kGateThreads * i;
+        bv[i] = (p.topk_method == 0 && p.bias && e < E) ? __ldg(p.bias + e) : 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < kGateEPT; i++) {
         v[i] = 0.f;
@@ -133,7 +139,7 @@ __device__ void gate_select_token(const GateParams& pin, int t, float* sm, int64
         const int e = tid + kGateThreads * i;
         c[i] = -INFINITY;
         if (e < E) {
-            c[i] = v[i] + ((p.topk_method == 0 && p.bias) ? p.bias[e] : 0.f);
+            c[i] = v[i] + bv[i];
             scores[e] = v[i];
             choice[e] = c[i];
         }
@@ -174,49 +180,48 @@ __device__ void gate_select_token(const GateParams& pin, int t, float* sm, int64
         gate_sync<BAR>();
     }
 
-    // top-k by iterative arg-max; ties -> lowest expert index
-    float wsum = 0.f, myw = 0.f;
-    long myidx = 0;
-    for (int it = 0; it < p.top_k; it++) {
-        unsigned bk = 0;
-        int bi = 0x7fffffff;
+    // top-k by iterative arg-max, ties -> lowest expert index.  ONE warp does it from registers (lane owns experts
+    // lane + 32*i): two REDUX per pick and no block-level barrier inside the loop.
+    if (warp == 0) {
+        constexpr int EPL = kGateThreads * kGateEPT / 32;
+        float cc[EPL];
 #pragma unroll
-        for (int i = 0; i < kGateEPT; i++) {
-            const int e = tid + kGateThreads * i;
-            const unsigned kk = (e < E) ? fkey(c[i]) : 0u;
-            if (kk > bk) { bk = kk; bi = e; }
+        for (int i = 0; i < EPL; i++) {
+            const int e = lane + 32 * i;
+            cc[i] = (e < E) ? choice[e] : -INFINITY;
         }
-        const unsigned mx = __reduce_max_sync(0xffffffffu, bk);
-        const int wi = __reduce_min_sync(0xffffffffu, (bk == mx) ? bi : 0x7fffffff);
-        if (lane == 0) { wbest[2 * warp] = mx; wbest[2 * warp + 1] = (unsigned)wi; }
-        gate_sync<BAR>();
-        unsigned gk = wbest[0];
-        int win = (int)wbest[1];
+        float wsum = 0.f, myw = 0.f;
+        long myidx = 0;
+        for (int it = 0; it < p.top_k; it++) {
+            unsigned bk = 0;
+            int bi = 0x7fffffff;
 #pragma unroll
-        for (int w = 1; w < kGateWarps; w++) {
-            const unsigned kk = wbest[2 * w];
-            const int ii = (int)wbest[2 * w + 1];
-            if (kk > gk || (kk == gk && ii < win)) { gk = kk; win = ii; }
+            for (int i = 0; i < EPL; i++) {
+                const int e = lane + 32 * i;
+                const unsigned kk = (e < E) ? fkey(cc[i]) : 0u;
+                if (kk > bk) { bk = kk; bi = e; }
+            }
+            const unsigned mx = __reduce_max_sync(0xffffffffu, bk);
+            int win = __reduce_min_sync(0xffffffffu, (bk == mx) ? bi : 0x7fffffff);
+            if (win == 0x7fffffff || win < 0 || win >= E) win = 0;  // degenerate (all NaN)
+            // V3 gathers the weight from the un-biased scores; V2 group_limited takes the (masked) score itself
+            const float wv = (p.topk_method == 2) ? choice[win] : scores[win];
+#pragma unroll
+            for (int i = 0; i < EPL; i++)
+                if (lane + 32 * i == win) cc[i] = -INFINITY;
+            if (lane == it) { myw = wv; myidx = win; }
+            wsum += wv;
         }
-        if (win == 0x7fffffff || win < 0 || win >= E) win = 0;  // degenerate (all NaN)
-        // V3 gathers the weight from the un-biased scores; V2 group_limited takes the (masked) score itself
-        const float wv = (p.topk_method == 2) ? choice[win] : scores[win];
-#pragma unroll
-        for (int i = 0; i < kGateEPT; i++)
-            if (tid + kGateThreads * i == win) c[i] = -INFINITY;
-        if (tid == it) { myw = wv; myidx = win; }
-        wsum += wv;
-        gate_sync<BAR>();   // wbest is rewritten in the next iteration
-    }
-    // V3 (modeling_deepseek_v3.py:474-479): normalise (if top_k>1 && norm_topk_prob) THEN always scale;
-    // V2 (modeling_deepseek.py:455-459): normalise XOR scale.
-    if (tid < p.top_k) {
-        float w = myw;
-        const bool do_norm = p.top_k > 1 && p.norm_topk_prob;
-        if (do_norm) w = __fdiv_rn(w, wsum + 1e-20f);
-        if (p.topk_method == 0 || !do_norm) w = w * p.routed_scaling_factor;
-        idx_out[tid] = myidx;
-        w_out[tid] = w;
+        // V3 (modeling_deepseek_v3.py:474-479): normalise (if top_k>1 && norm_topk_prob) THEN always scale;
+        // V2 (modeling_deepseek.py:455-459): normalise XOR scale.
+        if (lane < p.top_k) {
+            float w = myw;
+            const bool do_norm = p.top_k > 1 && p.norm_topk_prob;
+            if (do_norm) w = __fdiv_rn(w, wsum + 1e-20f);
+            if (p.topk_method == 0 || !do_norm) w = w * p.routed_scaling_factor;
+            idx_out[lane] = myidx;
+            w_out[lane] = w;
+        }
     }
     gate_sync<BAR>();
 }

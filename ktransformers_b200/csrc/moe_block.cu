@@ -27,6 +27,7 @@
 namespace ktb {
 
 constexpr int kBlockWarps = 15;    // 480 threads -> 128 registers; 15 x 13440-byte rings + staging = 227 KB
+constexpr int kBlockWarpsLo = 12;  // 384 threads -> 168 registers (KTB200_BLK_WARPS <= 12)
 constexpr int kBlockMaxTokens = 8;
 
 struct BlockParams {
@@ -52,16 +53,21 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
-// all CTAs of the (co-resident) grid; `gen` counts the barriers this CTA has passed
-__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& gen) {
+// Grid-wide barrier over the (co-resident) CTAs, split in two so that work which does not depend on the other CTAs —
+// here: requesting the next phase's weights — can be issued in between.  `gen` counts the barriers passed.  The arrive
+// side fences BEFORE any of those requests exist (a fence issued with bulk copies in flight waits for them: measured).
+__device__ __forceinline__ void grid_arrive(unsigned* counter, unsigned& gen) {
     __syncthreads();
     gen++;
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned gen) {
+    if (threadIdx.x == 0) {
         const unsigned target = gen * gridDim.x;
         while (ld_acquire_u32(counter) < target) {}
-        __threadfence();
     }
     __syncthreads();
 }
@@ -125,9 +131,9 @@ __device__ __forceinline__ BlockLay block_layout(const BlockParams& p, uint8_t* 
     return L;
 }
 
-// ---- cold phases: their own register allocation, called once per token ------------------------------------------
+// ---- the phases around the two streaming loops, once per token --------------------------------------------------
 // x -> Q8_K (padded staging)
-__device__ __noinline__ void blk_quantize_x(int t) {
+__device__ __forceinline__ void blk_quantize_x(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockParams& p = reinterpret_cast<const BlockShared*>(smem)->prm;
     const BlockLay L = block_layout<8>(p, smem);
@@ -150,7 +156,7 @@ __device__ __noinline__ void blk_quantize_x(int t) {
 }
 
 // router partial sums: unit = (expert row e, column split s); same loop and summation order as gate_dot<1> (gate.cuh)
-__device__ __noinline__ void blk_router(int t) {
+__device__ __forceinline__ void blk_router(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockParams& p = reinterpret_cast<const BlockShared*>(smem)->prm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -186,7 +192,7 @@ __device__ __noinline__ void blk_router(int t) {
 }
 
 // top-k selection (first 4 warps of EVERY CTA, identical results), work-list compaction, routing outputs (CTA 0)
-__device__ __noinline__ void blk_select(int t) {
+__device__ __forceinline__ void blk_select(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
     const BlockParams& p = sh.prm;
@@ -215,7 +221,7 @@ __device__ __noinline__ void blk_select(int t) {
 
 // a (fp32 phase-1 output, written by all CTAs) -> Q8_K
 template <int KBS>
-__device__ __noinline__ void blk_quantize_a(int t) {
+__device__ __forceinline__ void blk_quantize_a(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockShared& sh = *reinterpret_cast<const BlockShared*>(smem);
     const BlockParams& p = sh.prm;
@@ -255,7 +261,7 @@ __device__ __noinline__ void blk_quantize_a(int t) {
 // weighted accumulation over the k experts IN expert_ids ORDER (moe.cpp:222-236), one FMA per expert; then the
 // shared expert as a second rounded term (experts.py:1011)
 template <int KBS>
-__device__ __noinline__ void blk_combine(int t) {
+__device__ __forceinline__ void blk_combine(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockShared& sh = *reinterpret_cast<const BlockShared*>(smem);
     const BlockParams& p = sh.prm;
@@ -275,8 +281,8 @@ __device__ __noinline__ void blk_combine(int t) {
     }
 }
 
-template <class DownFmt>
-__global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const BlockParams p) {
+template <class DownFmt, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockParams p) {
     constexpr int RW = 4, SU = 3, SD = 2;   // rows per down item, ring depth in rows (gate/up) and in tiles (down)
     extern __shared__ __align__(16) uint8_t smem[];
     BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
@@ -345,14 +351,15 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const Bl
         };
         blk_quantize_x(t);
         block_stamp(p, 1);
-        // the shared expert's rows do not depend on the routing: request a few before the router's barrier.  Only a
-        // few: everything requested here queues in front of the latency-critical loads of the next phases.
+        blk_router(t);
+        block_stamp(p, 2);
+        grid_arrive(p.sync, gen);
+        // the shared expert's rows do not depend on the routing: they stream while the barrier completes and the
+        // top-k runs
 #pragma unroll
         for (int s = 0; s < SU; s++)
             if (s < p.prime_u) issue_u();
-        blk_router(t);
-        block_stamp(p, 2);
-        grid_sync(p.sync, gen);
+        grid_wait(p.sync, gen);
         block_stamp(p, 3);
         blk_select(t);
         block_stamp(p, 4);
@@ -420,11 +427,12 @@ __global__ void __launch_bounds__(kBlockWarps * 32, 1) moe_block_kernel(const Bl
                 dslot_i = (dslot_i + 1 == SD) ? 0 : dslot_i + 1;
             }
         };
-        // the first tiles depend on the expert ids only: some can be requested before the barrier
+        grid_arrive(p.sync, gen);   // this CTA's rows of `inter` are written
+        // the first tiles depend on the expert ids only: they stream while the barrier completes and `a` is quantised
 #pragma unroll
         for (int s = 0; s < SD; s++)
             if (s < p.prime_d) issue_d();
-        grid_sync(p.sync, gen);   // every row of `inter` is written and visible
+        grid_wait(p.sync, gen);     // every row of `inter` is written and visible
         block_stamp(p, 6);
         blk_quantize_a<DownFmt::kBs>(t);
 #pragma unroll
@@ -546,7 +554,9 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
         size_t base = (size_t)kBlockSharedBytes + p.region_a + (size_t)p.nrows_max * ns * 4;
         base = (base + 15) & ~(size_t)15;
         W = base + 64 < 232448 - 1024 ? (int)((232448 - 1024 - base - 16) / (ring + 24)) : 0;
+        static const int want_w = [] { const char* e = getenv("KTB200_BLK_WARPS"); return e ? atoi(e) : kBlockWarps; }();
         if (W > kBlockWarps) W = kBlockWarps;
+        if (want_w >= 8 && W > want_w) W = want_w;
         smem = base + (((size_t)W * 3 * 8 + 15) & ~(size_t)15) + (size_t)W * ring;
         if (W < 8 || c.hidden_size % 4 || item % 16 || c.intermediate_size < 1) fused = false;
     }
@@ -570,12 +580,14 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     p.n_local = c.expert_num; p.id_offset = c.expert_id_offset;
     p.H = c.hidden_size; p.I = c.intermediate_size; p.k = k; p.hidden_type = c.hidden_type; p.use_silu = c.use_silu;
     p.inter = m->inter; p.out = output; p.sync = g_bsync[d]; p.trace = g_btrace;
-    static const int prime_u = [] { const char* e = getenv("KTB200_BLK_PRIME_U"); return e ? atoi(e) : 1; }();
-    static const int prime_d = [] { const char* e = getenv("KTB200_BLK_PRIME_D"); return e ? atoi(e) : 1; }();
+    static const int prime_u = [] { const char* e = getenv("KTB200_BLK_PRIME_U"); return e ? atoi(e) : 3; }();
+    static const int prime_d = [] { const char* e = getenv("KTB200_BLK_PRIME_D"); return e ? atoi(e) : 2; }();
     p.prime_u = prime_u; p.prime_d = prime_d;
 
     void* args[] = {&p};
-    const void* fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T> : (const void*)moe_block_kernel<BulkQ4K>;
+    const void* fn;
+    if (W > kBlockWarpsLo) fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarps> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarps>;
+    else fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarpsLo> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarpsLo>;
     KTB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KTB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(W * 32), args, smem, s));
     count_launch(1);
