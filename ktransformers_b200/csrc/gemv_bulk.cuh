@@ -436,17 +436,9 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
         const uint8_t* sl = ring + slot_u * item_bytes;
         const int j = s_vs[cvi];
         float res;
-        if (nrb == 32) {   // 4 rows x 8 blocks: lane = (rw, blk), one block per lane
-            const int blk = lane & 7;
-            const int ab = j * nb + blk;
-            float v = Fmt::dot(sl, lane, nrb, q8 + (size_t)ab * kActBlkStride, bs + ab * Fmt::kBs, dx[ab]);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            res = v;
-        } else {
+        {
             float acc[RW] = {0.f, 0.f, 0.f, 0.f};
-            for (int f = lane; f < nrb; f += 32) {
+            for (int f = lane; f < nrb; f += 32) {   // (row, block) pairs of the tile; 4 x 8 = one per lane for I = 2048
                 const int rw = f / nb, blk = f - rw * nb;
                 const int ab = j * nb + blk;
                 const float val = Fmt::dot(sl, f, nrb, q8 + (size_t)ab * kActBlkStride, bs + ab * Fmt::kBs, dx[ab]);

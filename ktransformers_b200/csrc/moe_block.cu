@@ -138,20 +138,18 @@ __device__ __forceinline__ void blk_quantize_x(int t) {
     const BlockParams& p = reinterpret_cast<const BlockShared*>(smem)->prm;
     const BlockLay L = block_layout<8>(p, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5, nblk = p.H / QK_K;
-    for (int g0 = warp; g0 < nblk; g0 += W * 2) {
-        float x[2][8];
-        bool live[2];
+    // one block per warp and iteration, the next block's load already in flight (rolled: one copy of the quantiser)
+    float cur[8], nxt[8];
+    int b = warp;
+    if (b < nblk) load_block8(p.g.x, (long)t * p.H + (long)b * QK_K + lane * 8, p.hidden_type, cur);
+#pragma unroll 1
+    while (b < nblk) {
+        const int bn = b + W;
+        if (bn < nblk) load_block8(p.g.x, (long)t * p.H + (long)bn * QK_K + lane * 8, p.hidden_type, nxt);
+        warp_quantize_q8k_block(cur, lane, reinterpret_cast<uint32_t*>(L.xq + (size_t)b * kActBlkStride), L.xdx + b, nullptr, L.xbs + b * 8);
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int b = g0 + i * W;
-            live[i] = b < nblk;
-            if (live[i]) load_block8(p.g.x, (long)t * p.H + (long)b * QK_K + lane * 8, p.hidden_type, x[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int b = g0 + i * W;
-            if (live[i]) warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(L.xq + (size_t)b * kActBlkStride), L.xdx + b, nullptr, L.xbs + b * 8);
-        }
+        for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+        b = bn;
     }
 }
 
@@ -202,6 +200,7 @@ __device__ __forceinline__ void blk_select(int t) {
         gate_select_token<1>(p.g, t, L.sel, sh.ids, sh.w, blockIdx.x == 0 ? p.g.logits_out : nullptr);
     }
     __syncthreads();
+    block_stamp(p, 10);
     if (threadIdx.x == 0) {
         unsigned sk = 0;
         int nv = p.s_gate ? 1 : 0;
@@ -230,31 +229,29 @@ __device__ __forceinline__ void blk_quantize_a(int t) {
     const int k = p.k, nb = p.I / QK_K, ns = k + (p.s_gate ? 1 : 0);
     const unsigned skip = sh.skip;
     const int totalb = ns * nb;
-    for (int g0 = warp; g0 < totalb; g0 += W * 5) {
-        float x[5][8];
-        bool live[5];
+    // block gb = (slot r, block b of its row); `inter` was written by other SMs in this launch: read at L2
+    auto fetch = [&](int gb, float (&x)[8]) -> bool {
+        const int r = gb / nb, b = gb - r * nb;
+        if (r != k && ((skip >> r) & 1u)) return false;
+        const float4* src = reinterpret_cast<const float4*>(p.inter + ((long)t * ns + r) * p.I + (long)b * QK_K + lane * 8);
+        const float4 v0 = __ldcg(src), v1 = __ldcg(src + 1);
+        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+        return true;
+    };
+    float cur[8], nxt[8];
+    int gb = warp;
+    bool live = gb < totalb && fetch(gb, cur);
+#pragma unroll 1
+    while (gb < totalb) {
+        const int gn = gb + W;
+        const bool nlive = gn < totalb && fetch(gn, nxt);
+        if (live)
+            warp_quantize_q8k_block(cur, lane, reinterpret_cast<uint32_t*>(L.aq + (size_t)gb * kActBlkStride), L.adx + gb,
+                                    KBS == 16 ? L.abs_ + gb * 16 : nullptr, KBS == 8 ? L.abs_ + gb * 8 : nullptr);
 #pragma unroll
-        for (int i = 0; i < 5; i++) {
-            const int gb = g0 + i * W;
-            live[i] = gb < totalb;
-            if (live[i]) {
-                const int r = gb / nb, b = gb - r * nb;
-                live[i] = r == k || !((skip >> r) & 1u);
-                if (live[i]) {   // written by other SMs in this launch: read at L2
-                    const float4* src = reinterpret_cast<const float4*>(p.inter + ((long)t * ns + r) * p.I + (long)b * QK_K + lane * 8);
-                    const float4 v0 = __ldcg(src), v1 = __ldcg(src + 1);
-                    x[i][0] = v0.x; x[i][1] = v0.y; x[i][2] = v0.z; x[i][3] = v0.w;
-                    x[i][4] = v1.x; x[i][5] = v1.y; x[i][6] = v1.z; x[i][7] = v1.w;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            const int gb = g0 + i * W;
-            if (live[i])
-                warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(L.aq + (size_t)gb * kActBlkStride), L.adx + gb,
-                                        KBS == 16 ? L.abs_ + gb * 16 : nullptr, KBS == 8 ? L.abs_ + gb * 8 : nullptr);
-        }
+        for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+        gb = gn;
+        live = nlive;
     }
 }
 
@@ -283,7 +280,8 @@ __device__ __forceinline__ void blk_combine(int t) {
 
 template <class DownFmt, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockParams p) {
-    constexpr int RW = 4, SU = 3, SD = 2;   // rows per down item, ring depth in rows (gate/up) and in tiles (down)
+    // rows per down tile; ring depth in rows (gate/up: 4 with 12 warps, 3 with 15) and in tiles (down)
+    constexpr int RW = 4, SU = MAXW <= kBlockWarpsLo ? 4 : 3, SD = 2;
     extern __shared__ __align__(16) uint8_t smem[];
     BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -449,16 +447,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
             const uint8_t* sl = ring + dslot_u * item_bytes;
             const int j = sh.vs[evi];
             float res;
-            if (nrb == 32) {   // 4 rows x 8 blocks: lane = (rw, blk)
-                const int ab = j * nb + (lane & 7);
-                float v = DownFmt::dot(sl, lane, nrb, L.aq + (size_t)ab * kActBlkStride, L.abs_ + ab * DownFmt::kBs, L.adx[ab]);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                res = v;
-            } else {
+            {
                 float acc[RW] = {0.f, 0.f, 0.f, 0.f};
-                for (int f = lane; f < nrb; f += 32) {
+                for (int f = lane; f < nrb; f += 32) {   // (row, block) pairs of the tile; 4 x 8 = one per lane for I = 2048
                     const int rw = f / nb, blk = f - rw * nb;
                     const int ab = j * nb + blk;
                     const float val = DownFmt::dot(sl, f, nrb, L.aq + (size_t)ab * kActBlkStride, L.abs_ + ab * DownFmt::kBs, L.adx[ab]);
@@ -549,15 +540,18 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
         const size_t xq = (((size_t)nblk * (kActBlkStride + 16 + 4) + 15) & ~(size_t)15) + ((size_t)2 * gc->n_experts + 32 + 4 * kGateWarps) * 4;
         const size_t aqb = (size_t)ns * nb * (kActBlkStride + 2 * kbs + 4);
         p.region_a = (int)(((xq > aqb ? xq : aqb) + 15) & ~(size_t)15);
-        size_t ring = 3 * row > 2 * item ? 3 * row : 2 * item;
-        p.ring_bytes = (int)ring;
         size_t base = (size_t)kBlockSharedBytes + p.region_a + (size_t)p.nrows_max * ns * 4;
         base = (base + 15) & ~(size_t)15;
-        W = base + 64 < 232448 - 1024 ? (int)((232448 - 1024 - base - 16) / (ring + 24)) : 0;
-        static const int want_w = [] { const char* e = getenv("KTB200_BLK_WARPS"); return e ? atoi(e) : kBlockWarps; }();
-        if (W > kBlockWarps) W = kBlockWarps;
+        // 12 warps x (4 rows | 2 tiles) with 168 registers by default; KTB200_BLK_WARPS=15: 15 warps x (3 rows | 2 tiles), 128 registers
+        static const int want_w = [] { const char* e = getenv("KTB200_BLK_WARPS"); return e ? atoi(e) : kBlockWarpsLo; }();
+        const int su = want_w > kBlockWarpsLo ? 3 : 4;
+        size_t ring = su * row > 2 * item ? su * row : 2 * item;
+        p.ring_bytes = (int)ring;
+        W = base + 64 < 232448 - 1024 ? (int)((232448 - 1024 - base - 16) / (ring + 8 * su)) : 0;
+        if (W > (want_w > kBlockWarpsLo ? kBlockWarps : kBlockWarpsLo)) W = want_w > kBlockWarpsLo ? kBlockWarps : kBlockWarpsLo;
         if (want_w >= 8 && W > want_w) W = want_w;
-        smem = base + (((size_t)W * 3 * 8 + 15) & ~(size_t)15) + (size_t)W * ring;
+        if (want_w > kBlockWarpsLo && W <= kBlockWarpsLo) W = 0;   // the 3-row ring needs the 15-warp kernel
+        smem = base + (((size_t)W * su * 8 + 15) & ~(size_t)15) + (size_t)W * ring;
         if (W < 8 || c.hidden_size % 4 || item % 16 || c.intermediate_size < 1) fused = false;
     }
     if (!fused) {

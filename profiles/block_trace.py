@@ -34,14 +34,15 @@ y = torch.zeros(1, H, dtype=torch.bfloat16, device="cuda")
 ids = torch.zeros(1, K, dtype=torch.int64, device="cuda"); wts = torch.zeros(1, K, device="cuda")
 trace = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 names = ["start", "x quantised (+ shared rows requested)", "router partials written", "grid barrier 1 passed", "top-k selected",
-         "gate/up done (CTA)", "grid barrier 2 passed", "a quantised", "down tiles done (CTA)", "combined + stored"]
+         "gate/up done (CTA)", "grid barrier 2 passed", "a quantised", "down tiles done (CTA)", "combined + stored",
+         "  (top-k done, before the work-list build)"]
 acc = []
 for rep in range(12):
     gc, moe, mlp, _ = layers[rep % 3]
     lib.ktb200_debug_block_trace(trace.data_ptr())
     native.check(lib.ktb200_moe_block_forward(C.byref(gc), moe, mlp, 1, x.data_ptr(), y.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, S()))
     torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(148, 16)[:, :10].astype(np.float64)
+    t = trace.cpu().numpy().reshape(148, 16)[:, :11].astype(np.float64)
     t -= t[:, 0].min()
     if rep >= 3:
         acc.append(t)
