@@ -55,7 +55,7 @@ __device__ __forceinline__ void warp_quantize_q8k_block(const float (&x)[8], int
              ((uint32_t)(q[3] & 0xff) << 24);
         w1 = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) |
              ((uint32_t)(q[7] & 0xff) << 24);
-        d = __fdiv_rn(1.f, iscale);
+        d = __frcp_rn(iscale);   // correctly rounded reciprocal == 1.f / iscale
     }
     q8_out[2 * lane] = w0;
     q8_out[2 * lane + 1] = w1;

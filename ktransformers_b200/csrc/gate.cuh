@@ -23,10 +23,11 @@ struct GateParams {
     unsigned* ticket;
 };
 
-// Column splits of the router GEMV: enough (row, split) units for ~15 warps on every SM, at least 64 float4 per unit.
-// ktb200_moe_gate_forward and the fused MoE-block kernel use the SAME S: their partial sums are bit-identical.
+// Column splits of the router GEMV: as many (row, split) units as fit ONE wave of the persistent MoE-block kernel
+// (12 warps on every SM; a second wave doubles the router's latency), at least 64 float4 per unit.
+// ktb200_moe_gate_forward and the fused kernel use the SAME S: their partial sums are bit-identical.
 static inline int gate_splits(int E, int H, int nsms) {
-    int S = (nsms * 15 + E - 1) / E;
+    int S = nsms * 12 / E;
     if (S < 1) S = 1;
     if (S > 8) S = 8;
     while (S > 1 && H / 4 / S < 64) S--;
@@ -184,11 +185,11 @@ __device__ void gate_select_token(const GateParams& pin, int t, float* sm, int64
     // lane + 32*i): two REDUX per pick and no block-level barrier inside the loop.
     if (warp == 0) {
         constexpr int EPL = kGateThreads * kGateEPT / 32;
-        float cc[EPL];
+        unsigned ck[EPL];   // order-preserving keys of the selection scores; 0 = absent / already picked
 #pragma unroll
         for (int i = 0; i < EPL; i++) {
             const int e = lane + 32 * i;
-            cc[i] = (e < E) ? choice[e] : -INFINITY;
+            ck[i] = (e < E) ? fkey(choice[e]) : 0u;
         }
         float wsum = 0.f, myw = 0.f;
         long myidx = 0;
@@ -196,11 +197,8 @@ __device__ void gate_select_token(const GateParams& pin, int t, float* sm, int64
             unsigned bk = 0;
             int bi = 0x7fffffff;
 #pragma unroll
-            for (int i = 0; i < EPL; i++) {
-                const int e = lane + 32 * i;
-                const unsigned kk = (e < E) ? fkey(cc[i]) : 0u;
-                if (kk > bk) { bk = kk; bi = e; }
-            }
+            for (int i = 0; i < EPL; i++)
+                if (ck[i] > bk) { bk = ck[i]; bi = lane + 32 * i; }
             const unsigned mx = __reduce_max_sync(0xffffffffu, bk);
             int win = __reduce_min_sync(0xffffffffu, (bk == mx) ? bi : 0x7fffffff);
             if (win == 0x7fffffff || win < 0 || win >= E) win = 0;  // degenerate (all NaN)
@@ -208,7 +206,7 @@ __device__ void gate_select_token(const GateParams& pin, int t, float* sm, int64
             const float wv = (p.topk_method == 2) ? choice[win] : scores[win];
 #pragma unroll
             for (int i = 0; i < EPL; i++)
-                if (lane + 32 * i == win) cc[i] = -INFINITY;
+                if (lane + 32 * i == win) ck[i] = 0u;
             if (lane == it) { myw = wv; myidx = win; }
             wsum += wv;
         }

@@ -166,15 +166,16 @@ __device__ __forceinline__ void blk_router(int t) {
         const float4* wrow = reinterpret_cast<const float4*>(p.g.W + (long)e * p.H) + c0;
         const long xbase = (long)t * n4 + c0;
         float acc = 0.f;
-        for (int cb = lane; cb < nc4; cb += 32 * 8) {
-            float4 w[8], xv[8];
+        constexpr int NQ = 10;   // float4 in flight per lane: one batch covers H/S up to 1280 columns
+        for (int cb = lane; cb < nc4; cb += 32 * NQ) {
+            float4 w[NQ], xv[NQ];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < NQ; q++) {
                 const int c = cb + 32 * q;
                 if (c < nc4) { w[q] = __ldg(wrow + c); xv[q] = load_x4(p.g.x, xbase + c, p.hidden_type); }
             }
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < NQ; q++) {
                 const int c = cb + 32 * q;
                 if (c < nc4) {
                     acc = fmaf(w[q].x, xv[q].x, acc);
@@ -316,24 +317,33 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
     __syncthreads();   // previous token: region A, partial and the work list are free (first token: barriers initialised)
     {
         // ------------------------------------------------------------ gate/up: rows [ur0, ur0 + nr) of EVERY work-list entry
-        // unit u of this CTA (u = warp, warp + W, ...) = (entry u / nr, row ur0 + u % nr); 2 rows (gate, up) each
+        // A warp walks a list of units (entry, row) — 2 rows (gate, up) each — given by (first entry, end entry, its
+        // first unit, its stride).  Two lists per token:
+        //   S: the shared expert (entry 0), walked by warps 4.. WHILE warps 0..3 run the top-k (it needs no routing);
+        //   R: the routed entries, all warps.
         const int nblk = p.H / QK_K, row_bytes = nblk * SZ_Q4_K;
         const int ur0 = (int)((long)p.I * blockIdx.x / gridDim.x), nr = (int)((long)p.I * (blockIdx.x + 1) / gridDim.x) - ur0;
-        int ivi = warp / nr, irr = warp - ivi * nr, isub = 0;   // issue cursor, rows requested
-        int cvi = ivi, crr = irr, csub = 0;                     // consume cursor, rows consumed
-        int vi_limit = has_shared ? 1 : 0;                      // entries of the work list known so far
+        const int ns = k + (has_shared ? 1 : 0);
+        int ie = 0, ir = 0, isub = 0;   // issue cursor (entry, row), rows requested
+        int ce = 0, cr = 0, csub = 0;   // consume cursor, rows consumed
+        int e_end = 0, stride = W;      // end entry of the current list (0: nothing to do), unit stride of this warp
         int slot_i = 0, slot_u = 0;
+        auto start_list = [&](int e0, int e1, int first, int stride_) {
+            ie = e0 + first / nr; ir = first - (first / nr) * nr;
+            ce = ie; cr = ir;
+            e_end = e1; stride = stride_;
+        };
         auto issue_u = [&]() {
-            if (ivi < vi_limit && isub - csub < SU) {
+            if (ie < e_end && isub - csub < SU) {
                 if (lane == 0) {
-                    const int s = sh.vs[ivi];
+                    const int s = sh.vs[ie];
                     const bool second = isub & 1;
                     const uint8_t* src;
                     if (s == k) {
-                        src = reinterpret_cast<const uint8_t*>(second ? p.s_up : p.s_gate) + (long)(ur0 + irr) * row_bytes;
+                        src = reinterpret_cast<const uint8_t*>(second ? p.s_up : p.s_gate) + (long)(ur0 + ir) * row_bytes;
                     } else {
                         const long e = (long)sh.ids[s] - p.id_offset;
-                        src = reinterpret_cast<const uint8_t*>(second ? p.w_up : p.w_gate) + (e * p.I + ur0 + irr) * row_bytes;
+                        src = reinterpret_cast<const uint8_t*>(second ? p.w_up : p.w_gate) + (e * p.I + ur0 + ir) * row_bytes;
                     }
                     const uint32_t bar = bar_u32 + 8 * slot_i;
                     mbar_expect_tx(bar, (uint32_t)row_bytes);
@@ -341,57 +351,60 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
                 }
                 isub++;
                 if (!(isub & 1)) {
-                    irr += W;
-                    while (irr >= nr) { irr -= nr; ivi++; }
+                    ir += stride;
+                    while (ir >= nr) { ir -= nr; ie++; }
                 }
                 slot_i = (slot_i + 1 == SU) ? 0 : slot_i + 1;
             }
         };
+        if (has_shared && warp >= kGateWarps) start_list(0, 1, warp - kGateWarps, W - kGateWarps);
         blk_quantize_x(t);
         block_stamp(p, 1);
         blk_router(t);
         block_stamp(p, 2);
         grid_arrive(p.sync, gen);
-        // the shared expert's rows do not depend on the routing: they stream while the barrier completes and the
-        // top-k runs
+        // the shared expert's rows stream while the barrier completes ...
 #pragma unroll
         for (int s = 0; s < SU; s++)
             if (s < p.prime_u) issue_u();
         grid_wait(p.sync, gen);
         block_stamp(p, 3);
-        blk_select(t);
-        block_stamp(p, 4);
-        const int nv = sh.nv;
-        vi_limit = nv;
-#pragma unroll
-        for (int s = 0; s < SU; s++) issue_u();
-
         const BlockLay L = block_layout<DownFmt::kBs>(p, smem);
         const uint8_t* ring = smem + (ring_u32 - (uint32_t)__cvta_generic_to_shared(smem));
-        const int ns = k + (has_shared ? 1 : 0);
-        float acc_first = 0.f;
-        while (cvi < nv) {
-            mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
-            phase ^= 1u << slot_u;
-            const uint8_t* row0 = ring + slot_u * row_bytes;
-            float acc = 0.f;
-            if (lane < nblk)
-                acc = q4k_block_dot(row0 + lane * SZ_Q4_K, L.xq + (size_t)lane * kActBlkStride,
-                                    *reinterpret_cast<const uint4*>(L.xbs + lane * 8), L.xdx[lane]);
-            __syncwarp();
-            slot_u = (slot_u + 1 == SU) ? 0 : slot_u + 1;
-            csub++;
-            issue_u();
-            if (csub & 1) { acc_first = acc; continue; }
-            float g = acc_first, uu = acc;
+#pragma unroll 1
+        for (int list = 0; list < 2; list++) {
+            if (list == 1) {
+                // ... and were consumed by warps 4.. (list 0) while warps 0..3 run the top-k now
+                blk_select(t);
+                block_stamp(p, 4);
+                start_list(has_shared ? 1 : 0, sh.nv, warp, W);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                g += __shfl_xor_sync(0xffffffffu, g, o);
-                uu += __shfl_xor_sync(0xffffffffu, uu, o);
+                for (int s = 0; s < SU; s++) issue_u();
             }
-            if (lane == 0) p.inter[((long)t * ns + sh.vs[cvi]) * p.I + ur0 + crr] = (p.use_silu ? act_silu(g) : act_relu(g)) * uu;
-            crr += W;
-            while (crr >= nr) { crr -= nr; cvi++; }
+            float acc_first = 0.f;
+            while (ce < e_end) {
+                mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
+                phase ^= 1u << slot_u;
+                const uint8_t* row0 = ring + slot_u * row_bytes;
+                float acc = 0.f;
+                if (lane < nblk)
+                    acc = q4k_block_dot(row0 + lane * SZ_Q4_K, L.xq + (size_t)lane * kActBlkStride,
+                                        *reinterpret_cast<const uint4*>(L.xbs + lane * 8), L.xdx[lane]);
+                __syncwarp();
+                slot_u = (slot_u + 1 == SU) ? 0 : slot_u + 1;
+                csub++;
+                issue_u();
+                if (csub & 1) { acc_first = acc; continue; }
+                float g = acc_first, uu = acc;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    g += __shfl_xor_sync(0xffffffffu, g, o);
+                    uu += __shfl_xor_sync(0xffffffffu, uu, o);
+                }
+                if (lane == 0) p.inter[((long)t * ns + sh.vs[ce]) * p.I + ur0 + cr] = (p.use_silu ? act_silu(g) : act_relu(g)) * uu;
+                cr += stride;
+                while (cr >= nr) { cr -= nr; ce++; }
+            }
         }
         if (p.trace) { __syncthreads(); block_stamp(p, 5); }
     }
@@ -583,7 +596,14 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     if (W > kBlockWarpsLo) fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarps> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarps>;
     else fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarpsLo> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarpsLo>;
     KTB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KTB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(W * 32), args, smem, s));
+    // cooperative launch: the driver guarantees (or refuses) co-residency of the G <= #SM CTAs the grid barriers need.
+    // KTB200_BLK_COOP=0 launches the same grid plainly (it is co-resident whenever the GPU runs nothing else).
+    static const int coop = [] { const char* e = getenv("KTB200_BLK_COOP"); return e ? atoi(e) : 1; }();
+    if (coop) {
+        KTB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(W * 32), args, smem, s));
+    } else {
+        KTB_CUDA_CHECK(cudaLaunchKernel(fn, dim3(G), dim3(W * 32), args, smem, s));
+    }
     count_launch(1);
     return KTB200_OK;
 }
