@@ -316,34 +316,35 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
   for (int t = 0; t < Teff; t++) {
     __syncthreads();   // previous token: region A, partial and the work list are free (first token: barriers initialised)
     {
-        // ------------------------------------------------------------ gate/up: rows [ur0, ur0 + nr) of EVERY work-list entry
-        // A warp walks a list of units (entry, row) — 2 rows (gate, up) each — given by (first entry, end entry, its
-        // first unit, its stride).  Two lists per token:
-        //   S: the shared expert (entry 0), walked by warps 4.. WHILE warps 0..3 run the top-k (it needs no routing);
-        //   R: the routed entries, all warps.
+        // ------------------------------------------------------------ gate/up
+        // A warp walks a list of units (work-list entry, row) — 2 weight rows (gate, up) each.  Two lists per token:
+        //   S: the shared expert (entry 0), rows [ur0, ur0 + nr) of it, walked by warps 4.. WHILE warps 0..3 run the
+        //      top-k (the shared expert needs no routing);
+        //   R: the routed entries, all warps: the (entry, row) pairs of ALL routed entries form one global list that is
+        //      cut into equal contiguous ranges per CTA (+-1 unit) and dealt round-robin to the CTA's warps.
         const int nblk = p.H / QK_K, row_bytes = nblk * SZ_Q4_K;
-        const int ur0 = (int)((long)p.I * blockIdx.x / gridDim.x), nr = (int)((long)p.I * (blockIdx.x + 1) / gridDim.x) - ur0;
         const int ns = k + (has_shared ? 1 : 0);
-        int ie = 0, ir = 0, isub = 0;   // issue cursor (entry, row), rows requested
-        int ce = 0, cr = 0, csub = 0;   // consume cursor, rows consumed
-        int e_end = 0, stride = W;      // end entry of the current list (0: nothing to do), unit stride of this warp
+        int ie = 0, ir = 0, ileft = 0, isub = 0;   // issue cursor (entry, row), units left to request, rows requested
+        int ce = 0, cr = 0, cleft = 0, csub = 0;   // consume cursor, units left to finish, rows consumed
+        int stride = W;
         int slot_i = 0, slot_u = 0;
-        auto start_list = [&](int e0, int e1, int first, int stride_) {
-            ie = e0 + first / nr; ir = first - (first / nr) * nr;
+        auto start_list = [&](int e0, int first_row, int count, int stride_) {   // first_row may exceed I: it wraps into the next entries
+            ie = e0 + first_row / p.I; ir = first_row - (first_row / p.I) * p.I;
             ce = ie; cr = ir;
-            e_end = e1; stride = stride_;
+            ileft = cleft = count > 0 ? count : 0;
+            stride = stride_;
         };
         auto issue_u = [&]() {
-            if (ie < e_end && isub - csub < SU) {
+            if (ileft > 0 && isub - csub < SU) {
                 if (lane == 0) {
                     const int s = sh.vs[ie];
                     const bool second = isub & 1;
                     const uint8_t* src;
                     if (s == k) {
-                        src = reinterpret_cast<const uint8_t*>(second ? p.s_up : p.s_gate) + (long)(ur0 + ir) * row_bytes;
+                        src = reinterpret_cast<const uint8_t*>(second ? p.s_up : p.s_gate) + (long)ir * row_bytes;
                     } else {
                         const long e = (long)sh.ids[s] - p.id_offset;
-                        src = reinterpret_cast<const uint8_t*>(second ? p.w_up : p.w_gate) + (e * p.I + ur0 + ir) * row_bytes;
+                        src = reinterpret_cast<const uint8_t*>(second ? p.w_up : p.w_gate) + (e * p.I + ir) * row_bytes;
                     }
                     const uint32_t bar = bar_u32 + 8 * slot_i;
                     mbar_expect_tx(bar, (uint32_t)row_bytes);
@@ -351,22 +352,27 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
                 }
                 isub++;
                 if (!(isub & 1)) {
+                    ileft--;
                     ir += stride;
-                    while (ir >= nr) { ir -= nr; ie++; }
+                    while (ir >= p.I) { ir -= p.I; ie++; }
                 }
                 slot_i = (slot_i + 1 == SU) ? 0 : slot_i + 1;
             }
         };
-        if (has_shared && warp >= kGateWarps) start_list(0, 1, warp - kGateWarps, W - kGateWarps);
-        blk_quantize_x(t);
-        block_stamp(p, 1);
         blk_router(t);
         block_stamp(p, 2);
         grid_arrive(p.sync, gen);
-        // the shared expert's rows stream while the barrier completes ...
+        // while the barrier completes: request the shared expert's first rows, then quantise x (the router read x itself)
+        if (has_shared && warp >= kGateWarps) {
+            const int ur0 = (int)((long)p.I * blockIdx.x / gridDim.x), nr = (int)((long)p.I * (blockIdx.x + 1) / gridDim.x) - ur0;
+            const int first = warp - kGateWarps, st = W - kGateWarps;
+            start_list(0, ur0 + first, (nr - first + st - 1) / st, st);
+        }
 #pragma unroll
         for (int s = 0; s < SU; s++)
             if (s < p.prime_u) issue_u();
+        blk_quantize_x(t);
+        block_stamp(p, 1);
         grid_wait(p.sync, gen);
         block_stamp(p, 3);
         const BlockLay L = block_layout<DownFmt::kBs>(p, smem);
@@ -374,15 +380,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
 #pragma unroll 1
         for (int list = 0; list < 2; list++) {
             if (list == 1) {
-                // ... and were consumed by warps 4.. (list 0) while warps 0..3 run the top-k now
+                // list 0 (the shared expert) was consumed by warps 4.. while warps 0..3 run the top-k now
                 blk_select(t);
                 block_stamp(p, 4);
-                start_list(has_shared ? 1 : 0, sh.nv, warp, W);
+                const int e0 = has_shared ? 1 : 0;
+                const long total = (long)(sh.nv - e0) * p.I;
+                const int u0 = (int)(total * blockIdx.x / gridDim.x), u1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+                start_list(e0, u0 + warp, (u1 - u0 - warp + W - 1) / W, W);
 #pragma unroll
                 for (int s = 0; s < SU; s++) issue_u();
             }
             float acc_first = 0.f;
-            while (ce < e_end) {
+            while (cleft > 0) {
                 mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
                 phase ^= 1u << slot_u;
                 const uint8_t* row0 = ring + slot_u * row_bytes;
@@ -401,9 +410,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
                     g += __shfl_xor_sync(0xffffffffu, g, o);
                     uu += __shfl_xor_sync(0xffffffffu, uu, o);
                 }
-                if (lane == 0) p.inter[((long)t * ns + sh.vs[ce]) * p.I + ur0 + cr] = (p.use_silu ? act_silu(g) : act_relu(g)) * uu;
+                if (lane == 0) p.inter[((long)t * ns + sh.vs[ce]) * p.I + cr] = (p.use_silu ? act_silu(g) : act_relu(g)) * uu;
+                cleft--;
                 cr += stride;
-                while (cr >= nr) { cr -= nr; ce++; }
+                while (cr >= p.I) { cr -= p.I; ce++; }
             }
         }
         if (p.trace) { __syncthreads(); block_stamp(p, 5); }

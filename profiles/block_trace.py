@@ -33,7 +33,7 @@ x = (torch.randn(1, H, device="cuda") / 100).to(torch.bfloat16)
 y = torch.zeros(1, H, dtype=torch.bfloat16, device="cuda")
 ids = torch.zeros(1, K, dtype=torch.int64, device="cuda"); wts = torch.zeros(1, K, device="cuda")
 trace = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
-names = ["start", "x quantised (+ shared rows requested)", "router partials written", "grid barrier 1 passed", "top-k selected",
+names = ["start", "x quantised (under barrier 1)", "router partials written", "grid barrier 1 passed", "top-k selected",
          "gate/up done (CTA)", "grid barrier 2 passed", "a quantised", "down tiles done (CTA)", "combined + stored",
          "  (top-k done, before the work-list build)"]
 acc = []
@@ -49,5 +49,5 @@ for rep in range(12):
 lib.ktb200_debug_block_trace(None)
 t = np.mean(acc, axis=0) / 1e3
 print(f"{'boundary':42s} {'first':>8s} {'median':>8s} {'last':>8s}   (us after the first CTA started; mean of {len(acc)} launches)")
-for i, n in enumerate(names):
-    print(f"{n:42s} {t[:, i].min():8.2f} {np.median(t[:, i]):8.2f} {t[:, i].max():8.2f}")
+for i in sorted(range(len(names)), key=lambda i: np.median(t[:, i])):
+    print(f"{names[i]:42s} {t[:, i].min():8.2f} {np.median(t[:, i]):8.2f} {t[:, i].max():8.2f}")
