@@ -391,11 +391,11 @@ def main():
             for l in range(N_MOE_LAYERS):
                 Lr = layers[l % L]
                 native.check(lib.ktb200_moe_block_forward_host(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], 1, x_host.data_ptr(), out_host.data_ptr(),
-                                                               ids_host.data_ptr(), w_host.data_ptr(), S()))
+                                                               None, None, S()))
             return out_host
         h2d = N_MOE_LAYERS * H * 2
-        d2h = N_MOE_LAYERS * (H * 2 + K * 8 + K * 4)
-        e2e_api = "per layer: ktb200_moe_block_forward_host(pinned host token -> host output + routing): H2D, one launch, D2H, sync"
+        d2h = N_MOE_LAYERS * H * 2
+        e2e_api = "per layer: ktb200_moe_block_forward_host(pinned host token -> pinned host output): H2D, one launch, D2H, sync"
     else:
         def e2e_step():
             x_own.copy_(x_host, non_blocking=True)
