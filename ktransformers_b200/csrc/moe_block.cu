@@ -154,11 +154,9 @@ __device__ __forceinline__ void blk_quantize_x(int t) {
 }
 
 // router partial sums: unit = (expert row e, column split s); same loop and summation order as gate_dot<1> (gate.cuh)
-// ... and, hidden under the latency of the first batch of weight loads, this warp's share of "x -> Q8_K"
 __device__ __forceinline__ void blk_router(int t) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockParams& p = reinterpret_cast<const BlockShared*>(smem)->prm;
-    bool quantised = false;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int E = p.g.E, S = p.g.S, n4 = p.H / 4;
     const int gw = blockIdx.x * W + warp, tw = gridDim.x * W;
@@ -176,7 +174,6 @@ __device__ __forceinline__ void blk_router(int t) {
                 const int c = cb + 32 * q;
                 if (c < nc4) { w[q] = __ldg(wrow + c); xv[q] = load_x4(p.g.x, xbase + c, p.hidden_type); }
             }
-            if (!quantised) { blk_quantize_x(t); quantised = true; }
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
                 const int c = cb + 32 * q;
@@ -191,7 +188,6 @@ __device__ __forceinline__ void blk_router(int t) {
         const float v = warp_sum(acc);
         if (lane == 0) p.g.partial[((long)t * S + s) * E + e] = v;
     }
-    if (!quantised) blk_quantize_x(t);
 }
 
 // top-k selection (first 4 warps of EVERY CTA, identical results), work-list compaction, routing outputs (CTA 0)
@@ -366,7 +362,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
         blk_router(t);
         block_stamp(p, 2);
         grid_arrive(p.sync, gen);
-        // while the barrier completes: request the shared expert's first rows
+        // while the barrier completes: request the shared expert's first rows, then quantise x (the router read x itself)
         if (has_shared && warp >= kGateWarps) {
             const int ur0 = (int)((long)p.I * blockIdx.x / gridDim.x), nr = (int)((long)p.I * (blockIdx.x + 1) / gridDim.x) - ur0;
             const int first = warp - kGateWarps, st = W - kGateWarps;
@@ -375,6 +371,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
 #pragma unroll
         for (int s = 0; s < SU; s++)
             if (s < p.prime_u) issue_u();
+        blk_quantize_x(t);
         block_stamp(p, 1);
         grid_wait(p.sync, gen);
         block_stamp(p, 3);
