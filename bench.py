@@ -295,29 +295,31 @@ def main():
     w_host = torch.zeros((1, K), dtype=torch.float32).pin_memory()
     out_host = torch.zeros((1, H), dtype=torch.bfloat16).pin_memory()
 
+    side_stream = torch.cuda.Stream() if world > 1 else None
+    y_sh = torch.zeros((1, H), dtype=torch.bfloat16, device=dev)
+
     def layer_device(l):
         Lr = layers[l % L]
-        if world > 1:
-            dist.all_gather_into_tensor(x_all, x_own)
-            xin = x_all
-        else:
-            xin = x_own
         if world == 1:
             # KDeepseekV3MoE.forward in one call: router + routed experts + shared expert (one persistent launch)
-            native.check(lib.ktb200_moe_block_forward(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], 1, xin.data_ptr(), y.data_ptr(),
+            native.check(lib.ktb200_moe_block_forward(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], 1, x_own.data_ptr(), y.data_ptr(),
                                                       ids.data_ptr(), wts.data_ptr(), None, S()))
             return
+        # expert-parallel: the shared expert of this GPU's own token needs no communication: it runs on a side stream
+        # under the all-gather, and joins as the second rounded term (KDeepseekV3MoE.forward, experts.py:984-1011)
+        main = torch.cuda.current_stream()
+        side_stream.wait_stream(main)
+        with torch.cuda.stream(side_stream):
+            native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y_sh.data_ptr(), 0, None, S()))
+        dist.all_gather_into_tensor(x_all, x_own)
+        xin = x_all
         native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, xin.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))
-        if world > 1:
-            x_all_f32.copy_(xin)
-            native.check(lib.ktb200_moe_forward(Lr["moe"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(), None, S()))
-            dist.reduce_scatter_tensor(own_f32, part)
-            y.copy_(own_f32)
-            # y += shared_experts(x)   (KDeepseekV3MoE.forward, experts.py:984-1011)
-            native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y.data_ptr(), 1, None, S()))
-        else:
-            # routed + shared expert in the same two launches (y = experts(x); y += shared_experts(x))
-            native.check(lib.ktb200_moe_forward_shared(Lr["moe"], Lr["mlp"], 1, K, ids.data_ptr(), wts.data_ptr(), xin.data_ptr(), y.data_ptr(), None, S()))
+        x_all_f32.copy_(xin)
+        native.check(lib.ktb200_moe_forward(Lr["moe"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(), None, S()))
+        dist.reduce_scatter_tensor(own_f32, part)
+        y.copy_(own_f32)
+        main.wait_stream(side_stream)
+        y.add_(y_sh)
 
     def step_device():
         for l in range(N_MOE_LAYERS):

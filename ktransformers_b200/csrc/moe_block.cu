@@ -72,6 +72,11 @@ __device__ __forceinline__ void grid_wait(unsigned* counter, unsigned gen) {
     __syncthreads();
 }
 
+// Programmatic dependent launch: the next layer's launch is processed, and its CTAs start on SMs as they free up,
+// while the tail of this one still runs; everything that depends on the previous kernel comes after griddep_wait().
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void block_stamp(const BlockParams& p, int i) {
     if (p.trace && threadIdx.x == 0) {
         unsigned long long t;
@@ -154,7 +159,9 @@ __device__ __forceinline__ void blk_quantize_x(int t) {
 }
 
 // router partial sums: unit = (expert row e, column split s); same loop and summation order as gate_dot<1> (gate.cuh)
-__device__ __forceinline__ void blk_router(int t) {
+// `waited`: whether this thread already passed griddep_wait() — the router's WEIGHT loads are issued before it (they do
+// not depend on the previous kernel), x is read after it.
+__device__ __forceinline__ void blk_router(int t, bool& waited) {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlockParams& p = reinterpret_cast<const BlockShared*>(smem)->prm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -172,7 +179,13 @@ __device__ __forceinline__ void blk_router(int t) {
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
                 const int c = cb + 32 * q;
-                if (c < nc4) { w[q] = __ldg(wrow + c); xv[q] = load_x4(p.g.x, xbase + c, p.hidden_type); }
+                if (c < nc4) w[q] = __ldg(wrow + c);
+            }
+            if (!waited) { griddep_wait(); waited = true; }
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const int c = cb + 32 * q;
+                if (c < nc4) xv[q] = load_x4(p.g.x, xbase + c, p.hidden_type);
             }
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
@@ -188,6 +201,7 @@ __device__ __forceinline__ void blk_router(int t) {
         const float v = warp_sum(acc);
         if (lane == 0) p.g.partial[((long)t * S + s) * E + e] = v;
     }
+    if (!waited) { griddep_wait(); waited = true; }
 }
 
 // top-k selection (first 4 warps of EVERY CTA, identical results), work-list compaction, routing outputs (CTA 0)
@@ -286,8 +300,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
     extern __shared__ __align__(16) uint8_t smem[];
     BlockShared& sh = *reinterpret_cast<BlockShared*>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    griddep_launch_dependents();
+    bool waited = false;
     int Teff = p.g.T;
-    if (p.g.bsz) Teff = min(Teff, *p.g.bsz);
+    if (p.g.bsz) { griddep_wait(); waited = true; Teff = min(Teff, *p.g.bsz); }   // a device-side batch size is an input too
     const int k = p.k;
     const bool has_shared = p.s_gate != nullptr;
     uint32_t bar_u32, ring_u32;
@@ -359,7 +375,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
                 slot_i = (slot_i + 1 == SU) ? 0 : slot_i + 1;
             }
         };
-        blk_router(t);
+        blk_router(t, waited);
         block_stamp(p, 2);
         grid_arrive(p.sync, gen);
         // while the barrier completes: request the shared expert's first rows, then quantise x (the router read x itself)
@@ -509,7 +525,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
 
 // per-device scratch: router partial sums [kBlockMaxTokens][S<=8][E<=512] + the two barrier words
 static float* g_bpartial[64] = {nullptr};
-static unsigned* g_bsync[64] = {nullptr};
+static unsigned* g_bsync[64] = {nullptr};   // two pairs of barrier words, used alternately: with programmatic dependent
+static unsigned g_bflip[64] = {0};           // launch the next kernel's CTAs may arrive before this one's last CTA resets its pair
 
 static unsigned long long* g_btrace = nullptr;
 
@@ -586,8 +603,8 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     const int S = gate_splits(gc->n_experts, gc->hidden_size, num_sms(dev));
     if (!g_bpartial[d]) {   // not capturable: call once before graph capture (the first call allocates)
         KTB_CUDA_CHECK(cudaMalloc(&g_bpartial[d], (size_t)kBlockMaxTokens * 8 * kGateThreads * kGateEPT * sizeof(float)));
-        KTB_CUDA_CHECK(cudaMalloc(&g_bsync[d], 2 * sizeof(unsigned)));
-        KTB_CUDA_CHECK(cudaMemset(g_bsync[d], 0, 2 * sizeof(unsigned)));
+        KTB_CUDA_CHECK(cudaMalloc(&g_bsync[d], 4 * sizeof(unsigned)));
+        KTB_CUDA_CHECK(cudaMemset(g_bsync[d], 0, 4 * sizeof(unsigned)));
     }
     p.g = GateParams{gc->weight, input, gc->hidden_type, gc->n_experts, gc->hidden_size, qlen, S, k, gc->n_group, gc->topk_group,
                      gc->scoring, gc->topk_method, gc->norm_topk_prob, gc->routed_scaling_factor, gc->bias, g_bpartial[d], nullptr,
@@ -596,7 +613,7 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     p.s_gate = sh ? sh->gate : nullptr; p.s_up = sh ? sh->up : nullptr; p.s_down = sh ? sh->down : nullptr;
     p.n_local = c.expert_num; p.id_offset = c.expert_id_offset;
     p.H = c.hidden_size; p.I = c.intermediate_size; p.k = k; p.hidden_type = c.hidden_type; p.use_silu = c.use_silu;
-    p.inter = m->inter; p.out = output; p.sync = g_bsync[d]; p.trace = g_btrace;
+    p.inter = m->inter; p.out = output; p.sync = g_bsync[d] + 2 * (g_bflip[d]++ & 1u); p.trace = g_btrace;
     static const int prime_u = [] { const char* e = getenv("KTB200_BLK_PRIME_U"); return e ? atoi(e) : 3; }();
     static const int prime_d = [] { const char* e = getenv("KTB200_BLK_PRIME_D"); return e ? atoi(e) : 2; }();
     p.prime_u = prime_u; p.prime_d = prime_d;
@@ -606,14 +623,26 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     if (W > kBlockWarpsLo) fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarps> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarps>;
     else fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarpsLo> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarpsLo>;
     KTB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // cooperative launch: the driver guarantees (or refuses) co-residency of the G <= #SM CTAs the grid barriers need.
-    // KTB200_BLK_COOP=0 launches the same grid plainly (it is co-resident whenever the GPU runs nothing else).
+    // Launch attributes.  Cooperative: the driver guarantees (or refuses) co-residency of the G <= #SM CTAs the grid
+    // barriers need (KTB200_BLK_COOP=0: plain grid, co-resident whenever the GPU runs nothing else).  Programmatic
+    // stream serialization (KTB200_BLK_PDL=0 to disable): see griddep_wait() in the kernel.
     static const int coop = [] { const char* e = getenv("KTB200_BLK_COOP"); return e ? atoi(e) : 1; }();
-    if (coop) {
-        KTB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(W * 32), args, smem, s));
-    } else {
-        KTB_CUDA_CHECK(cudaLaunchKernel(fn, dim3(G), dim3(W * 32), args, smem, s));
+    static const int pdl = [] { const char* e = getenv("KTB200_BLK_PDL"); return e ? atoi(e) : 1; }();
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(G); lc.blockDim = dim3(W * 32); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (coop) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; na++; }
+    if (pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    lc.attrs = at; lc.numAttrs = na;
+    cudaError_t le = cudaLaunchKernelExC(&lc, fn, args);
+    if (le != cudaSuccess && coop && pdl) {   // the two attributes together are not accepted everywhere: keep the overlap
+        (void)cudaGetLastError();
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.numAttrs = 1;
+        le = cudaLaunchKernelExC(&lc, fn, args);
     }
+    if (le != cudaSuccess) { set_error("moe_block launch failed: %s", cudaGetErrorString(le)); return KTB200_ECUDA; }
     count_launch(1);
     return KTB200_OK;
 }
