@@ -46,20 +46,32 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(const GateParams p) 
         }
     }
 
-    // ---- last CTA selects -------------------------------------------------------------------------------
-    __shared__ unsigned s_last;
+    // ---- the last CTAs to finish select: one token each (round-robin), in parallel ----------------------------------
+    // ticket[0] counts finished CTAs, ticket[1] finished selectors; both are zero again when the launch ends
+    // (graph-replay safe).  A selector that is not the very last CTA spins until all partial sums are written: the whole
+    // grid is resident (<= 16 small CTAs per SM), so the CTAs it waits for are running.
+    __shared__ int s_sel;
+    const unsigned total = gridDim.x * gridDim.y;
+    const int nsel = min(Teff, (int)min(total, 16u));
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
         const unsigned prev = atomicAdd(p.ticket, 1u);
-        s_last = (prev == total - 1);
-        if (s_last) *p.ticket = 0;   // self-reset: the next launch (or graph replay) starts from zero
+        s_sel = nsel > 0 ? (int)prev - (int)(total - nsel) : -1;
+        if (nsel == 0 && prev == total - 1) p.ticket[0] = 0;   // device-side batch size 0: nothing to select
+        if (s_sel >= 0) {
+            unsigned v;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ticket) : "memory"); } while (v < total);
+        }
     }
     __syncthreads();
-    if (!s_last) return;
+    if (s_sel < 0) return;
     __threadfence();
-    for (int t = 0; t < Teff; t++) gate_select_token<0>(p, t, xs, p.idx + (long)t * p.top_k, p.w + (long)t * p.top_k, p.logits_out);
+    for (int t = s_sel; t < Teff; t += nsel) gate_select_token<0>(p, t, xs, p.idx + (long)t * p.top_k, p.w + (long)t * p.top_k, p.logits_out);
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(p.ticket + 1, 1u);
+        if (done == (unsigned)nsel - 1) { p.ticket[0] = 0; p.ticket[1] = 0; }
+    }
 }
 
 // per-device scratch: partial sums + ticket
@@ -99,8 +111,8 @@ extern "C" int ktb200_moe_gate_forward(const ktb200_gate_config* c, int qlen, co
         KTB_CUDA_CHECK(cudaMalloc(&g_partial[d], cap));
         g_partial_cap[d] = cap;
         if (!g_ticket[d]) {
-            KTB_CUDA_CHECK(cudaMalloc(&g_ticket[d], sizeof(unsigned)));
-            KTB_CUDA_CHECK(cudaMemset(g_ticket[d], 0, sizeof(unsigned)));
+            KTB_CUDA_CHECK(cudaMalloc(&g_ticket[d], 2 * sizeof(unsigned)));
+            KTB_CUDA_CHECK(cudaMemset(g_ticket[d], 0, 2 * sizeof(unsigned)));
         }
     }
     GateParams p{c->weight, x, c->hidden_type, c->n_experts, c->hidden_size, qlen, S, c->top_k, c->n_group, c->topk_group,

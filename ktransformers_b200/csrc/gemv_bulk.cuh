@@ -24,7 +24,6 @@
 namespace ktb {
 
 constexpr int kBulkMaxWarps = 18;        // gate/up kernel (<= 96 registers per thread)
-constexpr int kBulkMaxWarpsAreg = 16;    // gate/up kernel with register-resident activations (128 registers)
 constexpr int kBulkMaxWarpsDown = 16;    // down kernel: 128 registers per thread, and shared memory caps it at 15 anyway
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -103,27 +102,29 @@ __device__ __forceinline__ float q4k_block_dot(const uint8_t* wb, const uint8_t*
 // Gate/up (PAIR) or dense (PAIR = false) rows of Q4_K tensors.  Per warp: a private ring of SLOTS row slots; the
 // warp's stream of sub-units is g(u0), u(u0), g(u0+W), u(u0+W), ... (PAIR) and at any time SLOTS-1 rows are in
 // flight behind the one being consumed.
-// AREG (rows of <= 32 super-blocks, i.e. ncols <= 8192): lane b always meets activation block b, so the block's 256
-// int8 + sums + scale live in 69 REGISTERS for the whole token and the dot product reads only weights from shared
-// memory (9 instead of 27 LDS.128 per row); costs registers -> 16 warps instead of 18.
-template <bool PAIR, int SLOTS, bool AREG>
-__global__ void __launch_bounds__((AREG ? kBulkMaxWarpsAreg : kBulkMaxWarps) * 32, 1) rows_bulk_q4k_kernel(const RowsParams p, int act_bytes) {
+//
+// Tokens are processed in chunks of `tc` (launcher: as many as fit next to >= 12 rings).  Within a chunk ALL
+// (token, slot) pairs this launch owns form ONE work list — expert-parallel shards and decode batches keep the ring
+// streaming across tokens instead of draining it once per token — and all the chunk's activation rows are staged as
+// Q8_K side by side (`act_tok` bytes each).
+template <bool PAIR, int SLOTS>
+__global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) rows_bulk_q4k_kernel(const RowsParams p, int act_tok, int tc) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_vs[36];   // compacted list of the slots this launch computes for the current token
-    __shared__ int s_nv;
+    __shared__ int s_np;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     int Teff = p.ntokens;
     if (p.bsz) Teff = min(Teff, *p.bsz);
     const int nblk = p.ncols / QK_K;
     const int row_bytes = nblk * SZ_Q4_K;
     constexpr int NM = PAIR ? 2 : 1;
-    // activation staging: q8 [nblk][272] | bs32 [nblk][8] int16 | dx [nblk] float | mbarriers | rings
-    uint8_t* q8 = smem;
-    int16_t* bs32 = reinterpret_cast<int16_t*>(smem + (size_t)nblk * kActBlkStride);
-    float* dx = reinterpret_cast<float*>(smem + (size_t)nblk * kActBlkStride + (size_t)nblk * 16);
+    const int nslots = p.slots + (p.x0 ? 1 : 0);
+    const int total_out = nslots * p.rows;
+    // [tc activation rows: q8 [nblk][272] | bs32 [nblk][8] int16 | dx [nblk]] [pair list: tc*nslots ints] [mbarriers] [rings]
+    int* pairs = reinterpret_cast<int*>(smem + (size_t)tc * act_tok);                 // (token in chunk) << 8 | slot
+    const size_t off = ((size_t)tc * act_tok + (size_t)tc * nslots * 4 + 15) & ~(size_t)15;
     const int bar_bytes = (W * SLOTS * 8 + 15) & ~15;
-    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(smem + act_bytes) + warp * SLOTS * 8;
-    uint8_t* ring = smem + act_bytes + bar_bytes + (size_t)warp * SLOTS * row_bytes;
+    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(smem + off) + warp * SLOTS * 8;
+    uint8_t* ring = smem + off + bar_bytes + (size_t)warp * SLOTS * row_bytes;
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
     if (lane == 0) {
 #pragma unroll
@@ -134,40 +135,41 @@ __global__ void __launch_bounds__((AREG ? kBulkMaxWarpsAreg : kBulkMaxWarps) * 3
     int slot_i = 0, slot_u = 0;   // ring cursors (issue / use); they advance in lock step over the whole launch
     uint32_t phase = 0;           // bit s = parity the next use of slot s waits for
 
-    const int nslots = p.slots + (p.x0 ? 1 : 0);
-    const int total_out = nslots * p.rows;
-  for (int t = 0; t < Teff; t++) {
-    __syncthreads();   // previous token: everyone is done with the activation staging and s_vs (and the barriers are initialised)
+  for (int t0 = 0; t0 < Teff; t0 += tc) {
+    const int nt = min(tc, Teff - t0);
+    __syncthreads();   // previous chunk: everyone is done with the staging and the pair list (and the barriers are initialised)
     if (threadIdx.x == 0) {
-        int nv = 0;
-        for (int s = 0; s < p.slots; s++) {
-            const long e = p.ids ? (long)p.ids[(long)t * p.slots + s] - p.id_offset : 0;
-            if (e >= 0 && e < p.n_experts) s_vs[nv++] = s;
+        int np = 0;
+        for (int tl = 0; tl < nt; tl++) {
+            for (int s = 0; s < p.slots; s++) {
+                const long e = p.ids ? (long)p.ids[(long)(t0 + tl) * p.slots + s] - p.id_offset : 0;
+                if (e >= 0 && e < p.n_experts) pairs[np++] = (tl << 8) | s;
+            }
+            if (p.x0) pairs[np++] = (tl << 8) | p.slots;
         }
-        if (p.x0) s_vs[nv++] = p.slots;
-        s_nv = nv;
+        s_np = np;
     }
     __syncthreads();
-    const int total = s_nv * p.rows;
+    const int total = s_np * p.rows;
     const int u0 = (int)((long)total * blockIdx.x / gridDim.x), u1 = (int)((long)total * (blockIdx.x + 1) / gridDim.x);
     int nu = u1 - u0 - warp;
     nu = nu > 0 ? (nu + W - 1) / W : 0;                     // units of this warp: u0 + warp + i*W
     const int nsub = nu * NM;
-    // issue cursor: (valid-slot index, row) of the next unit to request, and how many rows were requested
-    int ivi = 0, irr = 0, isub = 0;
-    if (nu > 0) { ivi = (u0 + warp) / p.rows; irr = (u0 + warp) - ivi * p.rows; }
-    int cvi = ivi, crr = irr;                               // consume cursor
+    // issue cursor: (pair index, row) of the next unit to request, and how many rows were requested
+    int ipi = 0, irr = 0, isub = 0;
+    if (nu > 0) { ipi = (u0 + warp) / p.rows; irr = (u0 + warp) - ipi * p.rows; }
+    int cpi = ipi, crr = irr;                               // consume cursor
 
     auto issue_one = [&]() {
         if (isub < nsub) {
             if (lane == 0) {
-                const int s = s_vs[ivi];
+                const int pr = pairs[ipi], s = pr & 0xff, tl = pr >> 8;
                 const bool second = PAIR && (isub & 1);
                 const uint8_t* src;
                 if (s == p.slots) {
                     src = reinterpret_cast<const uint8_t*>(second ? p.x1 : p.x0) + (long)irr * row_bytes;
                 } else {
-                    const long e = p.ids ? (long)p.ids[(long)t * p.slots + s] - p.id_offset : 0;
+                    const long e = p.ids ? (long)p.ids[(long)(t0 + tl) * p.slots + s] - p.id_offset : 0;
                     src = reinterpret_cast<const uint8_t*>(second ? p.w1 : p.w0) + (e * p.rows + irr) * row_bytes;
                 }
                 const uint32_t bar = bar_u32 + 8 * slot_i;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__((AREG ? kBulkMaxWarpsAreg : kBulkMaxWarps) * 3
             isub++;
             if (!PAIR || !(isub & 1)) {
                 irr += W;
-                while (irr >= p.rows) { irr -= p.rows; ivi++; }
+                while (irr >= p.rows) { irr -= p.rows; ipi++; }
             }
             slot_i = (slot_i + 1 == SLOTS) ? 0 : slot_i + 1;
         }
@@ -185,47 +187,40 @@ __global__ void __launch_bounds__((AREG ? kBulkMaxWarpsAreg : kBulkMaxWarps) * 3
 #pragma unroll
     for (int s = 0; s < SLOTS; s++) issue_one();
 
-    {   // quantise the token's activation row into the padded layout (one warp per block, 4 blocks in flight)
-        for (int g0 = warp; g0 < nblk; g0 += W * 4) {
-            float x[4][8];
-            bool live[4];
+    {   // quantise the chunk's activation rows into the padded layout: block g = (token in chunk, block of the row)
+        float cur[8], nxt[8];
+        const int totalb = nt * nblk;
+        int g = warp;
+        if (g < totalb) load_block8(p.x, (long)(t0 + g / nblk) * p.ncols + (long)(g % nblk) * QK_K + lane * 8, p.hidden_type, cur);
+#pragma unroll 1
+        while (g < totalb) {
+            const int gn = g + W;
+            if (gn < totalb) load_block8(p.x, (long)(t0 + gn / nblk) * p.ncols + (long)(gn % nblk) * QK_K + lane * 8, p.hidden_type, nxt);
+            const int tl = g / nblk, b = g - tl * nblk;
+            uint8_t* at = smem + (size_t)tl * act_tok;
+            warp_quantize_q8k_block(cur, lane, reinterpret_cast<uint32_t*>(at + (size_t)b * kActBlkStride),
+                                    reinterpret_cast<float*>(at + (size_t)nblk * (kActBlkStride + 16)) + b, nullptr,
+                                    reinterpret_cast<int16_t*>(at + (size_t)nblk * kActBlkStride) + b * 8);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int b = g0 + i * W;
-                live[i] = b < nblk;
-                if (live[i]) load_block8(p.x, (long)t * p.ncols + (long)b * QK_K + lane * 8, p.hidden_type, x[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int b = g0 + i * W;
-                if (live[i]) warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(q8 + (size_t)b * kActBlkStride), dx + b, nullptr, bs32 + b * 8);
-            }
+            for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+            g = gn;
         }
     }
     __syncthreads();
-
-    uint4 areg[AREG ? 16 : 1];
-    if (AREG) {
-        const int b = lane < nblk ? lane : 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) areg[i] = *reinterpret_cast<const uint4*>(q8 + (size_t)b * kActBlkStride + 16 * i);
-    }
 
     float acc_first = 0.f;
     for (int n = 0; n < nsub; n++) {
         mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
         phase ^= 1u << slot_u;
         const uint8_t* row0 = ring + slot_u * row_bytes;
+        const int pr = pairs[cpi];
+        const uint8_t* at = smem + (size_t)(pr >> 8) * act_tok;
+        const int16_t* bs32 = reinterpret_cast<const int16_t*>(at + (size_t)nblk * kActBlkStride);
+        const float* dx = reinterpret_cast<const float*>(at + (size_t)nblk * (kActBlkStride + 16));
         float acc = 0.f;
-        if (AREG) {
-            // (sums and scale are re-read per row: two LDS are cheaper than five more live registers)
-            if (lane < nblk) acc = q4k_block_dot_t(row0 + lane * SZ_Q4_K, [&](int i) { return areg[i]; },
-                                                   *reinterpret_cast<const uint4*>(bs32 + lane * 8), dx[lane]);
-        } else {
-            for (int blk = lane; blk < nblk; blk += 32)
-                acc += q4k_block_dot(row0 + blk * SZ_Q4_K, q8 + (size_t)blk * kActBlkStride,
-                                     *reinterpret_cast<const uint4*>(bs32 + blk * 8), dx[blk]);
-        }
+        for (int blk = lane; blk < nblk; blk += 32)
+            acc += q4k_block_dot(row0 + blk * SZ_Q4_K, at + (size_t)blk * kActBlkStride,
+                                 *reinterpret_cast<const uint4*>(bs32 + blk * 8), dx[blk]);
         __syncwarp();                       // every lane is done reading the slot: hand it back to the copy engine
         slot_u = (slot_u + 1 == SLOTS) ? 0 : slot_u + 1;
         issue_one();
@@ -237,8 +232,8 @@ __global__ void __launch_bounds__((AREG ? kBulkMaxWarpsAreg : kBulkMaxWarps) * 3
             if (PAIR) uu += __shfl_xor_sync(0xffffffffu, uu, o);
         }
         if (lane == 0) {
-            const int oidx = s_vs[cvi] * p.rows + crr;
-            const long o = (long)t * total_out + oidx;
+            const int oidx = (pr & 0xff) * p.rows + crr;
+            const long o = (long)(t0 + (pr >> 8)) * total_out + oidx;
             if (PAIR) {
                 p.out_f32[o] = (p.use_silu ? act_silu(g) : act_relu(g)) * uu;
             } else {
@@ -248,9 +243,9 @@ __global__ void __launch_bounds__((AREG ? kBulkMaxWarpsAreg : kBulkMaxWarps) * 3
             }
         }
         crr += W;
-        while (crr >= p.rows) { crr -= p.rows; cvi++; }
+        while (crr >= p.rows) { crr -= p.rows; cpi++; }
     }
-  }  // tokens
+  }  // token chunks
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -320,15 +315,20 @@ struct BulkQ6K4T {   // chunk-major 4-row tiles (see the header comment)
     }
 };
 
-// Down projection + weighted combine.  Work item of a warp = (valid slot, 4 consecutive output rows) = one bulk
-// copy; every CTA owns a contiguous range of row quads for ALL slots so the combine over experts stays in the CTA.
+// Down projection + weighted combine.  Work item of a warp = (pair, 4 consecutive output rows) = one bulk copy; every
+// CTA owns a contiguous range of row quads for ALL pairs so the combine over experts stays in the CTA.
+//
+// Tokens are processed in chunks: as many consecutive tokens as have, together, at most `pcap` (token, slot) pairs
+// owned by this launch (launcher: pcap >= slots + 1, so a chunk always holds at least one token).  Within a chunk all
+// pairs form ONE work list (expert-parallel shards and decode batches do not drain the ring per token) and all their
+// activation rows are staged as Q8_K side by side.
+constexpr int kBulkMaxChunkTokens = 16;
 template <class Fmt, int SLOTS>
-__global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(const ReduceParams p, int nrows_max) {
+__global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(const ReduceParams p, int nrows_max, int pcap) {
     constexpr int RW = 4;
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_vs[36];
-    __shared__ int s_nv;
-    __shared__ unsigned s_skip;
+    __shared__ int s_np, s_nt;
+    __shared__ int s_first[kBulkMaxChunkTokens + 1];   // first pair of every token of the chunk (+ end)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     int Teff = p.ntokens;
     if (p.bsz) Teff = min(Teff, *p.bsz);
@@ -337,12 +337,13 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
     const int ns = k + (p.xw ? 1 : 0);
     const int nrb = RW * nb;                                  // (row, block) pairs per item
     const int item_bytes = nrb * Fmt::kBlockBytes;
-    // staging: q8 [ns][nb][272] | bs [ns][nb][kBs] int16 | dx [ns][nb] | partial [nrows_max][ns] | mbarriers | rings
+    // staging: q8 [pcap][nb][272] | bs [pcap][nb][kBs] int16 | dx [pcap][nb] | partial [nrows_max][pcap] | pair list [pcap] | mbarriers | rings
     uint8_t* q8 = smem;
-    int16_t* bs = reinterpret_cast<int16_t*>(smem + (size_t)ns * nb * kActBlkStride);
-    float* dx = reinterpret_cast<float*>(smem + (size_t)ns * nb * (kActBlkStride + 2 * Fmt::kBs));
-    float* partial = dx + (size_t)ns * nb;
-    size_t off = (size_t)ns * nb * (kActBlkStride + 2 * Fmt::kBs + 4) + (size_t)nrows_max * ns * 4;
+    int16_t* bs = reinterpret_cast<int16_t*>(smem + (size_t)pcap * nb * kActBlkStride);
+    float* dx = reinterpret_cast<float*>(smem + (size_t)pcap * nb * (kActBlkStride + 2 * Fmt::kBs));
+    float* partial = dx + (size_t)pcap * nb;
+    int* pairs = reinterpret_cast<int*>(partial + (size_t)nrows_max * pcap);   // (token in chunk) << 8 | slot
+    size_t off = (size_t)pcap * nb * (kActBlkStride + 2 * Fmt::kBs + 4) + (size_t)nrows_max * pcap * 4 + (size_t)pcap * 4;
     off = (off + 15) & ~(size_t)15;
     const int bar_bytes = (W * SLOTS * 8 + 15) & ~15;
     const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(smem + off) + warp * SLOTS * 8;
@@ -360,36 +361,46 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
     const int q0 = (int)((long)quads * blockIdx.x / gridDim.x), q1 = (int)((long)quads * (blockIdx.x + 1) / gridDim.x);
     const int r0 = q0 * RW, nquads = q1 - q0, nrows = nquads * RW;
 
-  for (int t = 0; t < Teff; t++) {
+  for (int t0 = 0; t0 < Teff;) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned sk = 0;
-        int nv = 0;
-        for (int j = 0; j < k; j++) {
-            const long e = p.ids ? (long)p.ids[(long)t * k + j] - p.id_offset : 0;
-            if (e < 0 || e >= p.n_experts) sk |= 1u << j; else s_vs[nv++] = j;
+    if (threadIdx.x == 0) {   // greedy chunk: tokens t0.. while their owned pairs fit
+        int np = 0, nt = 0;
+        while (t0 + nt < Teff && nt < kBulkMaxChunkTokens) {
+            int cnt = p.xw ? 1 : 0;
+            for (int j = 0; j < k; j++) {
+                const long e = p.ids ? (long)p.ids[(long)(t0 + nt) * k + j] - p.id_offset : 0;
+                cnt += (e >= 0 && e < p.n_experts) ? 1 : 0;
+            }
+            if (nt > 0 && np + cnt > pcap) break;
+            s_first[nt] = np;
+            for (int j = 0; j < k; j++) {
+                const long e = p.ids ? (long)p.ids[(long)(t0 + nt) * k + j] - p.id_offset : 0;
+                if (e >= 0 && e < p.n_experts) pairs[np++] = (nt << 8) | j;
+            }
+            if (p.xw) pairs[np++] = (nt << 8) | k;
+            nt++;
         }
-        if (p.xw) s_vs[nv++] = k;
-        s_nv = nv;
-        s_skip = sk;
+        s_first[nt] = np;
+        s_np = np;
+        s_nt = nt;
     }
     __syncthreads();
-    const unsigned skip = s_skip;
-    const int total = nquads * s_nv;   // item = vi * nquads + quad over the VALID slots only
+    const int np = s_np, nt = s_nt;
+    const int total = nquads * np;   // item = pair * nquads + quad
     int ni = total - warp;
     ni = ni > 0 ? (ni + W - 1) / W : 0;
-    int ivi = 0, iq = 0, iss = 0;
-    if (ni > 0) { ivi = warp / nquads; iq = warp - ivi * nquads; }
-    int cvi = ivi, cq = iq;
+    int ipi = 0, iq = 0, iss = 0;
+    if (ni > 0) { ipi = warp / nquads; iq = warp - ipi * nquads; }
+    int cpi = ipi, cq = iq;
 
     auto issue_one = [&]() {
         if (iss < ni) {
             if (lane == 0) {
-                const int j = s_vs[ivi];
+                const int pr = pairs[ipi], j = pr & 0xff;
                 long row = r0 + iq * RW;
                 const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
                 if (j == k) wbase = reinterpret_cast<const uint8_t*>(p.xw);
-                else row += (p.ids ? (long)p.ids[(long)t * k + j] - p.id_offset : 0L) * p.rows;
+                else row += (p.ids ? (long)p.ids[(long)(t0 + (pr >> 8)) * k + j] - p.id_offset : 0L) * p.rows;
                 const uint8_t* src = wbase + (row >> 2) * item_bytes;
                 const uint32_t bar = bar_u32 + 8 * slot_i;
                 mbar_expect_tx(bar, (uint32_t)item_bytes);
@@ -397,35 +408,31 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
             }
             iss++;
             iq += W;
-            while (iq >= nquads) { iq -= nquads; ivi++; }
+            while (iq >= nquads) { iq -= nquads; ipi++; }
             slot_i = (slot_i + 1 == SLOTS) ? 0 : slot_i + 1;
         }
     };
 #pragma unroll
     for (int s = 0; s < SLOTS; s++) issue_one();
 
-    {   // quantise the ns activation rows (fp32 phase-1 output) into the padded layout
-        const int totalb = ns * nb;
-        for (int g0 = warp; g0 < totalb; g0 += W * 4) {
-            float x[4][8];
-            bool live[4];
+    {   // quantise the pairs' activation rows (fp32 phase-1 output) into the padded layout: block g = (pair, block)
+        float cur[8], nxt[8];
+        const int totalb = np * nb;
+        auto src_of = [&](int g) -> long {
+            const int pi = g / nb, b = g - pi * nb, pr = pairs[pi];
+            return ((long)(t0 + (pr >> 8)) * ns + (pr & 0xff)) * p.ncols + (long)b * QK_K + lane * 8;
+        };
+        int g = warp;
+        if (g < totalb) load_block8(p.a, src_of(g), KTB200_TYPE_F32, cur);
+#pragma unroll 1
+        while (g < totalb) {
+            const int gn = g + W;
+            if (gn < totalb) load_block8(p.a, src_of(gn), KTB200_TYPE_F32, nxt);
+            warp_quantize_q8k_block(cur, lane, reinterpret_cast<uint32_t*>(q8 + (size_t)g * kActBlkStride), dx + g,
+                                    Fmt::kBs == 16 ? bs + g * 16 : nullptr, Fmt::kBs == 8 ? bs + g * 8 : nullptr);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int gb = g0 + i * W;
-                live[i] = gb < totalb;
-                if (live[i]) {
-                    const int r = gb / nb, b = gb - r * nb;
-                    live[i] = !((skip >> r) & 1u);
-                    if (live[i]) load_block8(p.a, ((long)t * ns + r) * p.ncols + (long)b * QK_K + lane * 8, KTB200_TYPE_F32, x[i]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int gb = g0 + i * W;
-                if (live[i])
-                    warp_quantize_q8k_block(x[i], lane, reinterpret_cast<uint32_t*>(q8 + (size_t)gb * kActBlkStride), dx + gb,
-                                            Fmt::kBs == 16 ? bs + gb * 16 : nullptr, Fmt::kBs == 8 ? bs + gb * 8 : nullptr);
-            }
+            for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+            g = gn;
         }
     }
     __syncthreads();
@@ -434,13 +441,12 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
         mbar_wait(bar_u32 + 8 * slot_u, (phase >> slot_u) & 1u);
         phase ^= 1u << slot_u;
         const uint8_t* sl = ring + slot_u * item_bytes;
-        const int j = s_vs[cvi];
         float res;
         {
             float acc[RW] = {0.f, 0.f, 0.f, 0.f};
             for (int f = lane; f < nrb; f += 32) {   // (row, block) pairs of the tile; 4 x 8 = one per lane for I = 2048
                 const int rw = f / nb, blk = f - rw * nb;
-                const int ab = j * nb + blk;
+                const int ab = cpi * nb + blk;
                 const float val = Fmt::dot(sl, f, nrb, q8 + (size_t)ab * kActBlkStride, bs + ab * Fmt::kBs, dx[ab]);
                 acc[0] += rw == 0 ? val : 0.f; acc[1] += rw == 1 ? val : 0.f; acc[2] += rw == 2 ? val : 0.f; acc[3] += rw == 3 ? val : 0.f;
             }
@@ -449,25 +455,29 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
         __syncwarp();
         slot_u = (slot_u + 1 == SLOTS) ? 0 : slot_u + 1;
         issue_one();
-        if ((lane & 7) == 0) partial[(cq * RW + (lane >> 3)) * ns + j] = res;
+        if ((lane & 7) == 0) partial[(cq * RW + (lane >> 3)) * pcap + cpi] = res;
         cq += W;
-        while (cq >= nquads) { cq -= nquads; cvi++; }
+        while (cq >= nquads) { cq -= nquads; cpi++; }
     }
     __syncthreads();
-    // weighted accumulation over the k experts IN expert_ids ORDER (moe.cpp:222-236), one FMA per expert
-    for (int hl = threadIdx.x; hl < nrows; hl += W * 32) {
-        float acc = 0.f;
-        for (int j = 0; j < k; j++) {
-            if ((skip >> j) & 1u) continue;
-            const float dv = partial[hl * ns + j];
-            acc = p.weights ? __fmaf_rn(dv, p.weights[(long)t * k + j], acc) : acc + dv;
+    // weighted accumulation over a token's experts IN expert_ids ORDER (moe.cpp:222-236), one FMA per expert
+    for (int idx = threadIdx.x; idx < nrows * nt; idx += W * 32) {
+        const int tl = idx / nrows, hl = idx - tl * nrows;
+        const long t = t0 + tl;
+        float acc = 0.f, shared = 0.f;
+        for (int pi = s_first[tl]; pi < s_first[tl + 1]; pi++) {
+            const int j = pairs[pi] & 0xff;
+            const float dv = partial[hl * pcap + pi];
+            if (j == k) shared = dv;
+            else acc = p.weights ? __fmaf_rn(dv, p.weights[t * k + j], acc) : acc + dv;
         }
-        const long o = (long)t * p.rows + r0 + hl;
-        if (p.xw) acc = round_hidden(acc, p.hidden_type) + round_hidden(partial[hl * ns + k], p.hidden_type);
+        const long o = t * p.rows + r0 + hl;
+        if (p.xw) acc = round_hidden(acc, p.hidden_type) + round_hidden(shared, p.hidden_type);
         if (p.accumulate) acc = load_hidden(p.out, o, p.hidden_type) + round_hidden(acc, p.hidden_type);
         store_hidden(p.out, o, p.hidden_type, acc);
     }
-  }  // tokens
+    t0 += nt;
+  }  // token chunks
 }
 
 }  // namespace ktb

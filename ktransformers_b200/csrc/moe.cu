@@ -246,27 +246,29 @@ static int launch_rows_bulk_q4k(const RowsParams& p, int T, int device, cudaStre
     const int nblk = p.ncols / QK_K;
     const int row_bytes = nblk * SZ_Q4_K;
     if (nblk < 16) return 1;                             // needs >= 16 blocks per row to keep most lanes busy
-    const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
-    if (total >= (1L << 30) || p.slots + 1 > 36) return 1;
-    const int act = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
+    const int nslots = p.slots + (p.x0 ? 1 : 0);
+    const long total = (long)nslots * p.rows;
+    if (total >= (1L << 26) || nslots > 200) return 1;
+    const int act_tok = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
     const int S = cfg_bulk_slots_up();
-    static const int want_areg = env_int("KTB200_BULK_AREG", 1);
-    const bool areg = want_areg && nblk <= 32;
-    int W = (int)((kSmemCap - act - 16) / ((size_t)S * (row_bytes + 8)));
+    // tokens per chunk: as many (<= 8) as fit next to 12 rings; then as many warps as fit
+    int tc = T < 8 ? T : 8;
+    while (tc > 1 && (size_t)tc * (act_tok + nslots * 4) + 64 + (size_t)12 * S * (row_bytes + 8) > kSmemCap) tc--;
+    const size_t head = (((size_t)tc * act_tok + (size_t)tc * nslots * 4 + 15) & ~(size_t)15);
+    if (head + 64 >= kSmemCap) return 1;
+    int W = (int)((kSmemCap - head - 16) / ((size_t)S * (row_bytes + 8)));
     if (W > cfg_bulk_warps()) W = cfg_bulk_warps();
-    if (areg && W > kBulkMaxWarpsAreg) W = kBulkMaxWarpsAreg;
     if (W < 4) return 1;
-    const size_t smem = (size_t)act + (((size_t)W * S * 8 + 15) & ~(size_t)15) + (size_t)W * S * row_bytes;
+    const size_t smem = head + (((size_t)W * S * 8 + 15) & ~(size_t)15) + (size_t)W * S * row_bytes;
     int gx = num_sms(device);            // one CTA per SM walks all T tokens
     if (gx > total) gx = (int)total;
     if (gx < 1) gx = 1;
-#define KTB_BULK_ROWS(SL, AR)                                                                                          \
+#define KTB_BULK_ROWS(SL)                                                                                              \
     do {                                                                                                               \
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_bulk_q4k_kernel<PAIR, SL, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rows_bulk_q4k_kernel<PAIR, SL, AR><<<gx, W * 32, smem, stream>>>(p, act);                                      \
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_bulk_q4k_kernel<PAIR, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rows_bulk_q4k_kernel<PAIR, SL><<<gx, W * 32, smem, stream>>>(p, act_tok, tc);                                  \
     } while (0)
-    if (areg) { if (S == 2) KTB_BULK_ROWS(2, true); else if (S == 4) KTB_BULK_ROWS(4, true); else KTB_BULK_ROWS(3, true); }
-    else { if (S == 2) KTB_BULK_ROWS(2, false); else if (S == 4) KTB_BULK_ROWS(4, false); else KTB_BULK_ROWS(3, false); }
+    if (S == 2) KTB_BULK_ROWS(2); else if (S == 4) KTB_BULK_ROWS(4); else KTB_BULK_ROWS(3);
 #undef KTB_BULK_ROWS
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
@@ -391,11 +393,12 @@ static int launch_reduce_pipe_q6k_blk(const ReduceParams& p, int T, int device, 
     return KTB200_OK;
 }
 
-// Shared-memory plan of reduce_bulk_kernel<Fmt, S>: returns the warp count (0 = does not fit)
+// Shared-memory plan of reduce_bulk_kernel<Fmt, S> for `pcap` staged (token, slot) pairs: returns the warp count
+// (0 = does not fit)
 template <class Fmt>
-static int reduce_bulk_plan(int rows, int ncols, int ns, int S, int device, int* gx_out, int* nrows_max_out, size_t* smem_out) {
+static int reduce_bulk_plan(int rows, int ncols, int pcap, int S, int device, int* gx_out, int* nrows_max_out, size_t* smem_out) {
     const int nb = ncols / QK_K;
-    if (rows % 4 || nb < 1 || ns > 36) return 0;
+    if (rows % 4 || nb < 1 || pcap > 200) return 0;
     const size_t item = (size_t)4 * nb * Fmt::kBlockBytes;
     if (item % 16) return 0;
     const int quads = rows / 4;
@@ -403,7 +406,7 @@ static int reduce_bulk_plan(int rows, int ncols, int ns, int S, int device, int*
     if (gx > quads) gx = quads;
     if (gx < 1) gx = 1;
     const int nrows_max = ((quads + gx - 1) / gx) * 4;
-    size_t base = (size_t)ns * nb * (kActBlkStride + 2 * Fmt::kBs + 4) + (size_t)nrows_max * ns * 4;
+    size_t base = (size_t)pcap * nb * (kActBlkStride + 2 * Fmt::kBs + 4) + (size_t)nrows_max * pcap * 4 + (size_t)pcap * 4;
     base = (base + 15) & ~(size_t)15;
     if (base + 16 >= kSmemCap) return 0;
     int W = (int)((kSmemCap - base - 16) / ((size_t)S * (item + 8)));
@@ -422,16 +425,25 @@ static int launch_reduce_bulk(const ReduceParams& p, int T, int device, cudaStre
     if (!cfg_bulk()) return 1;
     const int ns = p.slots + (p.xw ? 1 : 0);
     const int S = cfg_bulk_slots_down();
+    // pair capacity of a token chunk: one token's worth at least; up to 2 tokens' worth (<= 18) when several tokens
+    // share the launch and >= 10 warps still fit
+    int pcap = ns;
+    if (T > 1) {
+        int want = 2 * ns < 18 ? 2 * ns : (ns > 18 ? ns : 18);
+        if ((long)T * ns < want) want = T * ns;
+        while (want > ns && reduce_bulk_plan<Fmt>(p.rows, p.ncols, want, S, device, nullptr, nullptr, nullptr) < 10) want--;
+        pcap = want;
+    }
     int gx = 0, nrows_max = 0;
     size_t smem = 0;
-    const int W = reduce_bulk_plan<Fmt>(p.rows, p.ncols, ns, S, device, &gx, &nrows_max, &smem);
+    const int W = reduce_bulk_plan<Fmt>(p.rows, p.ncols, pcap, S, device, &gx, &nrows_max, &smem);
     if (!W) return 1;
     if (S == 3) {
         KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_bulk_kernel<Fmt, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reduce_bulk_kernel<Fmt, 3><<<gx, W * 32, smem, stream>>>(p, nrows_max);
+        reduce_bulk_kernel<Fmt, 3><<<gx, W * 32, smem, stream>>>(p, nrows_max, pcap);
     } else {
         KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_bulk_kernel<Fmt, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reduce_bulk_kernel<Fmt, 2><<<gx, W * 32, smem, stream>>>(p, nrows_max);
+        reduce_bulk_kernel<Fmt, 2><<<gx, W * 32, smem, stream>>>(p, nrows_max, pcap);
     }
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
