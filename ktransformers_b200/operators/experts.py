@@ -306,12 +306,77 @@ class KTransformersExperts(BaseInjectedModule, KExpertsBase):
 
 
 class _KDeepseekMoEMixin:
-    """forward shared by KDeepseekV3MoE / KDeepseekV2MoE (experts.py:760-800, 972-1012)."""
+    """forward shared by KDeepseekV3MoE / KDeepseekV2MoE (experts.py:760-800, 972-1012).
+
+    Decode batches (<= 8 tokens) whose gate is a KMoEGateB200 and whose generate experts are a fully resident
+    KExpertsB200 take ONE call, `ktb200_moe_block_forward`: router, routed experts and shared expert in a single
+    persistent launch, bit-identical to the three-step path below (include/ktb200.h).  The shared expert for that call
+    is a `ktb200_mlp` handle built once from the raw GGUF tensors `<key>.shared_experts.{gate,up,down}_proj.weight`.
+    """
+
+    BLOCK_MAX_TOKENS = 8
+
+    def _block_handles(self, x):
+        """(gate_cfg, moe_handle, mlp_handle_or_None) when the single-launch path applies, else None."""
+        gate, gen = getattr(self, "gate", None), getattr(getattr(self, "experts", None), "generate_experts", None)
+        if not (isinstance(gen, KExpertsB200) and gen.handle is not None and gen.ep_size == 1 and x.is_cuda):
+            return None
+        if getattr(self.experts, "mode", None) != InferenceState.GENERATE or getattr(gate, "_w", None) is None:
+            return None
+        m = gate.orig_module
+        from .gate import _SCORING, _TOPK
+        if x.dtype not in TORCH_TO_GGML_HIDDEN or TORCH_TO_GGML_HIDDEN[x.dtype] != gen.hidden_type:
+            return None
+        cfg = native.GateConfig(m.n_routed_experts, x.shape[-1], m.top_k, m.n_group or 1, m.topk_group or 1,
+                                _SCORING[m.scoring_func], _TOPK[m.topk_method], int(bool(m.norm_topk_prob)),
+                                float(m.routed_scaling_factor), gate._w.data_ptr(),
+                                gate._b.data_ptr() if gate._b is not None else None, gen.hidden_type)
+        mlp = None
+        if self.config.n_shared_experts is not None:
+            mlp = self._shared_mlp_handle(gen)
+            if mlp is None:
+                return None
+        return cfg, gen.handle, mlp
+
+    def _shared_mlp_handle(self, gen):
+        if getattr(self, "_ktb_mlp", None) is not None:
+            return self._ktb_mlp
+        ld = self.gguf_loader
+        names = [f"{self.key}.shared_experts.{n}_proj.weight" for n in ("gate", "up", "down")]
+        if ld is None or not all(ld.has_tensor(n) for n in names):
+            return None
+        types = [int(ld.get_ggml_type(n)) for n in names]
+        if any(GGML_NAMES.get(t) not in B200_WEIGHT_TYPES for t in types):
+            return None
+        dev = torch.device("cuda", gen.dev_index)
+        raw = [torch.from_numpy(np.ascontiguousarray(np.asarray(ld.get_mmap_tensor(n))).view(np.uint8).reshape(-1)).to(dev) for n in names]
+        inter = self.config.moe_intermediate_size * self.config.n_shared_experts
+        h = C.c_void_p()
+        native.check(native.lib().ktb200_mlp_create(self.config.hidden_size, inter, raw[0].data_ptr(), raw[1].data_ptr(), raw[2].data_ptr(),
+                                                    types[0], types[1], types[2], gen.hidden_type, self.BLOCK_MAX_TOKENS, gen.dev_index, C.byref(h)))
+        native.check(native.lib().ktb200_mlp_load_weights(h, _stream(dev)))
+        self._ktb_mlp, self._ktb_mlp_raw = h, raw
+        return h
 
     def forward(self, hidden_states):
         identity = hidden_states
         orig_shape = hidden_states.shape
         sequence_length = orig_shape[1]
+        n_tok = hidden_states.numel() // orig_shape[-1]
+        if n_tok <= self.BLOCK_MAX_TOKENS:
+            hs = self._block_handles(hidden_states)
+            if hs is not None:
+                cfg, moe, mlp = hs
+                x = hidden_states.reshape(n_tok, orig_shape[-1]).contiguous()
+                gen = self.experts.generate_experts
+                capturing = torch.cuda.is_current_stream_capturing()
+                y = KExpertsB200.output_gpu_map[gen.out_device][:n_tok] if capturing else torch.empty_like(x)
+                idx = torch.empty((n_tok, cfg.top_k), dtype=torch.int64, device=x.device)
+                wt = torch.empty((n_tok, cfg.top_k), dtype=torch.float32, device=x.device)
+                native.check(native.lib().ktb200_moe_block_forward(C.byref(cfg), moe, mlp, n_tok, x.data_ptr(), y.data_ptr(),
+                                                                   idx.data_ptr(), wt.data_ptr(), None, _stream(x.device)))
+                self.last_topk = (idx, wt)
+                return y.view(*orig_shape)
         topk_idx, topk_weight = self.gate(hidden_states)
         hidden_states = hidden_states.view(-1, hidden_states.shape[-1])
         gen = getattr(self.experts, "generate_experts", None)

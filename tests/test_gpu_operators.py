@@ -1,0 +1,103 @@
+"""GPU tests of the Python operator layer (the reference-facing injection API) on a tiny GGUF file:
+`optimize_and_load_gguf` with the shipped B200 rule file -> KDeepseekV3MoE / KTransformersExperts(KExpertsB200) /
+KMoEGateB200 / KTransformersLinear(KLinearB200), decode through the single-launch block call and through the
+three-step path (reference control flow, experts.py:972-1012), both against a dense fp32 restatement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+E, H, I, K = 8, 4096, 512, 4   # rows of 16 super-blocks: the persistent block kernel applies
+
+
+def _write_gguf(path):
+    import gguf
+    from ktransformers_b200.util.synth import synth_blocks
+    from oracle.bindings import Oracle
+    orc = Oracle()
+    rng = np.random.default_rng(7)
+    w = gguf.GGUFWriter(path, "deepseek2")
+    dense, seed = {}, [100]
+
+    def add_q(name, shape, qt):
+        seed[0] += 1
+        n = int(np.prod(shape))
+        q = synth_blocks(int(qt), n, "cpu", seed[0]).numpy()
+        w.add_tensor(name, q.reshape(*shape[:-1], -1), raw_dtype=qt)
+        dense[name] = orc.to_float(q, int(qt), n).reshape(shape)
+
+    Q4, Q6 = gguf.GGMLQuantizationType.Q4_K, gguf.GGMLQuantizationType.Q6_K
+    for n in ("gate", "up"):
+        add_q(f"blk.0.ffn_{n}.weight", (I, H), Q4)
+        add_q(f"blk.1.ffn_{n}_exps.weight", (E, I, H), Q4)
+        add_q(f"blk.1.ffn_{n}_shexp.weight", (I, H), Q4)
+    add_q("blk.0.ffn_down.weight", (H, I), Q6)
+    add_q("blk.1.ffn_down_exps.weight", (E, H, I), Q6)
+    add_q("blk.1.ffn_down_shexp.weight", (H, I), Q6)
+    gi = rng.standard_normal((E, H)).astype(np.float32)
+    gb = rng.standard_normal((E,)).astype(np.float32)
+    w.add_tensor("blk.1.ffn_gate_inp.weight", gi)
+    w.add_tensor("blk.1.exp_probs_b.bias", gb)
+    dense["blk.1.ffn_gate_inp.weight"], dense["blk.1.exp_probs_b.bias"] = gi, gb
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    return dense
+
+
+def test_injected_v3_moe_decodes_through_one_launch_and_matches_dense(tmp_path):
+    from ktransformers_b200 import native
+    from ktransformers_b200.models.modeling_deepseek_v3 import DeepseekV3Config, DeepseekV3MoEOnlyForCausalLM
+    from ktransformers_b200.operators.experts import KDeepseekV3MoE, KExpertsB200
+    from ktransformers_b200.operators.gate import KMoEGateB200
+    from ktransformers_b200.optimize.optimize import optimize_and_load_gguf
+    import ktransformers_b200.optimize.optimize as opt
+    dense = _write_gguf(str(tmp_path / "tiny.gguf"))
+    rule = os.path.join(os.path.dirname(opt.__file__), "optimize_rules", "DeepSeek-V3-Chat-b200.yaml")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        cfg = DeepseekV3Config(hidden_size=H, intermediate_size=I, moe_intermediate_size=I, n_routed_experts=E, n_shared_experts=1,
+                               num_experts_per_tok=K, n_group=2, topk_group=1, num_hidden_layers=2, first_k_dense_replace=1)
+        with torch.device("meta"):
+            model = DeepseekV3MoEOnlyForCausalLM(cfg)
+        optimize_and_load_gguf(model, rule, str(tmp_path), cfg, default_device="cuda")
+        moe = model.model.layers[1].mlp
+        assert isinstance(moe, KDeepseekV3MoE) and isinstance(moe.gate, KMoEGateB200)
+        assert isinstance(moe.experts.generate_experts, KExpertsB200) and moe.experts.generate_experts.handle is not None
+
+        W = {k: torch.from_numpy(np.array(v)).cuda() for k, v in dense.items()}
+        for n_tok in (1, 3, 12):
+            x = (torch.randn(1, n_tok, H, device="cuda") / 10).to(torch.bfloat16)
+            n0 = native.launch_count()
+            y = moe(x)
+            torch.cuda.synchronize()
+            launches = native.launch_count() - n0
+            assert (launches == 1) if n_tok <= 8 else (launches >= 5), launches     # block call | gate + 2 (experts) + shared-expert linears
+            # the reference's three-step control flow gives the same bits (decode) / dense fp32 agrees (all)
+            if n_tok <= 8:
+                keep, KDeepseekV3MoE.BLOCK_MAX_TOKENS = KDeepseekV3MoE.BLOCK_MAX_TOKENS, 0
+                try:
+                    y3 = moe(x)
+                finally:
+                    KDeepseekV3MoE.BLOCK_MAX_TOKENS = keep
+                idx, wt = moe.last_topk
+                ridx, rwt = moe.gate(x)
+                assert torch.equal(idx, ridx) and torch.equal(wt, rwt)
+                # shared expert: one fused MLP handle vs three KLinearB200 calls with bf16 hand-offs -> close, not equal
+                assert (y.float() - y3.float()).abs().max() <= 0.03 * y3.float().abs().max()
+            xf = x.view(-1, H).float()
+            idx, wt = moe.gate(x)
+            ref = torch.zeros_like(xf)
+            for t in range(xf.shape[0]):
+                for j in range(K):
+                    e = int(idx[t, j])
+                    g, u, d = W["blk.1.ffn_gate_exps.weight"][e], W["blk.1.ffn_up_exps.weight"][e], W["blk.1.ffn_down_exps.weight"][e]
+                    ref[t] += (torch.nn.functional.silu(g @ xf[t]) * (u @ xf[t])) @ d.T * wt[t, j]
+            sh = (torch.nn.functional.silu(xf @ W["blk.1.ffn_gate_shexp.weight"].T) * (xf @ W["blk.1.ffn_up_shexp.weight"].T)) @ W["blk.1.ffn_down_shexp.weight"].T
+            want = ref + sh
+            # int8 activations (the reference CPU arithmetic) vs dense fp32: ~1-2 % of the output scale
+            assert (y.view(-1, H).float() - want).abs().max() <= 0.05 * want.abs().max()
+    finally:
+        torch.set_default_dtype(old)
