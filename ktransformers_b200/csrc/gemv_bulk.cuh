@@ -23,6 +23,7 @@
 
 namespace ktb {
 
+constexpr int kActBlkStride = QK_K + 16;   // int8 activation blocks padded to 272 B: 8 lanes x LDS.128 hit 32 distinct banks
 constexpr int kBulkMaxWarps = 18;        // gate/up kernel (<= 96 registers per thread)
 constexpr int kBulkMaxWarpsDown = 16;    // down kernel: 128 registers per thread, and shared memory caps it at 15 anyway
 

@@ -205,40 +205,6 @@ static int launch_rows_pipe(const RowsParams& p, int T, int device, cudaStream_t
     return KTB200_OK;
 }
 
-// Q4_K, one lane per super-block (rows_pipe_q4k_blk_kernel).  Returns 1 when the shape does not suit it.
-template <bool PAIR>
-static int launch_rows_pipe_q4k_blk(const RowsParams& p, int T, int device, cudaStream_t stream) {
-    if (cfg_pipe() < 2) return 1;
-    const int nblk = p.ncols / QK_K;
-    const int row_bytes = nblk * SZ_Q4_K;
-    const int slot = row_bytes * (PAIR ? 2 : 1);
-    const int act = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
-    if (slot < 4096 || nblk < 16) return 1;             // needs >= 16 blocks per row to keep most lanes busy
-    // (warps, slots): 24 x 1 by default (more eligible warps per scheduler), 12 x 2 with KTB200_PIPE_SLOTS=2
-    static const int want_slots = env_int("KTB200_PIPE_SLOTS", 2);
-    const long total = (long)(p.slots + (p.x0 ? 1 : 0)) * p.rows;
-    if (total >= (1L << 30) || p.slots + 1 > 36) return 1;
-    int gx = num_sms(device);            // one CTA per SM walks all T tokens
-    if (gx > total) gx = (int)total;
-    if (gx < 1) gx = 1;
-    dim3 grid(gx, 1);
-#define KTB_BLK(W, S)                                                                                                  \
-    do {                                                                                                               \
-        const size_t smem = (size_t)act + (size_t)(W) * (S) * slot;                                                    \
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(rows_pipe_q4k_blk_kernel<PAIR, W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rows_pipe_q4k_blk_kernel<PAIR, W, S><<<grid, (W) * 32, smem, stream>>>(p, act, slot);                        \
-    } while (0)
-    const size_t cap = 220 * 1024;
-    if (want_slots != 2 && (size_t)act + (size_t)24 * slot <= cap) KTB_BLK(24, 1);
-    else if ((size_t)act + (size_t)12 * 2 * slot <= cap) KTB_BLK(12, 2);
-    else if ((size_t)act + (size_t)16 * slot <= cap) KTB_BLK(16, 1);
-    else if ((size_t)act + (size_t)8 * 2 * slot <= cap) KTB_BLK(8, 2);
-    else return 1;
-#undef KTB_BLK
-    KTB_LAUNCH_CHECK();
-    return KTB200_OK;
-}
-
 // Q4_K rows through the bulk-copy ring (rows_bulk_q4k_kernel).  Returns 1 when the shape does not suit it.
 template <bool PAIR>
 static int launch_rows_bulk_q4k(const RowsParams& p, int T, int device, cudaStream_t stream) {
@@ -281,8 +247,6 @@ static int launch_rows(FmtId f, const RowsParams& p_in, int T, int device, cudaS
     if (f == FMT_Q4K) {
         const int rcb = launch_rows_bulk_q4k<PAIR>(p, T, device, stream);
         if (rcb != 1) return rcb;
-        const int rc = launch_rows_pipe_q4k_blk<PAIR>(p, T, device, stream);
-        if (rc != 1) return rc;
     }
     if (f == FMT_Q4K || f == FMT_Q5K) {
         const int rc = (f == FMT_Q4K) ? launch_rows_pipe<FmtQ4K32, PAIR>(p, T, device, stream) : launch_rows_pipe<FmtQ5K, PAIR>(p, T, device, stream);
@@ -356,38 +320,6 @@ static int launch_reduce_pipe_q6k8(const ReduceParams& p, int T, int device, cud
         reduce_pipe_q6k8_kernel<12, 2><<<grid, 12 * 32, smem, stream>>>(p, slot);
     } else {
         return 1;
-    }
-    KTB_LAUNCH_CHECK();
-    return KTB200_OK;
-}
-
-// Q6_K, one lane per super-block (reduce_pipe_q6k_blk_kernel).  Returns 1 when the shape does not suit it.
-static int launch_reduce_pipe_q6k_blk(const ReduceParams& p, int T, int device, cudaStream_t stream) {
-    if (cfg_pipe() < 2) return 1;
-    const int nb = p.ncols / QK_K;
-    if (p.rows % 4 || nb % 2 || (4 * nb) % 8) return 1;
-    const int ns = p.slots + (p.xw ? 1 : 0);
-    const int nrb = 4 * nb;
-    const int slot = (nrb * (kQ6QlStride + kQ6QhStride + 16) + nrb * 2 + 15) & ~15;
-    if (slot < 4096) return 1;
-    const int quads = p.rows / 4;
-    if (ns > 36) return 1;
-    int gx = num_sms(device);            // one CTA per SM walks all T tokens
-    if (gx > quads) gx = quads;
-    if (gx < 1) gx = 1;
-    const int nrows_max = ((quads + gx - 1) / gx + 1) * 4;
-    const size_t base = (size_t)ns * nb * (kActBlkStride + 32 + 4) + (size_t)nrows_max * ns * 4 + 16;
-    int warps = 0;
-    for (int w : {12, 8}) if (base + (size_t)w * 2 * slot <= 220 * 1024) { warps = w; break; }
-    if (!warps) return 1;
-    const size_t smem = base + (size_t)warps * 2 * slot;
-    dim3 grid(gx, 1);
-    if (warps == 12) {
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k_blk_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reduce_pipe_q6k_blk_kernel<12><<<grid, 12 * 32, smem, stream>>>(p, slot);
-    } else {
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(reduce_pipe_q6k_blk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reduce_pipe_q6k_blk_kernel<8><<<grid, 8 * 32, smem, stream>>>(p, slot);
     }
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
@@ -471,9 +403,7 @@ static int launch_reduce(FmtId f, const ReduceParams& p_in, int T, int device, c
         if (rc != 1) return rc;
     }
     if (f == FMT_Q6K8) {
-        int rc = launch_reduce_pipe_q6k_blk(p, T, device, stream);
-        if (rc != 1) return rc;
-        rc = launch_reduce_pipe_q6k8(p, T, device, stream);
+        const int rc = launch_reduce_pipe_q6k8(p, T, device, stream);
         if (rc != 1) return rc;
     }
     switch (f) {
