@@ -253,24 +253,20 @@ __device__ __forceinline__ void blk_quantize_a(int t) {
         x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
         return true;
     };
-    // two blocks per iteration (independent dependency chains for the scheduler), the next two already in flight
-    float c0[8], c1[8], n0[8], n1[8];
+    float cur[8], nxt[8];
     int gb = warp;
-    bool l0 = gb < totalb && fetch(gb, c0), l1 = gb + W < totalb && fetch(gb + W, c1);
+    bool live = gb < totalb && fetch(gb, cur);
 #pragma unroll 1
     while (gb < totalb) {
-        const int gn = gb + 2 * W;
-        const bool m0 = gn < totalb && fetch(gn, n0), m1 = gn + W < totalb && fetch(gn + W, n1);
-        if (l0)
-            warp_quantize_q8k_block(c0, lane, reinterpret_cast<uint32_t*>(L.aq + (size_t)gb * kActBlkStride), L.adx + gb,
+        const int gn = gb + W;
+        const bool nlive = gn < totalb && fetch(gn, nxt);
+        if (live)
+            warp_quantize_q8k_block(cur, lane, reinterpret_cast<uint32_t*>(L.aq + (size_t)gb * kActBlkStride), L.adx + gb,
                                     KBS == 16 ? L.abs_ + gb * 16 : nullptr, KBS == 8 ? L.abs_ + gb * 8 : nullptr);
-        if (l1)
-            warp_quantize_q8k_block(c1, lane, reinterpret_cast<uint32_t*>(L.aq + (size_t)(gb + W) * kActBlkStride), L.adx + gb + W,
-                                    KBS == 16 ? L.abs_ + (gb + W) * 16 : nullptr, KBS == 8 ? L.abs_ + (gb + W) * 8 : nullptr);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { c0[i] = n0[i]; c1[i] = n1[i]; }
+        for (int i = 0; i < 8; i++) cur[i] = nxt[i];
         gb = gn;
-        l0 = m0; l1 = m1;
+        live = nlive;
     }
 }
 

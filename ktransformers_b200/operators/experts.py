@@ -316,6 +316,14 @@ class _KDeepseekMoEMixin:
 
     BLOCK_MAX_TOKENS = 8
 
+    def load(self):
+        """children first (base_operator.py:45-48), then the shared expert's handle for the single-launch path: handles
+        are created here, never inside forward (which may be running under CUDA-graph capture)."""
+        super().load()
+        gen = getattr(getattr(self, "experts", None), "generate_experts", None)
+        if isinstance(gen, KExpertsB200) and gen.handle is not None and self.config.n_shared_experts is not None:
+            self._shared_mlp_handle(gen)
+
     def _block_handles(self, x):
         """(gate_cfg, moe_handle, mlp_handle_or_None) when the single-launch path applies, else None."""
         gate, gen = getattr(self, "gate", None), getattr(getattr(self, "experts", None), "generate_experts", None)
@@ -333,7 +341,7 @@ class _KDeepseekMoEMixin:
                                 gate._b.data_ptr() if gate._b is not None else None, gen.hidden_type)
         mlp = None
         if self.config.n_shared_experts is not None:
-            mlp = self._shared_mlp_handle(gen)
+            mlp = getattr(self, "_ktb_mlp", None)
             if mlp is None:
                 return None
         return cfg, gen.handle, mlp
