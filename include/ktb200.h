@@ -209,7 +209,8 @@ int ktb200_moe_gate_forward(const ktb200_gate_config* cfg, int qlen, const void*
  * combine; weights stream through the copy engine across the barriers); any other configuration runs as
  * ktb200_moe_gate_forward + ktb200_moe_forward_shared.  Results are bit-identical between the two.
  * idx_dev int64 [qlen][top_k] and w_dev fp32 [qlen][top_k] receive the routing (as from ktb200_moe_gate_forward).
- * `shared` may be NULL.  The first call per device allocates scratch: make it before CUDA-graph capture.
+ * `shared` may be NULL.  Capturable as is (its scratch belongs to the moe handle); when it falls back to the separate
+ * launches, ktb200_moe_gate_forward's first-call allocation rule applies.
  * ------------------------------------------------------------------------------------------ */
 int ktb200_moe_block_forward(const ktb200_gate_config* gate, ktb200_moe* moe, ktb200_mlp* shared, int qlen,
                              const void* input_dev, void* output_dev, int64_t* idx_dev, float* w_dev,

@@ -39,6 +39,11 @@ struct ktb200_moe {
     float* w_d;
     void* in_d;
     void* out_d;
+    // scratch of the persistent MoE-block kernel (moe_block.cu): router partial sums [8 tokens][8 splits][512 experts]
+    // and two pairs of grid-barrier words used alternately (zero between launches)
+    float* blk_partial;
+    unsigned* blk_sync;
+    unsigned blk_flip;
 };
 
 struct DeviceGuard {

@@ -523,11 +523,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
     }
 }
 
-// per-device scratch: router partial sums [kBlockMaxTokens][S<=8][E<=512] + the two barrier words
-static float* g_bpartial[64] = {nullptr};
-static unsigned* g_bsync[64] = {nullptr};   // two pairs of barrier words, used alternately: with programmatic dependent
-static unsigned g_bflip[64] = {0};           // launch the next kernel's CTAs may arrive before this one's last CTA resets its pair
-
 static unsigned long long* g_btrace = nullptr;
 
 static int env_fused() {
@@ -563,7 +558,7 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
                  gc->n_experts % gc->n_group == 0 && gc->topk_group >= 1 && gc->topk_group <= gc->n_group && gc->weight &&
                  gc->scoring >= 0 && gc->scoring <= 1 && gc->topk_method >= 0 && gc->topk_method <= 2 && k <= gc->n_experts;
     DeviceGuard guard(m->device);
-    const int dev = m->device, d = dev & 63;
+    const int dev = m->device;
     cudaStream_t s = (cudaStream_t)stream;
     BlockParams p{};
     size_t smem = 0;
@@ -601,19 +596,14 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     }
 
     const int S = gate_splits(gc->n_experts, gc->hidden_size, num_sms(dev));
-    if (!g_bpartial[d]) {   // not capturable: call once before graph capture (the first call allocates)
-        KTB_CUDA_CHECK(cudaMalloc(&g_bpartial[d], (size_t)kBlockMaxTokens * 8 * kGateThreads * kGateEPT * sizeof(float)));
-        KTB_CUDA_CHECK(cudaMalloc(&g_bsync[d], 4 * sizeof(unsigned)));
-        KTB_CUDA_CHECK(cudaMemset(g_bsync[d], 0, 4 * sizeof(unsigned)));
-    }
     p.g = GateParams{gc->weight, input, gc->hidden_type, gc->n_experts, gc->hidden_size, qlen, S, k, gc->n_group, gc->topk_group,
-                     gc->scoring, gc->topk_method, gc->norm_topk_prob, gc->routed_scaling_factor, gc->bias, g_bpartial[d], nullptr,
+                     gc->scoring, gc->topk_method, gc->norm_topk_prob, gc->routed_scaling_factor, gc->bias, m->blk_partial, nullptr,
                      idx, w, bsz, nullptr};
     p.w_gate = c.gate_proj; p.w_up = c.up_proj; p.w_down = c.down_proj;
     p.s_gate = sh ? sh->gate : nullptr; p.s_up = sh ? sh->up : nullptr; p.s_down = sh ? sh->down : nullptr;
     p.n_local = c.expert_num; p.id_offset = c.expert_id_offset;
     p.H = c.hidden_size; p.I = c.intermediate_size; p.k = k; p.hidden_type = c.hidden_type; p.use_silu = c.use_silu;
-    p.inter = m->inter; p.out = output; p.sync = g_bsync[d] + 2 * (g_bflip[d]++ & 1u); p.trace = g_btrace;
+    p.inter = m->inter; p.out = output; p.sync = m->blk_sync + 2 * (m->blk_flip++ & 1u); p.trace = g_btrace;
     static const int prime_u = [] { const char* e = getenv("KTB200_BLK_PRIME_U"); return e ? atoi(e) : 3; }();
     static const int prime_d = [] { const char* e = getenv("KTB200_BLK_PRIME_D"); return e ? atoi(e) : 2; }();
     p.prime_u = prime_u; p.prime_d = prime_d;
