@@ -298,6 +298,36 @@ def main():
     side_stream = torch.cuda.Stream() if world > 1 else None
     y_sh = torch.zeros((1, H), dtype=torch.bfloat16, device=dev)
 
+    # expert-parallel exchange over NVLink peer memory (ktb200_ep_*): one symmetric allocation per rank holds the
+    # token buffer, the fp32 partial buffer and the flag block; torch's symmetric memory maps the peers' copies.
+    # KTB200_EP_P2P=0 (or a failing rendezvous) keeps the NCCL collectives.
+    ep = None
+    ep_mode = "nccl all_gather + reduce_scatter"
+    if world > 1 and os.environ.get("KTB200_EP_P2P", "1") != "0":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            tok_b, part_b, flag_b = T * H * 2, T * H * 4, 4 * (2 * T + 2)
+            o_part = (tok_b + 255) // 256 * 256
+            o_flag = o_part + (part_b + 255) // 256 * 256
+            total_b = o_flag + (flag_b + 255) // 256 * 256
+            sym = symm_mem.empty(total_b, dtype=torch.uint8, device=dev)
+            sym.zero_()
+            hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+            base = [int(p_) for p_ in hdl.buffer_ptrs]
+            ep = native.EpComm.make(rank, world, H, BF16, base, [b + o_part for b in base], [b + o_flag for b in base])
+            part = sym[o_part:o_part + part_b].view(torch.float32).view(T, H)      # the shard's kernels write the symmetric copy
+            torch.cuda.synchronize(); dist.barrier()
+            ep_mode = "hand-written NVLink peer-memory exchange (ktb200_ep_all_gather_tokens / ktb200_ep_reduce_own_token)"
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                print(f"# symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            ep = None
+        ok = torch.tensor([1 if ep is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)               # all ranks or none
+        if int(ok.item()) == 0:
+            ep, ep_mode = None, "nccl all_gather + reduce_scatter"
+            part = torch.zeros((T, H), dtype=hid_torch, device=dev)
+
     def layer_device(l):
         Lr = layers[l % L]
         if world == 1:
@@ -311,6 +341,14 @@ def main():
         side_stream.wait_stream(main)
         with torch.cuda.stream(side_stream):
             native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y_sh.data_ptr(), 0, None, S()))
+        if ep is not None:
+            native.check(lib.ktb200_ep_all_gather_tokens(C.byref(ep), x_own.data_ptr(), x_all_f32.data_ptr(), S()))
+            # the router reads the gathered bf16 rows in this rank's symmetric token buffer
+            native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, ep._keep[0][rank], ids.data_ptr(), wts.data_ptr(), None, None, S()))
+            native.check(lib.ktb200_moe_forward(Lr["moe"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(), None, S()))
+            main.wait_stream(side_stream)
+            native.check(lib.ktb200_ep_reduce_own_token(C.byref(ep), y.data_ptr(), y_sh.data_ptr(), S()))
+            return
         dist.all_gather_into_tensor(x_all, x_own)
         xin = x_all
         native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, xin.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))
@@ -488,7 +526,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8xint4/int6->int32 dp4a, fp32 scales+accumulate, bf16 in/out", "data": "synthetic",
-                "config": workload_config(args, world), "clocks": clocks,
+                "config": {**workload_config(args, world), **({"ep_exchange": ep_mode} if world > 1 else {})}, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
                 "gpu_launches": launches_per_step * args.steps, "cuda_graph": graph is not None,
                 "roofline": roof_block if roof_block else roof, "roofline_gate_up": roof, "roofline_down": roof_down, "cpu_baseline": cpu_baseline,

@@ -221,6 +221,31 @@ int ktb200_moe_block_forward_host(const ktb200_gate_config* gate, ktb200_moe* mo
                                   const void* input_host, void* output_host, int64_t* idx_host, float* w_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Expert-parallel token exchange over NVLink peer memory (one process per GPU).  The reference shards experts over
+ * devices with `gpu_experts_mask` and exchanges activations through torch / NCCL (kt-kernel/python/experts_base.py:
+ * 377-483, archive/ktransformers/operators/experts.py:143-318 for the CPU<->GPU hand-off); here every rank maps the
+ * others' buffers (CUDA IPC / torch symmetric memory: the caller owns the allocation and the mapping) and two small
+ * kernels move one decode layer's tokens and partial sums with direct peer stores / loads and system-scope flags.
+ *   token_bufs[r]   : rank r's token buffer   [world][hidden] hidden_type   (this rank writes row `rank` of every one)
+ *   partial_bufs[r] : rank r's partial buffer [world][hidden] fp32          (this rank reads row `rank` of every one)
+ *   flag_bufs[r]    : rank r's flag block, 2*world + 2 uint32, zero-initialised once
+ * all three are HOST arrays of `world` DEVICE pointers valid on this rank.  Every rank must issue the same sequence of
+ * calls (they are barriers).  Graph-capturable; epochs live in the flag block.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ktb200_ep_comm {
+    int rank, world, hidden_size, hidden_type;
+    void* const* token_bufs;
+    float* const* partial_bufs;
+    unsigned* const* flag_bufs;
+} ktb200_ep_comm;
+/* all-gather: x_own [hidden] -> row `rank` of every rank's token buffer; returns when all `world` rows of THIS rank's
+ * buffer are complete; x_all_f32 (optional, [world][hidden]) receives them converted to fp32. */
+int ktb200_ep_all_gather_tokens(const ktb200_ep_comm* comm, const void* x_own_dev, float* x_all_f32_dev, void* stream);
+/* reduce-scatter + epilogue: y_out[hidden] = round_hidden(sum over ranks r of partial_bufs[r][rank][:]) (+ y_shared,
+ * the already rounded shared-expert term, optional).  Call after the kernels that wrote this rank's partial buffer. */
+int ktb200_ep_reduce_own_token(const ktb200_ep_comm* comm, void* y_out_dev, const void* y_shared_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Absorbed-MLA paged decode attention.  Replaces MLAWrapper.run / BatchMLAPagedAttentionWrapper
  * (archive/ktransformers/operators/flashinfer_wrapper.py:117-161; attention.py:419-447) and the
  * Triton split-KV decode (triton_attention.py:358-385).

@@ -78,12 +78,28 @@ SYMBOLS = {
     "ktb200_moe_gate_forward": (_I, [C.POINTER(GateConfig), _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ktb200_moe_block_forward": (_I, [C.POINTER(GateConfig), _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ktb200_moe_block_forward_host": (_I, [C.POINTER(GateConfig), _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "ktb200_ep_all_gather_tokens": (_I, [_VP, _VP, _VP, _VP]),
+    "ktb200_ep_reduce_own_token": (_I, [_VP, _VP, _VP, _VP]),
     "ktb200_debug_block_trace": (None, [_VP]),
     "ktb200_debug_stream_read": (_I, [_VP, _L, _I, _I, _I, _I, _VP, C.POINTER(C.c_float)]),
     "ktb200_mla_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "ktb200_mla_decode": (_I, [C.POINTER(MlaParams), _VP]),
     "ktb200_mla_kv_write": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP]),
 }
+
+
+class EpComm(C.Structure):
+    """ktb200_ep_comm (include/ktb200.h): peer-mapped token / partial / flag buffers of an expert-parallel group."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("hidden_size", C.c_int), ("hidden_type", C.c_int),
+                ("token_bufs", C.POINTER(C.c_void_p)), ("partial_bufs", C.POINTER(C.c_void_p)), ("flag_bufs", C.POINTER(C.c_void_p))]
+
+    @classmethod
+    def make(cls, rank, world, hidden_size, hidden_type, tok_ptrs, part_ptrs, flag_ptrs):
+        arr = lambda ps: (C.c_void_p * world)(*[int(x) for x in ps])
+        c = cls(rank, world, hidden_size, hidden_type)
+        c._keep = (arr(tok_ptrs), arr(part_ptrs), arr(flag_ptrs))      # the host arrays must outlive the struct
+        c.token_bufs, c.partial_bufs, c.flag_bufs = (C.cast(a, C.POINTER(C.c_void_p)) for a in c._keep)
+        return c
 
 
 def build(verbose: bool = False) -> str:
