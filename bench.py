@@ -482,8 +482,8 @@ def main():
             roof_block = {"kernel": "moe_block_kernel<BulkQ6K4T> (router GEMV + top-k + gate/up + SiLU*mul + down + combine, 1 launch/layer)",
                           "bound": "hbm", "achieved": bytes_b / (ms_b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": bytes_b / (ms_b * 1e-3) / 1e9 / peak, "peak_source": how,
-                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01f_kernels.md)
-                          "traffic": 265_867_264 + 16_657_408,
+                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01g_kernels.md)
+                          "traffic": 266_550_272 + 6_998_784,
                           "bytes_per_launch": bytes_b, "ms_per_launch": ms_b}
     if rank == 0:
         gu, dn = [], []
