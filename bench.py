@@ -335,20 +335,22 @@ def main():
             native.check(lib.ktb200_moe_block_forward(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], 1, x_own.data_ptr(), y.data_ptr(),
                                                       ids.data_ptr(), wts.data_ptr(), None, S()))
             return
-        # expert-parallel: the shared expert of this GPU's own token needs no communication: it runs on a side stream
-        # under the all-gather, and joins as the second rounded term (KDeepseekV3MoE.forward, experts.py:984-1011)
         main = torch.cuda.current_stream()
+        if ep is not None:
+            # expert-parallel layer in 5 launches: peer-memory all-gather (+ fp32 rows), router, the shard's two expert
+            # launches (the shared expert of this GPU's own token rides along as an extra slot), peer-memory reduction
+            # with the epilogue y = round(sum of partials) + round(shared)   (KDeepseekV3MoE.forward, experts.py:984-1011)
+            native.check(lib.ktb200_ep_all_gather_tokens(C.byref(ep), x_own.data_ptr(), x_all_f32.data_ptr(), S()))
+            native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, ep._keep[0][rank], ids.data_ptr(), wts.data_ptr(), None, None, S()))
+            native.check(lib.ktb200_moe_forward_ep(Lr["moe"], Lr["mlp"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(),
+                                                   rank, y_sh.data_ptr(), None, S()))
+            native.check(lib.ktb200_ep_reduce_own_token(C.byref(ep), y.data_ptr(), y_sh.data_ptr(), S()))
+            return
+        # NCCL route: the shared expert of this GPU's own token needs no communication: it runs on a side stream under the
+        # all-gather, and joins as the second rounded term
         side_stream.wait_stream(main)
         with torch.cuda.stream(side_stream):
             native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y_sh.data_ptr(), 0, None, S()))
-        if ep is not None:
-            native.check(lib.ktb200_ep_all_gather_tokens(C.byref(ep), x_own.data_ptr(), x_all_f32.data_ptr(), S()))
-            # the router reads the gathered bf16 rows in this rank's symmetric token buffer
-            native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, ep._keep[0][rank], ids.data_ptr(), wts.data_ptr(), None, None, S()))
-            native.check(lib.ktb200_moe_forward(Lr["moe"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(), None, S()))
-            main.wait_stream(side_stream)
-            native.check(lib.ktb200_ep_reduce_own_token(C.byref(ep), y.data_ptr(), y_sh.data_ptr(), S()))
-            return
         dist.all_gather_into_tensor(x_all, x_own)
         xin = x_all
         native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, xin.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))

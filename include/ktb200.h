@@ -198,6 +198,17 @@ typedef struct ktb200_gate_config {
 int ktb200_moe_gate_forward(const ktb200_gate_config* cfg, int qlen, const void* x_dev, int64_t* idx_dev,
                             float* w_dev, float* logits_dev, const int* bsz_tensor_dev, void* stream);
 
+/* Expert-parallel shard form of ktb200_moe_forward_shared: `partial_out` [qlen][hidden] receives the routed partial sums
+ * of the experts this shard owns (hidden_type of the moe handle, fp32 for an exact cross-rank sum), and the shared
+ * expert is computed for token `own_token` ONLY, as an extra slot of the same two launches; its result goes, rounded
+ * to the shared handle's hidden_type, to shared_out [hidden] (it is the second, separately rounded term of
+ * `y = experts(x); y += shared_experts(x)`, experts.py:984-1011, to be added after the cross-rank reduction).
+ * Needs the bulk-copy kernels (Q4_K gate/up rows of >= 16 super-blocks, tile-layout Q6_K or Q4_K down) and a shared
+ * expert with the routed experts' shapes and weight types; KTB200_EINVAL otherwise (run the two calls separately). */
+int ktb200_moe_forward_ep(ktb200_moe* moe, ktb200_mlp* shared, int qlen, int k, const int64_t* expert_ids_dev,
+                          const float* weights_dev, const void* input_dev, void* partial_out_dev, int own_token,
+                          void* shared_out_dev, const int* bsz_tensor_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * The whole MoE block of a decoder layer in ONE call — KDeepseekV3MoE.forward
  * (archive/ktransformers/operators/experts.py:972-1012):

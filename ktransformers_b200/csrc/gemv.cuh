@@ -47,6 +47,8 @@ struct RowsParams {
     // the routed launch (KDeepseekV3MoE: y = experts(x) + shared_experts(x), experts.py:984-1011)
     const void* x0;
     const void* x1;
+    int shared_token;       // -1: the extra slot applies to every token; t >= 0: to token t only (expert-parallel shards
+                            // compute the shared expert for their own token)
 };
 
 // one batch of N steps starting at step s0 for RW rows x NM matrices; all rows share ONE activation row
@@ -207,6 +209,9 @@ struct ReduceParams {
     int ntokens;            // T
     const void* xw;         // optional extra slot (shared expert down_proj); its result is rounded to
                             // hidden_type separately and added like `y += y_` (experts.py:1011)
+    int shared_token;       // see RowsParams
+    void* xw_out;           // null: add the shared term to `out` as above; else store it, rounded to xw_out_type, to
+    int xw_out_type;        // xw_out[t][rows] and leave `out` = the routed sum only
 };
 
 // Work item of a warp = (slot j, 4 consecutive output rows): the 4 rows share slot j's int8 activations,

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32, 1) rows_bulk_q4k_kernel(co
                 const long e = p.ids ? (long)p.ids[(long)(t0 + tl) * p.slots + s] - p.id_offset : 0;
                 if (e >= 0 && e < p.n_experts) pairs[np++] = (tl << 8) | s;
             }
-            if (p.x0) pairs[np++] = (tl << 8) | p.slots;
+            if (p.x0 && (p.shared_token < 0 || p.shared_token == t0 + tl)) pairs[np++] = (tl << 8) | p.slots;
         }
         s_np = np;
     }
@@ -367,7 +367,8 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
     if (threadIdx.x == 0) {   // greedy chunk: tokens t0.. while their owned pairs fit
         int np = 0, nt = 0;
         while (t0 + nt < Teff && nt < kBulkMaxChunkTokens) {
-            int cnt = p.xw ? 1 : 0;
+            const bool sh_here = p.xw && (p.shared_token < 0 || p.shared_token == t0 + nt);
+            int cnt = sh_here ? 1 : 0;
             for (int j = 0; j < k; j++) {
                 const long e = p.ids ? (long)p.ids[(long)(t0 + nt) * k + j] - p.id_offset : 0;
                 cnt += (e >= 0 && e < p.n_experts) ? 1 : 0;
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
                 const long e = p.ids ? (long)p.ids[(long)(t0 + nt) * k + j] - p.id_offset : 0;
                 if (e >= 0 && e < p.n_experts) pairs[np++] = (nt << 8) | j;
             }
-            if (p.xw) pairs[np++] = (nt << 8) | k;
+            if (sh_here) pairs[np++] = (nt << 8) | k;
             nt++;
         }
         s_first[nt] = np;
@@ -473,7 +474,10 @@ __global__ void __launch_bounds__(kBulkMaxWarpsDown * 32, 1) reduce_bulk_kernel(
             else acc = p.weights ? __fmaf_rn(dv, p.weights[t * k + j], acc) : acc + dv;
         }
         const long o = t * p.rows + r0 + hl;
-        if (p.xw) acc = round_hidden(acc, p.hidden_type) + round_hidden(shared, p.hidden_type);
+        bool has_sh = false;
+        for (int pi = s_first[tl]; pi < s_first[tl + 1]; pi++) has_sh |= (pairs[pi] & 0xff) == k;
+        if (p.xw_out) { if (has_sh) store_hidden(p.xw_out, o, p.xw_out_type, shared); }
+        else if (p.xw) acc = round_hidden(acc, p.hidden_type) + round_hidden(shared, p.hidden_type);
         if (p.accumulate) acc = load_hidden(p.out, o, p.hidden_type) + round_hidden(acc, p.hidden_type);
         store_hidden(p.out, o, p.hidden_type, acc);
     }

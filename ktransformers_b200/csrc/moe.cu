@@ -248,6 +248,7 @@ static int launch_rows(FmtId f, const RowsParams& p_in, int T, int device, cudaS
         const int rcb = launch_rows_bulk_q4k<PAIR>(p, T, device, stream);
         if (rcb != 1) return rcb;
     }
+    if (p.x0 && p.shared_token >= 0) { set_error("per-token shared slot: only the bulk-copy kernels implement it"); return KTB200_EINVAL; }
     if (f == FMT_Q4K || f == FMT_Q5K) {
         const int rc = (f == FMT_Q4K) ? launch_rows_pipe<FmtQ4K32, PAIR>(p, T, device, stream) : launch_rows_pipe<FmtQ5K, PAIR>(p, T, device, stream);
         if (rc != 1) return rc;
@@ -402,6 +403,7 @@ static int launch_reduce(FmtId f, const ReduceParams& p_in, int T, int device, c
         const int rc = launch_reduce_bulk<BulkQ4K>(p, T, device, stream);
         if (rc != 1) return rc;
     }
+    if (p.xw && (p.shared_token >= 0 || p.xw_out)) { set_error("per-token shared slot: only the bulk-copy kernels implement it"); return KTB200_EINVAL; }
     if (f == FMT_Q6K8) {
         const int rc = launch_reduce_pipe_q6k8(p, T, device, stream);
         if (rc != 1) return rc;
@@ -528,7 +530,8 @@ int ktb200_moe_load_weights(ktb200_moe* m, void* stream) {
 float* ktb200_moe_intermediate(ktb200_moe* m) { return m ? m->inter : nullptr; }
 
 static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
-                            void* output, const int* bsz, cudaStream_t s, cudaEvent_t mid, const ktb200_mlp* sh = nullptr) {
+                            void* output, const int* bsz, cudaStream_t s, cudaEvent_t mid, const ktb200_mlp* sh = nullptr,
+                            int shared_token = -1, void* shared_out = nullptr) {
     if (!m) { set_error("null handle"); return KTB200_EINVAL; }
     if (!m->loaded) { set_error("Not Loaded"); return KTB200_ESTATE; }
     if (qlen <= 0) return KTB200_OK;
@@ -541,6 +544,7 @@ static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, 
     FmtId fg = pick_fmt(c.gate_type, m->gu_soa), fu = pick_fmt(c.up_type, m->gu_soa);
     if (fg != fu) fg = fu = FMT_GENK;  // mixed gate/up types: the generic path reads the type per matrix
     RowsParams rp{};
+    rp.shared_token = -1;
     rp.w0 = c.gate_proj; rp.w1 = c.up_proj; rp.type0 = c.gate_type; rp.type1 = c.up_type;
     rp.n_experts = c.expert_num; rp.rows = c.intermediate_size; rp.ncols = c.hidden_size; rp.slots = k;
     rp.ids = ids; rp.id_offset = c.expert_id_offset; rp.x = input; rp.hidden_type = c.hidden_type;
@@ -549,18 +553,20 @@ static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, 
     // the shared expert rides in the same two launches as slot k when its tensors have the routed experts'
     // shapes and layouts (DeepSeek-V3: n_shared_experts = 1, same quant types); otherwise it runs separately
     const bool fuse = sh && sh->loaded && sh->H == c.hidden_size && sh->I == c.intermediate_size && c.use_silu &&
-                      sh->hidden_type == c.hidden_type && sh->gate_type == c.gate_type && sh->up_type == c.up_type &&
+                      (sh->hidden_type == c.hidden_type || shared_out) && sh->gate_type == c.gate_type && sh->up_type == c.up_type &&
                       sh->down_type == c.down_type && sh->gu_soa == m->gu_soa && sh->down_layout == m->down_layout;
-    if (fuse) { rp.x0 = sh->gate; rp.x1 = sh->up; }
+    if (shared_out && !fuse) { set_error("moe_forward_ep: the shared expert cannot ride in the routed launches"); return KTB200_EINVAL; }
+    if (fuse) { rp.x0 = sh->gate; rp.x1 = sh->up; rp.shared_token = shared_token; }
     int rc = launch_rows<true>(fg, rp, qlen, m->device, s);
     if (rc) return rc;
     if (mid) KTB_CUDA_CHECK(cudaEventRecord(mid, s));
 
     ReduceParams dp{};
+    dp.shared_token = -1;
     dp.w = c.down_proj; dp.type = c.down_type; dp.n_experts = c.expert_num; dp.rows = c.hidden_size;
     dp.ncols = c.intermediate_size; dp.slots = k; dp.ids = ids; dp.id_offset = c.expert_id_offset;
     dp.weights = weights; dp.a = m->inter; dp.out = output; dp.hidden_type = c.hidden_type; dp.accumulate = 0; dp.bsz = bsz;
-    if (fuse) dp.xw = sh->down;
+    if (fuse) { dp.xw = sh->down; dp.shared_token = shared_token; dp.xw_out = shared_out; dp.xw_out_type = sh->hidden_type; }
     rc = launch_reduce(fd, dp, qlen, m->device, s);
     if (rc || !sh || fuse) return rc;
     return ktb200_mlp_forward(const_cast<ktb200_mlp*>(sh), qlen, input, output, 1, bsz, (void*)s);
@@ -570,6 +576,15 @@ int ktb200_moe_forward_shared(ktb200_moe* m, ktb200_mlp* shared, int qlen, int k
                               const void* input, void* output, const int* bsz, void* stream) {
     if (shared && !shared->loaded) { set_error("shared expert: Not Loaded"); return KTB200_ESTATE; }
     return moe_forward_impl(m, qlen, k, ids, weights, input, output, bsz, (cudaStream_t)stream, nullptr, shared);
+}
+
+int ktb200_moe_forward_ep(ktb200_moe* m, ktb200_mlp* shared, int qlen, int k, const int64_t* ids, const float* weights,
+                          const void* input, void* partial_out, int own_token, void* shared_out, const int* bsz, void* stream) {
+    if (!shared || !shared_out || own_token < 0 || own_token >= qlen) { set_error("moe_forward_ep: shared handle, shared_out and 0 <= own_token < qlen are required"); return KTB200_EINVAL; }
+    if (!shared->loaded) { set_error("shared expert: Not Loaded"); return KTB200_ESTATE; }
+    // shared_out rows are indexed like the tokens: point the kernels at a virtual base so that row `own_token` is shared_out
+    uint8_t* base = reinterpret_cast<uint8_t*>(shared_out) - (size_t)own_token * shared->H * type_size(shared->hidden_type);
+    return moe_forward_impl(m, qlen, k, ids, weights, input, partial_out, bsz, (cudaStream_t)stream, nullptr, shared, own_token, base);
 }
 
 int ktb200_moe_forward(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
@@ -683,6 +698,7 @@ int ktb200_linear_forward(ktb200_linear* l, int qlen, const void* input, void* o
     if (!input || !output) { set_error("forward: null pointer"); return KTB200_EINVAL; }
     DeviceGuard g(l->device);
     RowsParams rp{};
+    rp.shared_token = -1;
     rp.w0 = l->proj; rp.w1 = nullptr; rp.type0 = rp.type1 = l->proj_type; rp.n_experts = 1; rp.rows = l->out_size;
     rp.ncols = l->in_size; rp.slots = 1; rp.ids = nullptr; rp.id_offset = 0; rp.x = input; rp.hidden_type = l->hidden_type;
     rp.use_silu = 0; rp.out_f32 = nullptr; rp.out_hidden = output; rp.bias = bias; rp.bsz = bsz;
@@ -752,12 +768,14 @@ int ktb200_mlp_forward(ktb200_mlp* m, int qlen, const void* input, void* output,
     FmtId fg = pick_fmt(m->gate_type, m->gu_soa), fu = pick_fmt(m->up_type, m->gu_soa);
     if (fg != fu) fg = fu = FMT_GENK;
     RowsParams rp{};
+    rp.shared_token = -1;
     rp.w0 = m->gate; rp.w1 = m->up; rp.type0 = m->gate_type; rp.type1 = m->up_type; rp.n_experts = 1; rp.rows = m->I;
     rp.ncols = m->H; rp.slots = 1; rp.ids = nullptr; rp.x = input; rp.hidden_type = m->hidden_type; rp.use_silu = 1;
     rp.out_f32 = m->inter; rp.bsz = bsz;
     int rc = launch_rows<true>(fg, rp, qlen, m->device, s);
     if (rc) return rc;
     ReduceParams dp{};
+    dp.shared_token = -1;
     dp.w = m->down; dp.type = m->down_type; dp.n_experts = 1; dp.rows = m->H; dp.ncols = m->I; dp.slots = 1; dp.ids = nullptr;
     dp.weights = nullptr; dp.a = m->inter; dp.out = output; dp.hidden_type = m->hidden_type; dp.accumulate = accumulate; dp.bsz = bsz;
     return launch_reduce(pick_fmt(m->down_type, m->down_layout), dp, qlen, m->device, s);

@@ -78,6 +78,7 @@ SYMBOLS = {
     "ktb200_moe_gate_forward": (_I, [C.POINTER(GateConfig), _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ktb200_moe_block_forward": (_I, [C.POINTER(GateConfig), _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ktb200_moe_block_forward_host": (_I, [C.POINTER(GateConfig), _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "ktb200_moe_forward_ep": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "ktb200_ep_all_gather_tokens": (_I, [_VP, _VP, _VP, _VP]),
     "ktb200_ep_reduce_own_token": (_I, [_VP, _VP, _VP, _VP]),
     "ktb200_debug_block_trace": (None, [_VP]),

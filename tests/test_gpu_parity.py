@@ -300,6 +300,40 @@ def test_gate_vs_oracle_full_shapes(E, H, k, ng, tg, scoring, method, norm, scal
     assert idx_b.shape == idx.shape and (idx_b >= 0).all() and (idx_b < E).all()
 
 
+def test_moe_forward_ep_shard_call_matches_the_separate_calls():
+    """ktb200_moe_forward_ep: routed partial sums of an expert-parallel shard (fp32) + the shared expert of ONE token in the
+    same two launches == ktb200_moe_forward on the shard + ktb200_mlp_forward on that token, bit for bit."""
+    import ctypes as C
+    Eg, k, H, I, offset = 16, 4, 4096, 512, 8
+    El = Eg - offset
+    m = G.Moe(El, k, H, I, _synth(Q4_K, El * I * H, 91), _synth(Q4_K, El * I * H, 92), _synth(Q6_K, El * H * I, 93), Q4_K, Q4_K, Q6_K, F32, offset=offset)
+    sg, su, sd = _synth(Q4_K, I * H, 94), _synth(Q4_K, I * H, 95), _synth(Q6_K, H * I, 96)
+    mlp = G.Mlp(H, I, sg, su, sd, Q4_K, Q4_K, Q6_K, BF16)
+    rng = np.random.default_rng(3)
+    lib = native.lib()
+    for qlen, own in ((1, 0), (3, 1), (8, 7)):
+        xb = f32_to_bf16_bits((rng.standard_normal((qlen, H)) / 10).astype(np.float32))
+        x = bf16_to_f32(xb)                                              # the shard's kernels take the gathered rows as fp32
+        ids = np.stack([rng.permutation(Eg)[:k] for _ in range(qlen)]).astype(np.int64)
+        w = rng.random((qlen, k)).astype(np.float32)
+        want = m.forward(ids, w, x)
+        x_d, ids_d, w_d = G.dev(x), G.dev(ids), G.dev(w)
+        part = torch.zeros((qlen, H), dtype=torch.float32, device="cuda")
+        sh_out = torch.zeros((H,), dtype=torch.bfloat16, device="cuda")
+        n0 = native.launch_count()
+        native.check(lib.ktb200_moe_forward_ep(m.h, mlp.h, qlen, k, ids_d.data_ptr(), w_d.data_ptr(), x_d.data_ptr(), part.data_ptr(), own,
+                                               sh_out.data_ptr(), None, G.stream()))
+        torch.cuda.synchronize()
+        assert native.launch_count() - n0 == 2
+        assert np.array_equal(part.cpu().numpy(), want)
+        sh_want = torch.zeros((1, H), dtype=torch.bfloat16, device="cuda")
+        xo = G.dev(xb[own:own + 1], torch.bfloat16)
+        native.check(lib.ktb200_mlp_forward(mlp.h, 1, xo.data_ptr(), sh_want.data_ptr(), 0, None, G.stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(sh_out.view(torch.int16), sh_want[0].view(torch.int16))
+    m.close(); mlp.close()
+
+
 # ------------------------------------------------------------------------------------------ fused MoE block
 @pytest.mark.parametrize("dt,hid,shared,offset,H,I", [
     (Q6_K, BF16, True, 0, 4096, 512),      # V3-like: Q4_K gate/up, Q6_K (tile layout) down, shared expert fused as slot k
