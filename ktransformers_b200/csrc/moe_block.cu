@@ -612,7 +612,14 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     const void* fn;
     if (W > kBlockWarpsLo) fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarps> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarps>;
     else fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarpsLo> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarpsLo>;
-    KTB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // raise the kernel's dynamic shared-memory limit once per (variant, device), not on every call
+        static size_t limit[4][64] = {};
+        const int v = (W > kBlockWarpsLo ? 2 : 0) + (fd == FMT_Q6K4T ? 1 : 0);
+        if (limit[v][dev & 63] < smem) {
+            KTB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            limit[v][dev & 63] = smem;
+        }
+    }
     // Launch attributes.  Cooperative: the driver guarantees (or refuses) co-residency of the G <= #SM CTAs the grid
     // barriers need (KTB200_BLK_COOP=0: plain grid, co-resident whenever the GPU runs nothing else).  Programmatic
     // stream serialization (KTB200_BLK_PDL=0 to disable): see griddep_wait() in the kernel.
