@@ -7,14 +7,18 @@
 // Why one kernel: a launch that streams ~100-150 MB lasts 25-30 us on a B200 of which ~6 us are fixed cost (launch
 // gap, pipeline ramp, activation prologue, tail) — profiles/probe_bulk.txt: the bare copy ring needs 27.3 us for the
 // gate/up bytes that take 21 us at the sustained rate.  Three launches per layer pay that three times.  Here the 148
-// CTAs (one per SM, cooperative launch) stay resident for the whole layer, separate the phases with two grid-wide
-// barriers, and keep the copy engine busy ACROSS them:
-//   * before the router's barrier every warp has already requested its first shared-expert rows (they do not depend
-//     on the routing), so the top-k selection and the barrier latency are covered by bytes in flight;
-//   * before the gate/up -> down barrier every warp has already requested its first down tiles (they depend on the
-//     expert ids only, not on the activations).
-// The selection runs redundantly in every CTA (128 threads, ~2 us, from the same partial sums in the same order):
-// no second barrier and no global round trip for the ids.
+// CTAs (one per SM, cooperative launch, 12 warps, 168 registers) stay resident for the whole layer and separate the
+// phases with two grid-wide barriers.  What overlaps what was decided with profiles/block_trace.py (%globaltimer at the
+// phase boundaries of every CTA):
+//   * a barrier is split into arrive / wait; weights that do not depend on the other CTAs are requested in between
+//     (the shared expert's rows behind barrier 1, the first down tiles — they need the expert ids only — behind
+//     barrier 2), never before the arrive: a fence issued with bulk copies in flight waits for them;
+//   * x is quantised under barrier 1 (the router reads x itself); the shared expert's gate/up rows are consumed by
+//     warps 4.. while warps 0..3 run the top-k;
+//   * the selection runs redundantly in every CTA (128 threads, from the same partial sums in the same order): no
+//     second barrier and no global round trip for the ids;
+//   * programmatic dependent launch: the router's weight loads are issued before griddepcontrol.wait, so the next
+//     layer's launch latency and first DRAM round trip hide under this layer's tail.
 //
 // Arithmetic, summation orders and rounding are exactly those of the separate kernels (gate.cuh, gemv_bulk.cuh):
 // the fused launch is bit-identical to ktb200_moe_gate_forward + ktb200_moe_forward_shared (tests/test_gpu_parity.py).
