@@ -85,7 +85,7 @@ class KExpertsB200(KExpertsBase):
 
     def __init__(self, key, gguf_loader, config, n_routed_experts, orig_module=None, device: str = "cuda",
                  out_device: str | None = None, expert_parallel_rank: int = 0, expert_parallel_size: int = 1,
-                 max_tokens: int | None = None, **kwargs):
+                 max_tokens: int | None = None, hidden_dtype: torch.dtype | None = None, **kwargs):
         super().__init__(key, gguf_loader, config, orig_module, device, **kwargs)
         assert "cuda" in str(device).lower(), "KExpertsB200 can only be loaded on a CUDA device"
         self.n_routed_experts = n_routed_experts
@@ -93,6 +93,7 @@ class KExpertsB200(KExpertsBase):
         self.ep_rank, self.ep_size = int(expert_parallel_rank), int(expert_parallel_size)
         assert n_routed_experts % self.ep_size == 0, "expert count must divide evenly across the EP group"
         self.max_tokens = int(max_tokens or KExpertsB200.MAX_TOKENS)
+        self.hidden_dtype = hidden_dtype      # None: torch's default dtype at load time (the reference's behaviour)
         self.handle = None
         self.gate = self.up = self.down = None
         self._pending = None
@@ -122,7 +123,8 @@ class KExpertsB200(KExpertsBase):
         self.gate, self.up, self.down = upload(w["gate"]), upload(w["up"]), upload(w["down"])
         dev = torch.device(device)
         self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
-        hidden_type = TORCH_TO_GGML_HIDDEN[torch.get_default_dtype()] if torch.get_default_dtype() in TORCH_TO_GGML_HIDDEN else 30
+        want_dtype = self.hidden_dtype or torch.get_default_dtype()
+        hidden_type = TORCH_TO_GGML_HIDDEN[want_dtype] if want_dtype in TORCH_TO_GGML_HIDDEN else 30
         self.hidden_type = hidden_type
         cfg = native.MoeConfig(per, self.config.num_experts_per_tok, self.config.hidden_size,
                                self.config.moe_intermediate_size, 64, 10, self.max_tokens,

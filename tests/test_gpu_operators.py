@@ -101,3 +101,40 @@ def test_injected_v3_moe_decodes_through_one_launch_and_matches_dense(tmp_path):
             assert (y.view(-1, H).float() - want).abs().max() <= 0.05 * want.abs().max()
     finally:
         torch.set_default_dtype(old)
+
+
+def test_kt_moe_wrapper_serves_a_layer_from_gguf(tmp_path):
+    """KTMoEWrapper(method="B200_GGUF"): load_weights with an EPLB permutation, gpu_experts_mask skipping, submit/sync on a
+    caller stream — against the dense fp32 restatement."""
+    from ktransformers_b200.kt_moe_wrapper import KTMoEWrapper
+    dense = _write_gguf(str(tmp_path / "tiny.gguf"))
+    KTMoEWrapper.clear_buffer_cache()
+    mask = torch.zeros(E, dtype=torch.bool); mask[2] = True                  # physical expert 2 is served elsewhere
+    w = KTMoEWrapper(1, E, K, H, I, mask, cpuinfer_threads=32, threadpool_count=2, weight_path=str(tmp_path), chunked_prefill_size=16)
+    p2l = torch.arange(E - 1, -1, -1)                                         # physical slot p holds logical expert E-1-p
+    w.load_weights(p2l)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n_tok = 5
+    x = (torch.randn(n_tok, H, generator=g) / 10).to(torch.bfloat16).cuda()
+    ids = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(n_tok)]).cuda()
+    ids[0, 0] = 2                                                             # make sure the mask is exercised
+    wt = torch.rand(n_tok, K, generator=g).cuda()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    w.submit_forward(x, ids, wt, st.cuda_stream)
+    y = w.sync_forward(x, st.cuda_stream)
+    st.synchronize()
+    W = {k_: torch.from_numpy(np.array(v)).cuda() for k_, v in dense.items() if "exps" in k_}
+    xf = x.float()
+    ref = torch.zeros_like(xf)
+    for t in range(n_tok):
+        for j in range(K):
+            p = int(ids[t, j])
+            if p == 2:
+                continue
+            e = int(p2l[p])
+            gw, uw, dw = W["blk.1.ffn_gate_exps.weight"][e], W["blk.1.ffn_up_exps.weight"][e], W["blk.1.ffn_down_exps.weight"][e]
+            ref[t] += (torch.nn.functional.silu(gw @ xf[t]) * (uw @ xf[t])) @ dw.T * wt[t, j]
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (n_tok, H)
+    assert (y.float() - ref).abs().max() <= 0.05 * ref.abs().max()
+    assert torch.equal(w.forward(x, ids, wt, None), y)                        # forward == submit + sync

@@ -230,3 +230,32 @@ def test_b200_ops_are_registered_and_refuse_cpu():
     rules = yaml.safe_load(open(os.path.join(ROOT, "ktransformers_b200", "optimize", "optimize_rules", "DeepSeek-V3-Chat-b200.yaml")))
     ops = [r["replace"]["kwargs"].get("generate_op") for r in rules if "kwargs" in r["replace"]]
     assert "KExpertsB200" in ops and "KLinearB200" in ops
+
+
+def test_kt_moe_wrapper_front_door_contract():
+    """KTMoEWrapper (kt-kernel/python/experts.py:72-262) for the B200 backend: constructor checks, mask handling and the
+    EPLB permutation are host logic; the compute goes through KExpertsB200 (GPU tests)."""
+    from ktransformers_b200.kt_moe_wrapper import KTMoEWrapper
+    with pytest.raises(NotImplementedError):
+        KTMoEWrapper(0, 8, 2, 256, 256, None, 32, 2, "/x", 64, method="AMXINT4")            # CPU backends are not built here
+    with pytest.raises(NotImplementedError):
+        KTMoEWrapper(0, 8, 2, 256, 256, None, 32, 2, "/x", 64, method="B200_GGUF", mode="sft")
+    with pytest.raises(ValueError):
+        KTMoEWrapper(0, 8, 2, 256, 256, None, 32, 2, "/x", 64, max_deferred_experts_per_token=1)
+    with pytest.raises(ValueError):
+        KTMoEWrapper(0, 8, 2, 256, 256, torch.zeros(7, dtype=torch.bool), 32, 2, "/x", 64)
+    mask = torch.zeros(8, dtype=torch.bool); mask[[0, 5]] = True
+    w = KTMoEWrapper(3, 8, 2, 256, 256, mask, 32, 2, "/x", 64)
+    assert w.num_gpu_experts == 2 and w.key == "model.layers.3.mlp.experts" and w.moe.hidden_dtype == torch.bfloat16
+    raw = torch.arange(8 * 4, dtype=torch.uint8)                                          # 8 experts x 4 bytes
+    p2l = torch.tensor([7, 6, 5, 4, 3, 2, 1, 0])
+    assert KTMoEWrapper._permute(raw, 8, p2l).reshape(8, 4)[0].tolist() == [28, 29, 30, 31]   # physical slot 0 holds logical expert 7
+    assert torch.equal(KTMoEWrapper._permute(raw, 8, None), raw)
+    with pytest.raises(ValueError):
+        KTMoEWrapper._permute(raw, 8, torch.tensor([0, 0, 1, 2, 3, 4, 5, 6]))
+    with pytest.raises(NotImplementedError):
+        w.load_weights_from_tensors(torch.zeros(8, 4, 4), torch.zeros(8, 4, 4), torch.zeros(8, 4, 4))   # no online K-quant quantiser
+    with pytest.raises(RuntimeError):
+        w.submit_forward(torch.zeros(1, 256), torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 2))
+    KTMoEWrapper.set_capture_batch_sizes([8, 1, 4])
+    assert KTMoEWrapper.get_capture_batch_sizes() == [1, 4, 8]
