@@ -259,3 +259,22 @@ def test_kt_moe_wrapper_front_door_contract():
         w.submit_forward(torch.zeros(1, 256), torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 2))
     KTMoEWrapper.set_capture_batch_sizes([8, 1, 4])
     assert KTMoEWrapper.get_capture_batch_sizes() == [1, 4, 8]
+
+
+def test_ep_comm_argument_checks_need_no_gpu():
+    """ktb200_ep_* validate their communicator before touching CUDA (include/ktb200.h)."""
+    import ctypes as C
+    from ktransformers_b200 import native
+    lib = native.lib()
+    ok = native.EpComm.make(0, 2, 256, 30, [16, 32], [48, 64], [80, 96])
+    assert ok.world == 2 and ok.token_bufs[1] == 32 and ok.flag_bufs[0] == 80
+    for bad in (native.EpComm.make(2, 2, 256, 30, [16, 32], [48, 64], [80, 96]),          # rank out of range
+                native.EpComm.make(0, 2, 250, 30, [16, 32], [48, 64], [80, 96]),          # hidden not a multiple of 8
+                native.EpComm.make(0, 2, 256, 12, [16, 32], [48, 64], [80, 96]),          # Q4_K is not a hidden type
+                native.EpComm.make(0, 2, 256, 30, [16, 0], [48, 64], [80, 96])):          # a peer pointer is missing
+        with pytest.raises(ValueError):
+            native.check(lib.ktb200_ep_all_gather_tokens(C.byref(bad), 16, None, None))
+        with pytest.raises(ValueError):
+            native.check(lib.ktb200_ep_reduce_own_token(C.byref(bad), 16, None, None))
+    with pytest.raises(ValueError):
+        native.check(lib.ktb200_ep_all_gather_tokens(C.byref(ok), None, None, None))       # null token
