@@ -271,9 +271,12 @@ typedef struct ktb200_mla_params {
     const int* page_table; const int* kv_len;
     void* out; float* lse_out;
     void* workspace; size_t workspace_bytes;  /* device scratch for split partials */
+    long kv_cache_rows;                       /* pages * page_size of the cache allocation (bounds the TMA tensor map); 0: unknown */
 } ktb200_mla_params;
 size_t ktb200_mla_workspace_bytes(int batch, int num_heads, int max_splits);
 int ktb200_mla_decode(const ktb200_mla_params* p, void* stream);
+/* Diagnostics: while non-NULL, one CTA of ktb200_mla_decode dumps the raw scores of its first tile (>= 2048 floats). */
+void ktb200_debug_mla(float* debug_dev);
 
 /* paged latent KV write: StaticCache.update (archive/ktransformers/models/custom_cache.py:147-200)
  * kv_cache[page_idx[t]][page_offset[t]][0:512] = ckv[t], [512:576] = k_pe[t] */

@@ -1,250 +1,301 @@
-// Absorbed-MLA paged decode attention + paged latent KV write (sm_100a).
+// Absorbed-MLA paged decode attention on the Blackwell tensor path (tcgen05 + TMEM + TMA) and the paged latent KV write.
 //
-// Replaces MLAWrapper.run / flashinfer BatchMLAPagedAttentionWrapper fa2
-// (archive/ktransformers/operators/flashinfer_wrapper.py:117-161, third_party/custom_flashinfer/include/
-// flashinfer/attention/mla.cuh:775-...) and the Triton split-KV decode (archive/ktransformers/operators/
-// triton_attention.py:16-385).  Math (attention.py:395-478, Appendix A of SURVEY.md):
-//     s[h,t] = (q_nope[h,:] . ckv[t,:] + q_pe[h,:] . k_pe[t,:]) * sm_scale          (576-long dot, bf16 MMA, fp32 acc)
-//     p      = softmax_t(s)  (fp32, online), P cast to bf16 before P.V            (triton_attention.py:137-141)
-//     out[h] = sum_t p[h,t] * ckv[t,:]                                             (512 wide)
+// Replaces MLAWrapper.run / flashinfer BatchMLAPagedAttentionWrapper
+// (archive/ktransformers/operators/flashinfer_wrapper.py:117-161, attention.py:419-447) and the Triton split-KV decode
+// (archive/ktransformers/operators/triton_attention.py:16-385).  Math (attention.py:395-478):
+//     s[h,t] = (q_nope[h,:] . ckv[t,:] + q_pe[h,:] . k_pe[t,:]) * sm_scale        576-long dot, bf16 x bf16 -> fp32
+//     p      = softmax_t(s)   fp32, online; P is cast to bf16 before P.V            (triton_attention.py:137-141)
+//     out[h] = sum_t p[h,t] * ckv[t,:]                                             512 wide
 //
-// Round-1 kernel: flash-decoding with warp-level bf16 tensor-core MMA (mma.sync m16n8k16, fp32 accumulate),
-// cp.async 3-stage paged KV pipeline in shared memory, split-KV across CTAs and an LSE merge kernel.
-// CTA = 32 heads x one KV split; 8 warps: QK^T is tiled 2 (head tiles of 16) x 4 (8-token tiles) over the
-// warps, P.V is tiled over the 512 latent dims (64 per warp).  K and V share ONE shared-memory tile (V is
-// the first 512 columns of the same latent row) so every KV byte is fetched from HBM once per head tile and
-// re-used for both products.  The tcgen05/TMEM version of the two products is the next step.
+// Work decomposition: CTA = (KV split, group of 64 heads, sequence); 6 warps with fixed roles
+//     warp 0      TMA producer: paged KV tiles of 32 tokens x 576 columns, 9 boxes of [32 rows x 64 columns] per tile
+//                 (cp.async.bulk.tensor, 128-byte swizzle) into a 4-stage ring, one mbarrier per stage
+//     warp 1      tensor-core issuer (one lane): S = Q.K^T and O^T = V^T.P^T as tcgen05.mma with TMEM accumulators
+//     warps 2..5  softmax / rescale / epilogue: tcgen05.ld of S, online softmax (thread = head), P -> shared memory
+// Both products read the SAME shared-memory tile: for S it is the K-major B operand [32 tokens x 576], for O^T its first
+// 512 columns are the MN-major A operand [latent x tokens] (the swizzle is a function of the shared-memory address only).
+// The output is accumulated TRANSPOSED — O^T[latent 512][head 64] = 4 blocks of 128 TMEM lanes x 64 columns — because a
+// [head][latent] accumulator for 64 heads would need 512 columns in the M=64 tcgen05 layout (half the lanes idle): the
+// whole tensor memory.  TMEM map (512 columns allocated): [0,256) O^T, [256,288) / [288,320) the two S buffers.
+//
+// Online softmax with a LAZY reference maximum: p = 2^(x - m_ref), m_ref is only raised (and O^T rescaled in TMEM, all
+// four warps) when some head's running maximum exceeds it by more than 8 — p stays <= 256, exact in bf16/fp32 terms —
+// so the steady-state tile costs no TMEM round trip of the accumulator.  Split-KV partials (fp32 O, base-2 LSE) are
+// merged by mla_merge_kernel.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace ktb {
 
-constexpr int kMlaThreads = 256;
-constexpr int kHT = 32;              // heads per CTA
-constexpr int kKT = 32;              // kv tokens per tile
+using namespace umma;
+
 constexpr int kDK = 576;             // 512 latent + 64 rope
 constexpr int kDV = 512;
-constexpr int kRowPad = kDK + 8;     // bf16 elements per smem row (1168 B: conflict-free ldmatrix)
-constexpr int kPPad = kKT + 8;
-constexpr int kStages = 3;
+constexpr int kHG = 64;              // heads per CTA (UMMA M of S)
+constexpr int kLT = 32;              // kv tokens per tile (UMMA N of S, K of O^T)
+constexpr int kStages = 4;
+constexpr int kChunks = kDK / 64;    // 9 column chunks of 64 bf16 = 128 B (one swizzle row)
+constexpr int kMlaThreads = 192;
+constexpr int kStageBytes = kLT * kDK * 2;         // 36,864 = 9 regions of 32 rows x 128 B
+constexpr int kKRegion = kLT * 128;                // 4,096
+constexpr int kQRegion = kHG * 128;                // 8,192
+constexpr int kQBytes = kHG * kDK * 2;             // 73,728
+constexpr int kPBytes = kHG * kLT * 2;             // 4,096: [8 head groups][4 token groups][8 heads][8 tokens]
+constexpr int kOffQ = kStages * kStageBytes;       // 147,456
+constexpr int kOffP = kOffQ + kQBytes;             // 221,184
+constexpr int kOffMisc = kOffP + kPBytes;          // 225,280
+constexpr int kTmemCols = 512;
+constexpr int kColO = 0, kColS = 256;
+constexpr float kRescaleThreshold = 8.f;
 
-struct MlaSmem {
-    __nv_bfloat16 q[kHT][kRowPad];
-    __nv_bfloat16 k[kStages][kKT][kRowPad];
-    __nv_bfloat16 p[kHT][kPPad];
-    float max_part[kHT][4];
-    float sum_part[kHT][4];
-    float row_max[kHT];
-    float row_sum[kHT];
-    float alpha[kHT];
+struct MlaMisc {
+    unsigned long long k_full[kStages], k_empty[kStages], s_full[2], s_empty[2], p_full, pv_done;
+    uint32_t tmem_base;
+    int need[4];
+    float alpha[kHG];     // per head: 2^(m_ref_old - m_ref_new) of the current rescale
+    float l[kHG];         // final row sums
+    float m[kHG];         // final reference maxima
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+constexpr int kMlaSmem = kOffMisc + (int)sizeof(MlaMisc) + 1024;   // + slack to align the base to 1024 B
 
 struct MlaKParams {
     const __nv_bfloat16* q_nope;   // [B][Hq][512]
     const __nv_bfloat16* q_pe;     // [B][Hq][64]
-    const __nv_bfloat16* kv;       // [pages][page_size][576]
     const int* page_table;         // [B][max_pages]
     const int* kv_len;             // [B]
     int num_heads, page_size, max_pages, num_splits;
     float scale_log2;              // sm_scale * log2(e)
     float* o_part;                 // [B][splits][Hq][512]
     float* lse_part;               // [B][splits][Hq]  (base-2)
+    float* debug;                  // optional: S of the first tile [64][32], P bytes, see ktb200_debug_mla
 };
 
-__global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_split_kernel(const MlaKParams p) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    MlaSmem& sm = *reinterpret_cast<MlaSmem*>(smem_raw);
-    const int split = blockIdx.x, ht = blockIdx.y, b = blockIdx.z;
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __grid_constant__ CUtensorMap kv_map, const MlaKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;           // 128-byte swizzle atoms are 1024-byte aligned
+    uint8_t* smem = smem_raw + (base - raw);
+    MlaMisc& misc = *reinterpret_cast<MlaMisc*>(smem + kOffMisc);
+    const int split = blockIdx.x, hg = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h0 = ht * kHT;
-    const int L = p.kv_len[b];
-    // this split's token range, in whole tiles
-    const int ntiles = (L + kKT - 1) / kKT;
+    const int h0 = hg * kHG;
+    int L = p.kv_len[b];
+    if (L > p.max_pages * p.page_size) L = p.max_pages * p.page_size;
+    const int ntiles = (L + kLT - 1) / kLT;
     const int tiles_per = (ntiles + p.num_splits - 1) / p.num_splits;
     const int tile0 = split * tiles_per, tile1 = min(ntiles, tile0 + tiles_per);
+    const int n = tile1 - tile0;
     float* o_out = p.o_part + (((long)b * p.num_splits + split) * p.num_heads + h0) * kDV;
     float* lse_out = p.lse_part + ((long)b * p.num_splits + split) * p.num_heads + h0;
 
-    if (tile0 >= tile1) {   // empty split: neutral element for the merge
-        for (int i = tid; i < kHT * kDV; i += kMlaThreads)
+    if (n <= 0) {   // empty split: the neutral element of the merge
+        for (int i = tid; i < kHG * kDV; i += kMlaThreads)
             if (h0 + i / kDV < p.num_heads) o_out[i] = 0.f;
-        if (tid < kHT && h0 + tid < p.num_heads) lse_out[tid] = -INFINITY;
+        if (tid < kHG && h0 + tid < p.num_heads) lse_out[tid] = -INFINITY;
         return;
     }
 
-    // ---- Q tile -> smem (rows beyond num_heads are zero) ----------------------------------------------
-    for (int i = tid; i < kHT * (kDK / 8); i += kMlaThreads) {
-        const int r = i / (kDK / 8), c = (i % (kDK / 8)) * 8;
+    // ---- one-time setup -----------------------------------------------------------------------------------------
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&kv_map);
+        for (int s = 0; s < kStages; s++) { bar_init(smem_u32(&misc.k_full[s]), 1); bar_init(smem_u32(&misc.k_empty[s]), 1); }
+        for (int s = 0; s < 2; s++) { bar_init(smem_u32(&misc.s_full[s]), 1); bar_init(smem_u32(&misc.s_empty[s]), 4); }
+        bar_init(smem_u32(&misc.p_full), 4);
+        bar_init(smem_u32(&misc.pv_done), 1);
+        bar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&misc.tmem_base), kTmemCols);
+    // Q (64 heads x 576) -> shared memory in the K-major 128-byte-swizzle layout: chunk region c (64 columns) holds 64
+    // rows of 128 B; the 16-byte piece j of row r sits at piece (j ^ (r & 7)).  Rows beyond num_heads are zero.
+    for (int i = tid; i < kHG * (kDK / 8); i += kMlaThreads) {
+        const int r = i / (kDK / 8), j = i - r * (kDK / 8);   // j: 16-byte piece of the 576-wide row (0..71)
         uint4 v = make_uint4(0, 0, 0, 0);
         if (h0 + r < p.num_heads) {
             const long hrow = (long)b * p.num_heads + h0 + r;
-            v = (c < kDV) ? *reinterpret_cast<const uint4*>(p.q_nope + hrow * kDV + c)
-                          : *reinterpret_cast<const uint4*>(p.q_pe + hrow * 64 + (c - kDV));
+            v = j < 64 ? reinterpret_cast<const uint4*>(p.q_nope + hrow * kDV)[j] : reinterpret_cast<const uint4*>(p.q_pe + hrow * 64)[j - 64];
         }
-        *reinterpret_cast<uint4*>(&sm.q[r][c]) = v;
+        const int c = j >> 3, jj = j & 7;
+        *reinterpret_cast<uint4*>(smem + kOffQ + c * kQRegion + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
     }
-    if (tid < kHT) { sm.row_max[tid] = -INFINITY; sm.row_sum[tid] = 0.f; }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = misc.tmem_base;
 
-    auto load_tile = [&](int tile, int stage) {
-        const int t_base = tile * kKT;
-        const int page = p.page_table[(long)b * p.max_pages + t_base / p.page_size];
-        const __nv_bfloat16* src = p.kv + ((long)page * p.page_size + (t_base % p.page_size)) * kDK;
-        for (int i = tid; i < kKT * (kDK / 8); i += kMlaThreads) {
-            const int r = i / (kDK / 8), c = (i % (kDK / 8)) * 8;
-            cp_async16(smem_u32(&sm.k[stage][r][c]), src + (long)r * kDK + c, t_base + r < L);
-        }
-    };
-
-    // prologue: fill kStages-1 stages
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            for (int j = 0; j < n; j++) {
+                const int s = j % kStages;
+                bar_wait(smem_u32(&misc.k_empty[s]), ((j / kStages) & 1) ^ 1);
+                const int t_base = (tile0 + j) * kLT;
+                const int page = p.page_table[(long)b * p.max_pages + t_base / p.page_size];
+                const int row = page * p.page_size + t_base % p.page_size;
+                const uint32_t bar = smem_u32(&misc.k_full[s]);
+                bar_expect_tx(bar, kStageBytes);
 #pragma unroll
-    for (int s = 0; s < kStages - 1; s++) {
-        if (tile0 + s < tile1) load_tile(tile0 + s, s);
-        cp_async_commit();
-    }
-
-    const int mt = warp >> 2, nt = warp & 3;   // QK^T: head tile (16 rows) x token tile (8 tokens)
-    float o[2][8][4];                          // P.V : 2 head tiles x 8 n-tiles of this warp's 64 latent dims
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int n = 0; n < 8; n++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) o[a][n][c] = 0.f;
-
-    for (int tile = tile0; tile < tile1; tile++) {
-        const int stage = (tile - tile0) % kStages;
-        cp_async_wait<kStages - 2>();
-        __syncthreads();                       // tile `tile` landed; everyone is done with the stage refilled below
-        if (tile + kStages - 1 < tile1) load_tile(tile + kStages - 1, (tile - tile0 + kStages - 1) % kStages);
-        cp_async_commit();
-
-        // ---- S = Q K^T for this warp's 16 x 8 tile ----------------------------------------------------
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        {
-            const uint32_t a_base = smem_u32(&sm.q[16 * mt + (lane & 15)][(lane >> 4) * 8]);
-            // B via ldmatrix.x4: matrices (k0, k0+8, k0+16, k0+24) of the 8 token rows
-            const uint32_t b_base = smem_u32(&sm.k[stage][8 * nt + (lane & 7)][(lane >> 3) * 8]);
-#pragma unroll 4
-            for (int k0 = 0; k0 < kDK; k0 += 32) {
-                uint32_t a0, a1, a2, a3, a4, a5, a6, a7, b0, b1, b2, b3;
-                ldsm_x4(a_base + k0 * 2, a0, a1, a2, a3);
-                ldsm_x4(a_base + (k0 + 16) * 2, a4, a5, a6, a7);
-                ldsm_x4(b_base + k0 * 2, b0, b1, b2, b3);
-                mma_bf16(s, a0, a1, a2, a3, b0, b1);
-                mma_bf16(s, a4, a5, a6, a7, b2, b3);
+                for (int c = 0; c < kChunks; c++) tma_load_2d(base + s * kStageBytes + c * kKRegion, &kv_map, bar, c * 64, row);
             }
         }
-        // ---- online softmax -----------------------------------------------------------------------------
-        const int r_lo = 16 * mt + (lane >> 2), r_hi = r_lo + 8;
-        const int col = 8 * nt + 2 * (lane & 3);
-        const int t_base = tile * kKT;
-        float v[4];
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================================ tensor-core issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = instr_desc(1, 1, 1, 0, 0, kHG, kLT);    // f32 += bf16 . bf16, A K-major, B K-major, 64 x 32
+            constexpr uint32_t idesc_pv = instr_desc(1, 1, 1, 1, 0, 128, kHG);    // A MN-major (V^T from the [token][latent] tile), 128 x 64
+            auto issue_qk = [&](int j) {
+                const int s = j % kStages, buf = j & 1;
+                bar_wait(smem_u32(&misc.s_empty[buf]), ((j >> 1) & 1) ^ 1);
+                bar_wait(smem_u32(&misc.k_full[s]), (j / kStages) & 1);
+                tc_fence_after();
+                const uint32_t kb = base + s * kStageBytes, qb = base + kOffQ;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int t = t_base + col + (c & 1);
-            v[c] = (t < L) ? s[c] * p.scale_log2 : -INFINITY;
+                for (int c = 0; c < kChunks; c++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        mma_f16(tmem + kColS + buf * kLT, smem_desc(qb + c * kQRegion + k * 32, 16, 1024, kLayoutSw128),
+                                smem_desc(kb + c * kKRegion + k * 32, 16, 1024, kLayoutSw128), idesc_qk, (c | k) != 0);
+                mma_commit(smem_u32(&misc.s_full[buf]));
+            };
+            issue_qk(0);
+            for (int j = 0; j < n; j++) {
+                if (j + 1 < n) issue_qk(j + 1);
+                bar_wait(smem_u32(&misc.p_full), j & 1);
+                tc_fence_after();
+                const int s = j % kStages;
+                const uint32_t kb = base + s * kStageBytes, pb = base + kOffP;
+#pragma unroll
+                for (int m = 0; m < 4; m++)
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                        mma_f16(tmem + kColO + m * kHG, smem_desc(kb + 2 * m * kKRegion + k * 2048, kKRegion, 1024, kLayoutSw128),
+                                smem_desc(pb + k * 256, 128, 512, kLayoutNone), idesc_pv, (j | k) != 0);
+                mma_commit(smem_u32(&misc.k_empty[s]));
+                mma_commit(smem_u32(&misc.pv_done));
+            }
         }
-        float m_lo = fmaxf(v[0], v[1]), m_hi = fmaxf(v[2], v[3]);
-        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
-        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
-        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
-        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
-        if ((lane & 3) == 0) { sm.max_part[r_lo][nt] = m_lo; sm.max_part[r_hi][nt] = m_hi; }
-        __syncthreads();
-        const float old_lo = sm.row_max[r_lo], old_hi = sm.row_max[r_hi];
-        float new_lo = old_lo, new_hi = old_hi;
+        __syncwarp();
+    } else {
+        // ================================================================ softmax / rescale / epilogue (4 warps)
+        const int sp = warp & 3;                       // TMEM sub-partition of this warp
+        const uint32_t lane_base = (uint32_t)(32 * sp) << 16;
+        const int head = 16 * sp + lane;               // S rows of this sub-partition live in its lanes 0..15 (M = 64 layout)
+        const bool owner = lane < 16;
+        const int st = tid - 64;                       // 0..127 among the softmax threads
+        float m_ref = -INFINITY, m_run = -INFINITY, l = 0.f;
+        for (int j = 0; j < n; j++) {
+            const int buf = j & 1;
+            bar_wait(smem_u32(&misc.s_full[buf]), (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[32];
+            tmem_ld32(tmem + lane_base + kColS + buf * kLT, sv);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(smem_u32(&misc.s_empty[buf]));
+            if (p.debug && j == 0 && owner && split == 0 && hg == 0 && b == 0)
+                for (int i = 0; i < 32; i++) p.debug[head * 32 + i] = __uint_as_float(sv[i]);
+            const int t_base = (tile0 + j) * kLT;
+            float x[32];
+            float mt = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 4; j++) { new_lo = fmaxf(new_lo, sm.max_part[r_lo][j]); new_hi = fmaxf(new_hi, sm.max_part[r_hi][j]); }
-        // at least one valid token exists in every tile of the range, so new_* is finite
-        float pr[4];
-        pr[0] = exp2f(v[0] - new_lo); pr[1] = exp2f(v[1] - new_lo);
-        pr[2] = exp2f(v[2] - new_hi); pr[3] = exp2f(v[3] - new_hi);
-        *reinterpret_cast<__nv_bfloat162*>(&sm.p[r_lo][col]) = __floats2bfloat162_rn(pr[0], pr[1]);
-        *reinterpret_cast<__nv_bfloat162*>(&sm.p[r_hi][col]) = __floats2bfloat162_rn(pr[2], pr[3]);
-        float l_lo = pr[0] + pr[1], l_hi = pr[2] + pr[3];
-        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
-        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
-        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-        if ((lane & 3) == 0) { sm.sum_part[r_lo][nt] = l_lo; sm.sum_part[r_hi][nt] = l_hi; }
-        if (nt == 0 && (lane & 3) == 0) {
-            sm.alpha[r_lo] = exp2f(old_lo - new_lo);   // exp2(-inf) = 0 on the first tile
-            sm.alpha[r_hi] = exp2f(old_hi - new_hi);
-        }
-        __syncthreads();
-        if (tid < kHT) {   // fold the tile into the running row statistics
-            const float a = sm.alpha[tid];
-            float mx = sm.row_max[tid];
+            for (int i = 0; i < 32; i++) {
+                x[i] = (t_base + i < L) ? __uint_as_float(sv[i]) * p.scale_log2 : -INFINITY;
+                mt = fmaxf(mt, x[i]);
+            }
+            m_run = fmaxf(m_run, mt);
+            // does any head need its reference raised?  (never on the first tile: O^T is overwritten by the first PV)
+            bool need = false;
+            if (j == 0) m_ref = m_run;
+            else need = owner && (m_run - m_ref > kRescaleThreshold);
+            const unsigned any_w = __ballot_sync(0xffffffffu, need);
+            if (lane == 0) misc.need[warp - 2] = any_w != 0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool any = misc.need[0] | misc.need[1] | misc.need[2] | misc.need[3];
+            // P is single-buffered and O^T must be quiescent before a rescale: the previous PV has to be complete
+            if (j > 0) bar_wait(smem_u32(&misc.pv_done), (j - 1) & 1);
+            if (any) {
+                tc_fence_after();
+                if (owner) {
+                    const float a = need ? exp2f(m_ref - m_run) : 1.f;
+                    misc.alpha[head] = a;
+                    if (need) { l *= a; m_ref = m_run; }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+                for (int q = 0; q < 8; q++) {   // 4 latent blocks x 2 halves of the 64 head columns
+                    uint32_t ov[32];
+                    const uint32_t ta = tmem + lane_base + kColO + q * 32;
+                    tmem_ld32(ta, ov);
+                    tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 4; j++) mx = fmaxf(mx, sm.max_part[tid][j]);
-            sm.row_sum[tid] = sm.row_sum[tid] * a + (sm.sum_part[tid][0] + sm.sum_part[tid][1] + sm.sum_part[tid][2] + sm.sum_part[tid][3]);
-            sm.row_max[tid] = mx;
-        }
-        // ---- O = O * alpha + P V  (this warp: latent dims [64*warp, 64*warp+64)) -----------------------
+                    for (int i = 0; i < 32; i++) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * misc.alpha[(q & 1) * 32 + i]);
+                    tmem_st32(ta, ov);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+            }
+            if (owner) {
+                float ps = 0.f;
+                uint32_t pk[16];
 #pragma unroll
-        for (int a = 0; a < 2; a++) {
-            const float al_lo = sm.alpha[16 * a + (lane >> 2)], al_hi = sm.alpha[16 * a + 8 + (lane >> 2)];
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = exp2f(x[i] - m_ref), p1 = exp2f(x[i + 1] - m_ref);
+                    ps += p0 + p1;
+                    pk[i >> 1] = pack_bf16(p0, p1);
+                }
+                l += ps;
+                // P[head][token] as the K-major no-swizzle B operand: core matrix (8 heads x 8 tokens) = 128 contiguous bytes
+                uint8_t* prow = smem + kOffP + (head >> 3) * 512 + (head & 7) * 16;
 #pragma unroll
-            for (int n = 0; n < 8; n++) { o[a][n][0] *= al_lo; o[a][n][1] *= al_lo; o[a][n][2] *= al_hi; o[a][n][3] *= al_hi; }
-        }
-#pragma unroll
-        for (int k0 = 0; k0 < kKT; k0 += 16) {
-            uint32_t pa[2][4];
-#pragma unroll
-            for (int a = 0; a < 2; a++)
-                ldsm_x4(smem_u32(&sm.p[16 * a + (lane & 15)][k0 + (lane >> 4) * 8]), pa[a][0], pa[a][1], pa[a][2], pa[a][3]);
-#pragma unroll
-            for (int n2 = 0; n2 < 4; n2++) {   // two 8-wide n-tiles per ldmatrix.x4.trans
-                uint32_t b0, b1, b2, b3;
-                // matrices: (k0..+7, n), (k0+8.., n), (k0..+7, n+8), (k0+8.., n+8)
-                const int krow = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int ncol = 64 * warp + 16 * n2 + (lane >> 4) * 8;
-                ldsm_x4_t(smem_u32(&sm.k[stage][krow][ncol]), b0, b1, b2, b3);
-#pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    mma_bf16(o[a][2 * n2], pa[a][0], pa[a][1], pa[a][2], pa[a][3], b0, b1);
-                    mma_bf16(o[a][2 * n2 + 1], pa[a][0], pa[a][1], pa[a][2], pa[a][3], b2, b3);
+                for (int g = 0; g < 4; g++) *reinterpret_cast<uint4*>(prow + g * 128) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            }
+            // rows of the tile beyond kv_len hold whatever the page contains: P is 0 there, but 0 * NaN is NaN -> zero the V rows
+            if (t_base + kLT > L) {
+                const int valid = L - t_base;
+                uint8_t* kb = smem + (j % kStages) * kStageBytes;
+                for (int i = st; i < (kLT - valid) * 64; i += 128) {      // 64 pieces of 16 B per row over the 8 latent chunks
+                    const int r = valid + i / 64, pc = i % 64;
+                    *reinterpret_cast<uint4*>(kb + (pc >> 3) * kKRegion + r * 128 + (pc & 7) * 16) = make_uint4(0, 0, 0, 0);
                 }
             }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) bar_arrive(smem_u32(&misc.p_full));
         }
-        // the __syncthreads at the top of the next iteration protects p / max_part / alpha / k[stage]
+        // ---- epilogue: O^T / l -> fp32 partial output, base-2 LSE ---------------------------------------------------
+        if (owner) { misc.l[head] = l; misc.m[head] = m_ref; }
+        bar_wait(smem_u32(&misc.pv_done), (n - 1) & 1);
+        tc_fence_after();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (st < kHG && h0 + st < p.num_heads) lse_out[st] = misc.m[st] + log2f(misc.l[st]);
+#pragma unroll 1
+        for (int q = 0; q < 8; q++) {
+            uint32_t ov[32];
+            tmem_ld32(tmem + lane_base + kColO + q * 32, ov);
+            tmem_wait_ld();
+            const int latent = (q >> 1) * 128 + 32 * sp + lane;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const int hh = (q & 1) * 32 + i;
+                if (h0 + hh < p.num_heads) o_out[(long)hh * kDV + latent] = __uint_as_float(ov[i]) / misc.l[hh];
+            }
+        }
+        tc_fence_before();
     }
-    cp_async_wait<0>();
     __syncthreads();
-    // ---- write normalised partial output + base-2 LSE ---------------------------------------------------
-#pragma unroll
-    for (int a = 0; a < 2; a++) {
-        const int r_lo = 16 * a + (lane >> 2), r_hi = r_lo + 8;
-        const float inv_lo = 1.f / sm.row_sum[r_lo], inv_hi = 1.f / sm.row_sum[r_hi];
-#pragma unroll
-        for (int n = 0; n < 8; n++) {
-            const int c = 64 * warp + 8 * n + 2 * (lane & 3);
-            if (h0 + r_lo < p.num_heads) *reinterpret_cast<float2*>(o_out + (long)r_lo * kDV + c) = make_float2(o[a][n][0] * inv_lo, o[a][n][1] * inv_lo);
-            if (h0 + r_hi < p.num_heads) *reinterpret_cast<float2*>(o_out + (long)r_hi * kDV + c) = make_float2(o[a][n][2] * inv_hi, o[a][n][3] * inv_hi);
-        }
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, kTmemCols);
     }
-    if (tid < kHT && h0 + tid < p.num_heads) lse_out[tid] = sm.row_max[tid] + log2f(sm.row_sum[tid]);
 }
 
 // out[b][h][:] = sum_s w_s * o_part[b][s][h][:],  w_s = 2^(lse_s - max) / sum ; lse (natural log) optional
@@ -253,9 +304,16 @@ __global__ void __launch_bounds__(128) mla_merge_kernel(const float* o_part, con
     const int bh = blockIdx.x, b = bh / num_heads, h = bh % num_heads;
     float mx = -INFINITY;
     for (int s = 0; s < num_splits; s++) mx = fmaxf(mx, lse_part[((long)b * num_splits + s) * num_heads + h]);
+    const int c = threadIdx.x * 4;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(out + ((long)b * num_heads + h) * kDV + c);
+    if (mx == -INFINITY) {   // kv_len == 0 (e.g. a padded CUDA-graph batch slot): zeros, lse = -inf
+        o2[0] = __floats2bfloat162_rn(0.f, 0.f);
+        o2[1] = __floats2bfloat162_rn(0.f, 0.f);
+        if (lse_out && threadIdx.x == 0) lse_out[(long)b * num_heads + h] = -INFINITY;
+        return;
+    }
     float den = 0.f;
     for (int s = 0; s < num_splits; s++) den += exp2f(lse_part[((long)b * num_splits + s) * num_heads + h] - mx);
-    const int c = threadIdx.x * 4;
     float4 acc = make_float4(0, 0, 0, 0);
     for (int s = 0; s < num_splits; s++) {
         const float w = exp2f(lse_part[((long)b * num_splits + s) * num_heads + h] - mx) / den;
@@ -264,7 +322,6 @@ __global__ void __launch_bounds__(128) mla_merge_kernel(const float* o_part, con
             acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
         }
     }
-    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(out + ((long)b * num_heads + h) * kDV + c);
     o2[0] = __floats2bfloat162_rn(acc.x, acc.y);
     o2[1] = __floats2bfloat162_rn(acc.z, acc.w);
     if (lse_out && threadIdx.x == 0) lse_out[(long)b * num_heads + h] = (mx + log2f(den)) * 0.6931471805599453f;
@@ -280,13 +337,30 @@ __global__ void __launch_bounds__(72) mla_kv_write_kernel(__nv_bfloat16* kv, int
 }
 
 static int pick_splits(int batch, int num_heads, int max_kv_tiles, int device) {
-    const int head_tiles = (num_heads + kHT - 1) / kHT;
-    int s = (2 * num_sms(device) + batch * head_tiles - 1) / (batch * head_tiles);
-    if (s > max_kv_tiles) s = max_kv_tiles;
+    const int groups = batch * ((num_heads + kHG - 1) / kHG);
+    int s = (num_sms(device) + groups - 1) / groups;          // one CTA per SM (227 KB of shared memory each)
+    const int cap = (max_kv_tiles + 3) / 4;                   // at least 4 tiles (128 tokens) per split
+    if (s > cap) s = cap;
     if (s > 128) s = 128;
     if (s < 1) s = 1;
     return s;
 }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libktb200.so links libcudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+static float* g_mla_debug = nullptr;
 
 }  // namespace ktb
 
@@ -301,33 +375,57 @@ int ktb200_mla_decode(const ktb200_mla_params* q, void* stream) {
     using namespace ktb;
     if (!q || !q->q_nope || !q->q_pe || !q->kv_cache || !q->page_table || !q->kv_len || !q->out || !q->workspace) { set_error("mla_decode: null pointer"); return KTB200_EINVAL; }
     if (q->batch <= 0) return KTB200_OK;
-    if (q->num_heads <= 0 || q->page_size <= 0 || q->page_size % kKT || q->max_pages_per_seq <= 0) {
-        set_error("mla_decode: page_size %d must be a positive multiple of %d", q->page_size, kKT);
+    if (q->num_heads <= 0 || q->page_size <= 0 || q->page_size % kLT || q->max_pages_per_seq <= 0) {
+        set_error("mla_decode: page_size %d must be a positive multiple of %d", q->page_size, kLT);
         return KTB200_EINVAL;
     }
+    if (((uintptr_t)q->kv_cache & 15) || ((uintptr_t)q->q_nope & 15) || ((uintptr_t)q->q_pe & 15)) { set_error("mla_decode: q / kv_cache must be 16-byte aligned"); return KTB200_EINVAL; }
     int dev = 0;
     KTB_CUDA_CHECK(cudaGetDevice(&dev));
-    const int max_tiles = q->max_pages_per_seq * (q->page_size / kKT);
+    const int max_tiles = q->max_pages_per_seq * (q->page_size / kLT);
     int splits = q->num_kv_splits > 0 ? q->num_kv_splits : pick_splits(q->batch, q->num_heads, max_tiles, dev);
     if (splits > max_tiles) splits = max_tiles;
     const size_t need = (size_t)q->batch * splits * q->num_heads * (kDV + 1) * sizeof(float);
     if (need > q->workspace_bytes) { set_error("mla_decode: workspace too small (%zu < %zu bytes for %d splits)", q->workspace_bytes, need, splits); return KTB200_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
+
+    // the paged cache as a 2-D tensor [token rows][576 columns]; a tile never crosses a page (page_size % 32 == 0)
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("mla_decode: cuTensorMapEncodeTiled is not available from this driver"); return KTB200_ECUDA; }
+    CUtensorMap map;
+    const cuuint64_t rows = q->kv_cache_rows > 0 ? (cuuint64_t)q->kv_cache_rows : (cuuint64_t)1 << 31;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kDK, rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)kDK * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)kLT};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(q->kv_cache), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("mla_decode: cuTensorMapEncodeTiled failed (%d)", (int)cr); return KTB200_ECUDA; }
+
     MlaKParams p{};
-    p.q_nope = (const __nv_bfloat16*)q->q_nope; p.q_pe = (const __nv_bfloat16*)q->q_pe; p.kv = (const __nv_bfloat16*)q->kv_cache;
+    p.q_nope = (const __nv_bfloat16*)q->q_nope; p.q_pe = (const __nv_bfloat16*)q->q_pe;
     p.page_table = q->page_table; p.kv_len = q->kv_len; p.num_heads = q->num_heads; p.page_size = q->page_size;
     p.max_pages = q->max_pages_per_seq; p.num_splits = splits; p.scale_log2 = q->sm_scale * 1.4426950408889634f;
     p.o_part = (float*)q->workspace;
     p.lse_part = p.o_part + (size_t)q->batch * splits * q->num_heads * kDV;
-    const size_t smem = sizeof(MlaSmem);
-    KTB_CUDA_CHECK(cudaFuncSetAttribute(mla_decode_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int head_tiles = (q->num_heads + kHT - 1) / kHT;
-    mla_decode_split_kernel<<<dim3(splits, head_tiles, q->batch), kMlaThreads, smem, s>>>(p);
+    p.debug = g_mla_debug;
+    static bool attr_set[64] = {};
+    if (!attr_set[dev & 63]) {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(mla_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlaSmem));
+        attr_set[dev & 63] = true;
+    }
+    const int head_groups = (q->num_heads + kHG - 1) / kHG;
+    mla_decode_tc_kernel<<<dim3(splits, head_groups, q->batch), kMlaThreads, kMlaSmem, s>>>(map, p);
     KTB_LAUNCH_CHECK();
     mla_merge_kernel<<<q->batch * q->num_heads, 128, 0, s>>>(p.o_part, p.lse_part, splits, q->num_heads, (__nv_bfloat16*)q->out, q->lse_out);
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
 }
+
+// Diagnostics: while set, CTA (split 0, head group 0, sequence 0) of ktb200_mla_decode writes the raw fp32 scores of its
+// first tile (S[64 heads][32 tokens], before scaling) to debug_dev (>= 2048 floats).
+void ktb200_debug_mla(float* debug_dev) { ktb::g_mla_debug = debug_dev; }
 
 int ktb200_mla_kv_write(void* kv_cache, int page_size, const void* ckv, const void* k_pe, const int* page_idx,
                         const int* page_offset, int n_tokens, void* stream) {

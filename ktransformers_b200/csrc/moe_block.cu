@@ -616,19 +616,32 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     const void* fn;
     if (W > kBlockWarpsLo) fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarps> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarps>;
     else fn = fd == FMT_Q6K4T ? (const void*)moe_block_kernel<BulkQ6K4T, kBlockWarpsLo> : (const void*)moe_block_kernel<BulkQ4K, kBlockWarpsLo>;
-    {   // raise the kernel's dynamic shared-memory limit once per (variant, device), not on every call
+    static const int coop = [] { const char* e = getenv("KTB200_BLK_COOP"); return e ? atoi(e) : 1; }();
+    static const int pdl = [] { const char* e = getenv("KTB200_BLK_PDL"); return e ? atoi(e) : 1; }();
+    auto separate = [&]() -> int {   // the same results from the separate launches (no grid barrier: nothing can hang)
+        int rc = ktb200_moe_gate_forward(gc, qlen, input, idx, w, nullptr, bsz, stream);
+        if (rc) return rc;
+        return ktb200_moe_forward_shared(m, sh, qlen, k, idx, w, input, output, bsz, stream);
+    };
+    {   // once per (variant, device): raise the dynamic shared-memory limit and check that the G CTAs CAN be co-resident —
+        // the spin grid barriers need all of them on the SMs at the same time (1 CTA / SM at this shared-memory size)
         static size_t limit[4][64] = {};
+        static int resident[4][64] = {};
         const int v = (W > kBlockWarpsLo ? 2 : 0) + (fd == FMT_Q6K4T ? 1 : 0);
         if (limit[v][dev & 63] < smem) {
             KTB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            KTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, W * 32, smem));
+            resident[v][dev & 63] = per_sm * num_sms(dev);
             limit[v][dev & 63] = smem;
         }
+        if (resident[v][dev & 63] < G) return separate();
     }
-    // Launch attributes.  Cooperative: the driver guarantees (or refuses) co-residency of the G <= #SM CTAs the grid
-    // barriers need (KTB200_BLK_COOP=0: plain grid, co-resident whenever the GPU runs nothing else).  Programmatic
-    // stream serialization (KTB200_BLK_PDL=0 to disable): see griddep_wait() in the kernel.
-    static const int coop = [] { const char* e = getenv("KTB200_BLK_COOP"); return e ? atoi(e) : 1; }();
-    static const int pdl = [] { const char* e = getenv("KTB200_BLK_PDL"); return e ? atoi(e) : 1; }();
+    // Launch attributes.  Cooperative (library default): the driver guarantees co-residency of the G <= #SM CTAs or REFUSES
+    // the launch (cudaErrorCooperativeLaunchTooLarge: MPS thread percentage, green contexts ...) — then the separate
+    // launches run.  KTB200_BLK_COOP=0 is the caller's statement that this process decodes on one stream and owns the
+    // GPU (bench.py): a plain grid of G <= occupancy * #SM CTAs (checked above) is co-resident as soon as the previous
+    // kernel's CTAs exit.  Programmatic stream serialization (KTB200_BLK_PDL=0 to disable): see griddep_wait().
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(G); lc.blockDim = dim3(W * 32); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute at[2];
@@ -637,11 +650,15 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     if (pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; na++; }
     lc.attrs = at; lc.numAttrs = na;
     cudaError_t le = cudaLaunchKernelExC(&lc, fn, args);
-    if (le != cudaSuccess && coop && pdl) {   // the two attributes together are not accepted everywhere: keep the overlap
+    if (le != cudaSuccess && coop && pdl && (le == cudaErrorNotSupported || le == cudaErrorInvalidValue)) {
+        // cooperative + programmatic together are not accepted by every driver: keep the co-residency guarantee, drop the overlap
         (void)cudaGetLastError();
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.numAttrs = 1;
         le = cudaLaunchKernelExC(&lc, fn, args);
+    }
+    if (le == cudaErrorCooperativeLaunchTooLarge) {   // the driver cannot make the grid co-resident right now
+        (void)cudaGetLastError();
+        return separate();
     }
     if (le != cudaSuccess) { set_error("moe_block launch failed: %s", cudaGetErrorString(le)); return KTB200_ECUDA; }
     count_launch(1);

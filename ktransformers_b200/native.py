@@ -42,7 +42,7 @@ class MlaParams(C.Structure):
     _fields_ = [("batch", C.c_int), ("num_heads", C.c_int), ("page_size", C.c_int), ("max_pages_per_seq", C.c_int),
                 ("num_kv_splits", C.c_int), ("sm_scale", C.c_float), ("q_nope", C.c_void_p), ("q_pe", C.c_void_p),
                 ("kv_cache", C.c_void_p), ("page_table", C.c_void_p), ("kv_len", C.c_void_p), ("out", C.c_void_p),
-                ("lse_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("lse_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("kv_cache_rows", C.c_long)]
 
 
 _lib = None
@@ -85,6 +85,7 @@ SYMBOLS = {
     "ktb200_debug_stream_read": (_I, [_VP, _L, _I, _I, _I, _I, _VP, C.POINTER(C.c_float)]),
     "ktb200_mla_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "ktb200_mla_decode": (_I, [C.POINTER(MlaParams), _VP]),
+    "ktb200_debug_mla": (None, [_VP]),
     "ktb200_mla_kv_write": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP]),
 }
 

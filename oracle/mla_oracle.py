@@ -5,8 +5,9 @@ flashinfer_wrapper.attention_ref_torch (archive/ktransformers/operators/flashinf
 the Triton split-KV kernel (triton_attention.py:16-163: fp32 scores/softmax, P cast to the KV dtype before P.V).
     s[h,t] = (q_nope[h] . ckv[t] + q_pe[h] . k_pe[t]) * sm_scale ; p = softmax_t(s) ; out[h] = sum_t p[h,t] ckv[t]
 The reference's own tolerances for this op are loose (rel-mean < 2e-1, kt-kernel/examples/test_mla.py:724); the GPU
-tests use much tighter ones.  Parity status: restated from the torch reference code above; no stored golden
-vectors exist in the reference for MLA, so this oracle is pinned only by construction.
+tests use much tighter ones.  Parity status: PINNED — tests/golden/mla_ref.npz holds outputs of the reference's own
+`attention_ref_torch` (executed from /root/reference by tests/golden/make_mla_golden.py); tests/test_oracle_pinned.py
+checks this restatement against them (bf16 output rounding, base-2 LSE to 1e-4).
 """
 from __future__ import annotations
 

@@ -263,7 +263,8 @@ def test_gate_vs_golden_reference_torch(golden_dir):
     idx, w, logits = G.gate_forward(g["x"], g["W"], g["bias"], 6, 8, 4, want_logits=True)
     _, _, margin, _ = gate_oracle.route(g["x"], g["W"], g["bias"], top_k=6, n_group=8, topk_group=4, routed_scaling_factor=2.5, dtype=np.float64)
     ok = margin > 1e-5
-    assert ok.mean() > 0.95
+    print(f"knife-edge tokens excluded (relative margin < 1e-5 in float64): {int((~ok).sum())} of {ok.size}")
+    assert (~ok).sum() <= 1
     assert np.array_equal(np.sort(idx[ok], axis=1), np.sort(g["idx"][ok], axis=1))        # bit-exact routed ids
     np.testing.assert_allclose(logits, g["logits64"], rtol=0, atol=1e-4)
     for t in np.nonzero(ok)[0]:
@@ -289,7 +290,8 @@ def test_gate_vs_oracle_full_shapes(E, H, k, ng, tg, scoring, method, norm, scal
     idx, w, _ = G.gate_forward(x, W, bias, k, ng, tg, scoring, method, norm, scale)
     oidx, ow, margin, _ = gate_oracle.route(x, W, bias, dtype=np.float64, **kw)
     ok = margin > 1e-5
-    assert ok.mean() > 0.9
+    print(f"knife-edge tokens excluded (relative margin < 1e-5 in float64): {int((~ok).sum())} of {ok.size}")
+    assert (~ok).sum() <= 1      # a real tie needs two of ~256 fp32 scores within 1e-5: at most one of these 64 tokens
     assert np.array_equal(np.sort(idx[ok], axis=1), np.sort(oidx[ok], axis=1))
     for t in np.nonzero(ok)[0]:
         ref_w = dict(zip(oidx[t].tolist(), ow[t].tolist()))
@@ -298,6 +300,24 @@ def test_gate_vs_oracle_full_shapes(E, H, k, ng, tg, scoring, method, norm, scal
     # bf16 activations take the same path
     idx_b, _, _ = G.gate_forward(f32_to_bf16_bits(x), W, bias, k, ng, tg, scoring, method, norm, scale, hidden_type=BF16)
     assert idx_b.shape == idx.shape and (idx_b >= 0).all() and (idx_b < E).all()
+
+
+def test_gate_reference_recipe_seed42_no_exclusions(golden_dir):
+    """kt-kernel/examples/test_gate.py: seed 42, W = randn(256, 7168), bias = randn(256), input = randn(64, 7168);
+    expert ids must match the reference's torch MoEGate EXACTLY for every token (:214), weights < 1e-2 (:215).
+    Expected values: tests/golden/gate_seed42.npz (reference source executed on CPU by make_gate_seed42.py)."""
+    g = np.load(os.path.join(golden_dir, "gate_seed42.npz"))
+    torch.manual_seed(42)
+    W = torch.randn((256, 7168), dtype=torch.float32)
+    bias = torch.randn((256,), dtype=torch.float32)
+    x = torch.randn(64, 7168, dtype=torch.float32)
+    probe = np.array([W[0, 0], W[255, 7167], bias[7], x[0, 0], x[63, 7167]], np.float32)
+    if not np.array_equal(probe, g["probe"]):
+        pytest.skip("torch CPU RNG stream differs from the one the fixture was minted with")
+    idx, w, _ = G.gate_forward(x.numpy(), W.numpy(), bias.numpy(), 8, 8, 4)
+    assert np.array_equal(np.sort(idx, axis=1), np.sort(g["idx"], axis=1))
+    order_g, order_r = np.argsort(idx, axis=1), np.argsort(g["idx"], axis=1)
+    assert np.abs(np.take_along_axis(w, order_g, 1) - np.take_along_axis(g["w"], order_r, 1)).max() < 1e-5
 
 
 def test_moe_forward_ep_shard_call_matches_the_separate_calls():
@@ -379,6 +399,55 @@ def test_moe_block_single_launch_is_bit_identical_to_separate_launches(dt, hid, 
         mlp.close()
 
 
+@pytest.mark.parametrize("name,E,H,I,k,ng,tg,scale", [
+    ("DeepSeek-V3", 256, 7168, 2048, 8, 8, 4, 2.5),       # the configuration bench.py times: 28 blocks/row, 6 router splits
+    ("Kimi-K2", 384, 7168, 2048, 8, 1, 1, 2.827),
+    ("H5120", 64, 5120, 1536, 6, 8, 3, 1.0),              # 20 blocks/row, I not a multiple of the CTA count
+])
+def test_moe_block_full_shape_vs_oracle(oracle, name, E, H, I, k, ng, tg, scale):
+    """The ONE-launch MoE block (ktb200_moe_block_forward: router + top-k + routed experts + shared expert) at the full
+    shapes bench.py times, against the CPU oracle: ids vs the numpy router restatement (float64 margins), output vs
+    oracle.moe_forward + oracle.mlp_forward as two separately rounded bf16 terms (experts.py:984-1011)."""
+    gate_w, up_w, down_w = _synth(Q4_K, E * I * H, 301), _synth(Q4_K, E * I * H, 302), _synth(Q6_K, E * H * I, 303)
+    sg, su, sd = _synth(Q4_K, I * H, 304), _synth(Q4_K, I * H, 305), _synth(Q6_K, H * I, 306)
+    down_raw = down_w.clone()                                  # load_weights re-tiles Q6_K in place
+    sg_np, su_np, sd_np = sg.cpu().numpy(), su.cpu().numpy(), sd.cpu().numpy()
+    gb, db = gate_w.numel() // E, down_w.numel() // E
+    m = G.Moe(E, k, H, I, gate_w, up_w, down_w, Q4_K, Q4_K, Q6_K, BF16, max_tokens=8)
+    mlp = G.Mlp(H, I, sg, su, sd, Q4_K, Q4_K, Q6_K, BF16)
+    rng = np.random.default_rng(E + H)
+    W = rng.standard_normal((E, H)).astype(np.float32)
+    bias = rng.standard_normal(E).astype(np.float32)
+    gate = G.Gate(W, bias, k, ng, tg, scale=scale, hidden_type=BF16)
+    for qlen in (1, 8):
+        xb = f32_to_bf16_bits((rng.standard_normal((qlen, H)) / 100).astype(np.float32))
+        n0 = native.launch_count()
+        out, idx, w = G.moe_block_forward(gate, m, mlp, xb)
+        assert native.launch_count() - n0 == 1, "the persistent single-launch kernel must take this configuration"
+        # routing: exact ids wherever the decision is not a float64 knife edge
+        oidx, ow, margin, _ = gate_oracle.route(bf16_to_f32(xb), W, bias, top_k=k, n_group=ng, topk_group=tg, routed_scaling_factor=scale, dtype=np.float64)
+        ok = margin > 1e-5
+        print(f"{name} qlen={qlen}: knife-edge tokens excluded {int((~ok).sum())} of {qlen}")
+        assert (~ok).sum() <= 1 and ok.any()
+        assert np.array_equal(np.sort(idx[ok], axis=1), np.sort(oidx[ok], axis=1))
+        for t in np.nonzero(ok)[0]:
+            ref_w = dict(zip(oidx[t].tolist(), ow[t].tolist()))
+            for e, wv in zip(idx[t].tolist(), w[t].tolist()):
+                assert abs(ref_w[e] - wv) < 2e-5 * max(1.0, abs(wv))
+        # experts: the oracle on the selected experts only (remapped to 0..n-1), with the routing the kernel produced
+        sel = sorted(set(idx.reshape(-1).tolist()))
+        remap = {e: i for i, e in enumerate(sel)}
+        g_np = torch.cat([gate_w[e * gb:(e + 1) * gb] for e in sel]).cpu().numpy()
+        u_np = torch.cat([up_w[e * gb:(e + 1) * gb] for e in sel]).cpu().numpy()
+        d_np = torch.cat([down_raw[e * db:(e + 1) * db] for e in sel]).cpu().numpy()
+        ids_l = np.vectorize(remap.get)(idx).astype(np.int64)
+        routed = oracle.moe_forward(len(sel), H, I, g_np, u_np, d_np, Q4_K, Q4_K, Q6_K, BF16, ids_l, w, xb)
+        shared = oracle.mlp_forward(H, I, sg_np, su_np, sd_np, Q4_K, Q4_K, Q6_K, BF16, xb)
+        want = (torch.from_numpy(routed.view(np.int16)).view(torch.bfloat16) + torch.from_numpy(shared.view(np.int16)).view(torch.bfloat16))
+        assert_bf16_close(out, want.view(torch.int16).numpy().view(np.uint16))
+    m.close(); mlp.close()
+
+
 # ------------------------------------------------------------------------------------------ MLA decode
 def _mla_case(rng, B, Hq, page_size, lens, shuffle_pages=True):
     from oracle.mla_oracle import bf16_round
@@ -411,6 +480,52 @@ def test_mla_decode_vs_oracle(B, Hq, page_size, lens, splits):
     assert np.abs(out - exact).max() <= 2e-2 * ref_mag
     assert np.abs(out - exact).mean() <= 5e-3 * np.abs(exact).mean() + 1e-6
     np.testing.assert_allclose(lse, want_lse, rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_mla_decode_vs_reference_golden(golden_dir, name):
+    """ktb200_mla_decode against outputs of the reference's attention_ref_torch (tests/golden/mla_ref.npz)."""
+    g = np.load(os.path.join(golden_dir, "mla_ref.npz"))
+    f = lambda k: bf16_to_f32(g[f"{name}_{k}"])
+    q_nope, q_pe, kv, scale, want, lse2 = f("q_nope"), f("q_pe"), f("kv"), float(g[f"{name}_scale"]), f("out"), g[f"{name}_lse2"]
+    B, L = kv.shape[0], kv.shape[1]
+    for page in (32, 64):
+        npg = (L + page - 1) // page
+        rng = np.random.default_rng(page)
+        cache = np.full((B * npg + 2, page, 576), np.nan, np.float32)      # unwritten cache rows are NaN: they must not leak
+        table = rng.permutation(B * npg + 2)[: B * npg].reshape(B, npg).astype(np.int32)
+        for b in range(B):
+            for i in range(npg):
+                rows = kv[b, i * page:(i + 1) * page]
+                cache[table[b, i], : rows.shape[0]] = rows
+        for splits in (0, 1, 2):
+            out, lse = G.mla_decode(q_nope, q_pe, cache, table, np.full(B, L, np.int32), scale, num_kv_splits=splits)
+            mag = np.abs(want).max()
+            assert np.isfinite(out).all()
+            assert np.abs(out - want).max() <= 2e-2 * mag                  # bf16 P (reference: fp32 P), bf16 output
+            assert np.abs(out - want).mean() <= 4e-3 * np.abs(want).mean() + 1e-6
+            np.testing.assert_allclose(lse / np.log(2.0), lse2, rtol=0, atol=2e-3)
+
+
+def test_mla_decode_lazy_rescale_and_padding_slots():
+    """(1) keys whose scores grow by >> 2^8 along the sequence force the lazily raised reference maximum (the O^T
+    rescale in tensor memory) several times; (2) kv_len == 0 (padded CUDA-graph batch slot) gives zeros, not NaN."""
+    from oracle import mla_oracle
+    rng = np.random.default_rng(11)
+    B, Hq, page = 2, 128, 64
+    L = 700
+    q_nope, q_pe, kv, pt, kl = _mla_case(rng, B, Hq, page, [L, L])
+    ramp = np.linspace(0.02, 3.0, page * pt.shape[1], dtype=np.float32)
+    for b in range(B):
+        for i, pg in enumerate(pt[b]):
+            kv[pg] = mla_oracle.bf16_round(kv[pg] * ramp[i * page:(i + 1) * page, None])
+    kl[1] = 0
+    out, lse = G.mla_decode(q_nope, q_pe, kv, pt, kl, 0.3)
+    want, want_lse = mla_oracle.mla_decode(q_nope[:1], q_pe[:1], kv, pt[:1], kl[:1], 0.3, p_bf16=True)
+    mag = np.abs(want).max()
+    assert np.abs(out[0] - want[0]).max() <= (2.0 ** -7 + 2e-3) * mag
+    np.testing.assert_allclose(lse[0], want_lse[0], rtol=0, atol=2e-3)
+    assert not out[1].any() and np.isneginf(lse[1]).all()
 
 
 def test_mla_kv_write_then_decode_roundtrip():

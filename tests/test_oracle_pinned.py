@@ -121,3 +121,31 @@ def test_moe_against_ref_fresh(oracle, ref, qlen):
     # ... on top of the 1-ulp (2^-8 relative) granularity of the bf16 output itself
     assert (np.abs(a - b) <= 2.0 ** -7 * np.maximum(np.abs(a), np.abs(b)) + 4e-3 * np.abs(b).max()).all()
     assert np.abs(a - b).mean() <= 1e-3 * np.abs(b).mean()
+
+
+def _mla_fixture(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "mla_ref.npz"))
+    f = lambda k: bf16_to_f32(g[f"{name}_{k}"])
+    return f("q_nope"), f("q_pe"), f("kv"), float(g[f"{name}_scale"]), f("out"), g[f"{name}_lse2"]
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_mla_oracle_matches_reference_attention_ref_torch(golden_dir, name):
+    """oracle/mla_oracle.py against the outputs of the reference's attention_ref_torch (flashinfer_wrapper.py:30-76):
+    contiguous cache rows are laid out as pages of 32 with a shuffled page table."""
+    from oracle import mla_oracle
+    q_nope, q_pe, kv, scale, want, lse2 = _mla_fixture(golden_dir, name)
+    B, L = kv.shape[0], kv.shape[1]
+    page = 32
+    npg = (L + page - 1) // page
+    rng = np.random.default_rng(1)
+    cache = rng.standard_normal((B * npg + 2, page, 576)).astype(np.float32)
+    table = rng.permutation(B * npg + 2)[: B * npg].reshape(B, npg).astype(np.int32)
+    for b in range(B):
+        for i in range(npg):
+            rows = kv[b, i * page:(i + 1) * page]
+            cache[table[b, i], : rows.shape[0]] = rows
+    out, lse = mla_oracle.mla_decode(q_nope, q_pe, cache, table, np.full(B, L, np.int32), scale, p_bf16=False)
+    mag = np.abs(want).max()
+    assert np.abs(out - want).max() <= 2.0 ** -8 * mag * 1.01          # the reference rounds its output to bf16
+    np.testing.assert_allclose(lse / np.log(2.0), lse2, rtol=0, atol=1e-4)
