@@ -257,6 +257,25 @@ int ktb200_ep_all_gather_tokens(const ktb200_ep_comm* comm, const void* x_own_de
 int ktb200_ep_reduce_own_token(const ktb200_ep_comm* comm, void* y_out_dev, const void* y_shared_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Expert-parallel MoE block in ONE launch per layer and GPU (decode, one token per GPU): KDeepseekV3MoE.forward
+ * (archive/ktransformers/operators/experts.py:972-1012) with the dispatch / combine exchange of
+ * archive/ktransformers/models/modeling_deepseek_v3.py:550-605 done INSIDE the kernel over NVLink peer memory:
+ *   router + top-k of the rank's own token  ->  the message {x, ids, weights} is stored into every peer's buffer  ->
+ *   every rank runs the (token, expert) pairs it owns (gate/up, grid barrier, down, weighted sum per token in slot order)
+ *   ->  stores its row slices of all partial sums into the token owners' buffers  ->  each owner adds the `world` partial
+ *   rows in rank order, rounds, and adds the rounded shared-expert term (computed locally for its own token).
+ * `comm` as for ktb200_ep_all_gather_tokens, except that token_bufs[r] are MESSAGE buffers of
+ * world * ktb200_ep_msg_bytes(hidden, type) bytes; flag blocks (2*world + 2 uint32) start zeroed and are private to this
+ * call sequence.  Every rank must issue the same sequence of calls.  moe->group_max_len >= world.  idx_dev / w_dev
+ * receive the own token's routing.  phase_mask: 7 = the whole layer (production); 1 / 2 / 4 run the route+send, the
+ * experts+deliver and the combine phase as separate launches (tests emulate N ranks on one GPU with them).
+ * KTB200_EINVAL when the configuration is not the persistent kernel's (see ktb200_moe_block_forward).
+ * ------------------------------------------------------------------------------------------ */
+long ktb200_ep_msg_bytes(int hidden_size, int hidden_type);
+int ktb200_moe_ep_block_forward(const ktb200_gate_config* gate, ktb200_moe* moe, ktb200_mlp* shared, const ktb200_ep_comm* comm,
+                                const void* x_own_dev, void* y_out_dev, int64_t* idx_dev, float* w_dev, int phase_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Absorbed-MLA paged decode attention.  Replaces MLAWrapper.run / BatchMLAPagedAttentionWrapper
  * (archive/ktransformers/operators/flashinfer_wrapper.py:117-161; attention.py:419-447) and the
  * Triton split-KV decode (triton_attention.py:358-385).

@@ -16,7 +16,10 @@
 // 512 columns are the MN-major A operand [latent x tokens] (the swizzle is a function of the shared-memory address only).
 // The output is accumulated TRANSPOSED — O^T[latent 512][head 64] = 4 blocks of 128 TMEM lanes x 64 columns — because a
 // [head][latent] accumulator for 64 heads would need 512 columns in the M=64 tcgen05 layout (half the lanes idle): the
-// whole tensor memory.  TMEM map (512 columns allocated): [0,256) O^T, [256,288) / [288,320) the two S buffers.
+// whole tensor memory.  TMEM map (512 columns allocated): [0,256) O^T, [256,384) / [384,512) the two S buffers, each FOUR
+// partial accumulators of 32 columns: a 64 x 32 x 16 MMA is 16 cycles of work behind a pipeline several times as deep, so
+// 36 of them chained through ONE accumulator run at the latency, not the throughput (measured: ~75 cycles each); the 36
+// k-steps are dealt round-robin to four independent accumulators and the softmax warps add the four partial scores.
 //
 // Online softmax with a LAZY reference maximum: p = 2^(x - m_ref), m_ref is only raised (and O^T rescaled in TMEM, all
 // four warps) when some head's running maximum exceeds it by more than 8 — p stays <= 256, exact in bf16/fp32 terms —
@@ -45,20 +48,22 @@ constexpr int kQBytes = kHG * kDK * 2;             // 73,728
 constexpr int kPBytes = kHG * kLT * 2;             // 4,096: [8 head groups][4 token groups][8 heads][8 tokens]
 constexpr int kOffQ = kStages * kStageBytes;       // 147,456
 constexpr int kOffP = kOffQ + kQBytes;             // 221,184
-constexpr int kOffMisc = kOffP + kPBytes;          // 225,280
+constexpr int kOffMisc = kOffP + 2 * kPBytes;      // 229,376 (P is double-buffered)
 constexpr int kTmemCols = 512;
 constexpr int kColO = 0, kColS = 256;
+constexpr int kSChains = 4;          // independent partial-score accumulators per S buffer
 constexpr float kRescaleThreshold = 8.f;
 
 struct MlaMisc {
-    unsigned long long k_full[kStages], k_empty[kStages], s_full[2], s_empty[2], p_full, pv_done;
+    unsigned long long k_full[kStages], k_empty[kStages], s_full[2], s_empty[2], p_full, p_free[2];
     uint32_t tmem_base;
-    int need[4];
+    int need[2][4];
     float alpha[kHG];     // per head: 2^(m_ref_old - m_ref_new) of the current rescale
     float l[kHG];         // final row sums
     float m[kHG];         // final reference maxima
 };
 constexpr int kMlaSmem = kOffMisc + (int)sizeof(MlaMisc) + 1024;   // + slack to align the base to 1024 B
+static_assert(kMlaSmem <= 232448, "shared memory budget");
 
 struct MlaKParams {
     const __nv_bfloat16* q_nope;   // [B][Hq][512]
@@ -72,6 +77,16 @@ struct MlaKParams {
     float* debug;                  // optional: S of the first tile [64][32], P bytes, see ktb200_debug_mla
 };
 
+__device__ __forceinline__ float ex2(float x) {   // 2^x, one MUFU (x = -inf -> 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&v);
@@ -102,38 +117,74 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
         return;
     }
 
+    const bool dbg_cta = p.debug && tid == 0 && split == 0 && hg == 0 && b == 0;
+    if (dbg_cta) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(p.debug + 2048)[0] = t;
+    }
     // ---- one-time setup -----------------------------------------------------------------------------------------
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&kv_map);
         for (int s = 0; s < kStages; s++) { bar_init(smem_u32(&misc.k_full[s]), 1); bar_init(smem_u32(&misc.k_empty[s]), 1); }
         for (int s = 0; s < 2; s++) { bar_init(smem_u32(&misc.s_full[s]), 1); bar_init(smem_u32(&misc.s_empty[s]), 4); }
         bar_init(smem_u32(&misc.p_full), 4);
-        bar_init(smem_u32(&misc.pv_done), 1);
+        bar_init(smem_u32(&misc.p_free[0]), 1);
+        bar_init(smem_u32(&misc.p_free[1]), 1);
         bar_fence_init();
+        // the first tiles do not depend on anything set up below: request them now
+        for (int j = 0; j < n && j < kStages; j++) {
+            const int t_base = (tile0 + j) * kLT;
+            const int page = p.page_table[(long)b * p.max_pages + t_base / p.page_size];
+            const int row = page * p.page_size + t_base % p.page_size;
+            const uint32_t bar = smem_u32(&misc.k_full[j]);
+            bar_expect_tx(bar, kStageBytes);
+#pragma unroll
+            for (int c = 0; c < kChunks; c++) tma_load_2d(base + j * kStageBytes + c * kKRegion, &kv_map, bar, c * 64, row);
+            if (p.debug && split == 0 && hg == 0 && b == 0) reinterpret_cast<unsigned long long*>(p.debug + 2048)[192 + j] = gtime();
+        }
     }
     if (warp == 1) tmem_alloc(smem_u32(&misc.tmem_base), kTmemCols);
     // Q (64 heads x 576) -> shared memory in the K-major 128-byte-swizzle layout: chunk region c (64 columns) holds 64
     // rows of 128 B; the 16-byte piece j of row r sits at piece (j ^ (r & 7)).  Rows beyond num_heads are zero.
-    for (int i = tid; i < kHG * (kDK / 8); i += kMlaThreads) {
-        const int r = i / (kDK / 8), j = i - r * (kDK / 8);   // j: 16-byte piece of the 576-wide row (0..71)
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (h0 + r < p.num_heads) {
-            const long hrow = (long)b * p.num_heads + h0 + r;
-            v = j < 64 ? reinterpret_cast<const uint4*>(p.q_nope + hrow * kDV)[j] : reinterpret_cast<const uint4*>(p.q_pe + hrow * 64)[j - 64];
+    {
+        constexpr int kPieces = kHG * (kDK / 8), kIter = kPieces / kMlaThreads;   // 4608 = 24 x 192
+        static_assert(kPieces % kMlaThreads == 0, "Q pieces");
+#pragma unroll
+        for (int i0 = 0; i0 < kIter; i0 += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {   // 8 independent 16-byte loads in flight per thread
+                const int i = tid + (i0 + u) * kMlaThreads, r = i / (kDK / 8), j = i - r * (kDK / 8);
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (h0 + r < p.num_heads) {
+                    const long hrow = (long)b * p.num_heads + h0 + r;
+                    v[u] = j < 64 ? __ldg(reinterpret_cast<const uint4*>(p.q_nope + hrow * kDV) + j) : __ldg(reinterpret_cast<const uint4*>(p.q_pe + hrow * 64) + (j - 64));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = tid + (i0 + u) * kMlaThreads, r = i / (kDK / 8), j = i - r * (kDK / 8);
+                const int c = j >> 3, jj = j & 7;
+                *reinterpret_cast<uint4*>(smem + kOffQ + c * kQRegion + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
+            }
         }
-        const int c = j >> 3, jj = j & 7;
-        *reinterpret_cast<uint4*>(smem + kOffQ + c * kQRegion + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = misc.tmem_base;
+    if (dbg_cta) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(p.debug + 2048)[1] = t;
+    }
 
     if (warp == 0) {
         // ================================================================ TMA producer
         if (lane == 0) {
-            for (int j = 0; j < n; j++) {
+            for (int j = kStages; j < n; j++) {
                 const int s = j % kStages;
                 bar_wait(smem_u32(&misc.k_empty[s]), ((j / kStages) & 1) ^ 1);
                 const int t_base = (tile0 + j) * kLT;
@@ -143,6 +194,7 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
                 bar_expect_tx(bar, kStageBytes);
 #pragma unroll
                 for (int c = 0; c < kChunks; c++) tma_load_2d(base + s * kStageBytes + c * kKRegion, &kv_map, bar, c * 64, row);
+                if (p.debug && split == 0 && hg == 0 && b == 0 && j < 60) reinterpret_cast<unsigned long long*>(p.debug + 2048)[192 + j] = gtime();
             }
         }
         __syncwarp();
@@ -161,8 +213,8 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
                 for (int c = 0; c < kChunks; c++)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        mma_f16(tmem + kColS + buf * kLT, smem_desc(qb + c * kQRegion + k * 32, 16, 1024, kLayoutSw128),
-                                smem_desc(kb + c * kKRegion + k * 32, 16, 1024, kLayoutSw128), idesc_qk, (c | k) != 0);
+                        mma_f16(tmem + kColS + (buf * kSChains + (k & (kSChains - 1))) * kLT, smem_desc(qb + c * kQRegion + k * 32, 16, 1024, kLayoutSw128),
+                                smem_desc(kb + c * kKRegion + k * 32, 16, 1024, kLayoutSw128), idesc_qk, c != 0);
                 mma_commit(smem_u32(&misc.s_full[buf]));
             };
             issue_qk(0);
@@ -171,7 +223,7 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
                 bar_wait(smem_u32(&misc.p_full), j & 1);
                 tc_fence_after();
                 const int s = j % kStages;
-                const uint32_t kb = base + s * kStageBytes, pb = base + kOffP;
+                const uint32_t kb = base + s * kStageBytes, pb = base + kOffP + (j & 1) * kPBytes;
 #pragma unroll
                 for (int m = 0; m < 4; m++)
 #pragma unroll
@@ -179,56 +231,73 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
                         mma_f16(tmem + kColO + m * kHG, smem_desc(kb + 2 * m * kKRegion + k * 2048, kKRegion, 1024, kLayoutSw128),
                                 smem_desc(pb + k * 256, 128, 512, kLayoutNone), idesc_pv, (j | k) != 0);
                 mma_commit(smem_u32(&misc.k_empty[s]));
-                mma_commit(smem_u32(&misc.pv_done));
+                mma_commit(smem_u32(&misc.p_free[j & 1]));
+                if (p.debug && split == 0 && hg == 0 && b == 0 && j < 60) reinterpret_cast<unsigned long long*>(p.debug + 2048)[128 + j] = gtime();
             }
         }
         __syncwarp();
     } else {
         // ================================================================ softmax / rescale / epilogue (4 warps)
+        // S rows of a sub-partition live in its TMEM lanes 0..15 (M = 64 layout): lane l < 16 loads the 32 scores of head
+        // 16 sp + l and hands tokens 16..31 to lane l + 16, so that all 32 lanes work: lane = (head, half of the tile).
         const int sp = warp & 3;                       // TMEM sub-partition of this warp
         const uint32_t lane_base = (uint32_t)(32 * sp) << 16;
-        const int head = 16 * sp + lane;               // S rows of this sub-partition live in its lanes 0..15 (M = 64 layout)
-        const bool owner = lane < 16;
+        const int upper = lane >> 4;
+        const int head = 16 * sp + (lane & 15);
         const int st = tid - 64;                       // 0..127 among the softmax threads
-        float m_ref = -INFINITY, m_run = -INFINITY, l = 0.f;
+        float m_ref = -INFINITY, m_run = -INFINITY, l = 0.f;   // l: this lane's half of the row sum
         for (int j = 0; j < n; j++) {
             const int buf = j & 1;
             bar_wait(smem_u32(&misc.s_full[buf]), (j >> 1) & 1);
             tc_fence_after();
+            if (p.debug && st == 0 && split == 0 && hg == 0 && b == 0 && j < 60) reinterpret_cast<unsigned long long*>(p.debug + 2048)[64 + j] = gtime();
             uint32_t sv[32];
-            tmem_ld32(tmem + lane_base + kColS + buf * kLT, sv);
-            tmem_wait_ld();
+            {   // S = sum of the four partial accumulators
+                uint32_t t1[32], t2[32];
+                const uint32_t sa = tmem + lane_base + kColS + buf * kSChains * kLT;
+                tmem_ld32(sa, sv);
+                tmem_ld32(sa + kLT, t1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i++) sv[i] = __float_as_uint(__uint_as_float(sv[i]) + __uint_as_float(t1[i]));
+                tmem_ld32(sa + 2 * kLT, t1);
+                tmem_ld32(sa + 3 * kLT, t2);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i++) sv[i] = __float_as_uint(__uint_as_float(sv[i]) + (__uint_as_float(t1[i]) + __uint_as_float(t2[i])));
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bar_arrive(smem_u32(&misc.s_empty[buf]));
-            if (p.debug && j == 0 && owner && split == 0 && hg == 0 && b == 0)
+            if (p.debug && j == 0 && !upper && split == 0 && hg == 0 && b == 0)
                 for (int i = 0; i < 32; i++) p.debug[head * 32 + i] = __uint_as_float(sv[i]);
-            const int t_base = (tile0 + j) * kLT;
-            float x[32];
+            const int t_base = (tile0 + j) * kLT + 16 * upper;
+            float x[16];
             float mt = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                x[i] = (t_base + i < L) ? __uint_as_float(sv[i]) * p.scale_log2 : -INFINITY;
+            for (int i = 0; i < 16; i++) {
+                const uint32_t hi = __shfl_sync(0xffffffffu, sv[16 + i], lane & 15);
+                const float v = __uint_as_float(upper ? hi : sv[i]);
+                x[i] = (t_base + i < L) ? v * p.scale_log2 : -INFINITY;
                 mt = fmaxf(mt, x[i]);
             }
+            mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
             m_run = fmaxf(m_run, mt);
             // does any head need its reference raised?  (never on the first tile: O^T is overwritten by the first PV)
             bool need = false;
             if (j == 0) m_ref = m_run;
-            else need = owner && (m_run - m_ref > kRescaleThreshold);
+            else need = m_run - m_ref > kRescaleThreshold;
             const unsigned any_w = __ballot_sync(0xffffffffu, need);
-            if (lane == 0) misc.need[warp - 2] = any_w != 0;
+            if (lane == 0) misc.need[buf][warp - 2] = any_w != 0;
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            const bool any = misc.need[0] | misc.need[1] | misc.need[2] | misc.need[3];
-            // P is single-buffered and O^T must be quiescent before a rescale: the previous PV has to be complete
-            if (j > 0) bar_wait(smem_u32(&misc.pv_done), (j - 1) & 1);
+            const bool any = misc.need[buf][0] | misc.need[buf][1] | misc.need[buf][2] | misc.need[buf][3];
             if (any) {
+                // O^T must be quiescent: the previous PV has to be complete (it also frees the other P buffer)
+                bar_wait(smem_u32(&misc.p_free[(j - 1) & 1]), ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                if (owner) {
-                    const float a = need ? exp2f(m_ref - m_run) : 1.f;
-                    misc.alpha[head] = a;
-                    if (need) { l *= a; m_ref = m_run; }
-                }
+                const float a = need ? ex2(m_ref - m_run) : 1.f;
+                if (!upper) misc.alpha[head] = a;
+                if (need) { l *= a; m_ref = m_run; }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
                 for (int q = 0; q < 8; q++) {   // 4 latent blocks x 2 halves of the 64 head columns
@@ -242,25 +311,28 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
                 }
                 tmem_wait_st();
                 tc_fence_before();
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // alpha[] / need[] may be rewritten only after everyone used them
             }
-            if (owner) {
+            // this tile's P buffer was last read by PV(j - 2)
+            if (j >= 2) bar_wait(smem_u32(&misc.p_free[buf]), ((j >> 1) & 1) ^ 1);
+            {
                 float ps = 0.f;
-                uint32_t pk[16];
+                uint32_t pk[8];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = exp2f(x[i] - m_ref), p1 = exp2f(x[i + 1] - m_ref);
+                for (int i = 0; i < 16; i += 2) {
+                    const float p0 = ex2(x[i] - m_ref), p1 = ex2(x[i + 1] - m_ref);
                     ps += p0 + p1;
                     pk[i >> 1] = pack_bf16(p0, p1);
                 }
                 l += ps;
                 // P[head][token] as the K-major no-swizzle B operand: core matrix (8 heads x 8 tokens) = 128 contiguous bytes
-                uint8_t* prow = smem + kOffP + (head >> 3) * 512 + (head & 7) * 16;
-#pragma unroll
-                for (int g = 0; g < 4; g++) *reinterpret_cast<uint4*>(prow + g * 128) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                uint8_t* prow = smem + kOffP + buf * kPBytes + (head >> 3) * 512 + (head & 7) * 16 + upper * 256;
+                *reinterpret_cast<uint4*>(prow) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(prow + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
             // rows of the tile beyond kv_len hold whatever the page contains: P is 0 there, but 0 * NaN is NaN -> zero the V rows
-            if (t_base + kLT > L) {
-                const int valid = L - t_base;
+            if ((tile0 + j) * kLT + kLT > L) {
+                const int valid = L - (tile0 + j) * kLT;
                 uint8_t* kb = smem + (j % kStages) * kStageBytes;
                 for (int i = st; i < (kLT - valid) * 64; i += 128) {      // 64 pieces of 16 B per row over the 8 latent chunks
                     const int r = valid + i / 64, pc = i % 64;
@@ -270,26 +342,49 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
             fence_async_smem();
             __syncwarp();
             if (lane == 0) bar_arrive(smem_u32(&misc.p_full));
+            if (p.debug && st == 0 && split == 0 && hg == 0 && b == 0 && j < 60) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                reinterpret_cast<unsigned long long*>(p.debug + 2048)[4 + j] = t;
+            }
         }
         // ---- epilogue: O^T / l -> fp32 partial output, base-2 LSE ---------------------------------------------------
-        if (owner) { misc.l[head] = l; misc.m[head] = m_ref; }
-        bar_wait(smem_u32(&misc.pv_done), (n - 1) & 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        if (!upper) { misc.l[head] = l; misc.m[head] = m_ref; }
+        bar_wait(smem_u32(&misc.p_free[(n - 1) & 1]), ((n - 1) >> 1) & 1);   // the last PV (and with it every earlier one) is complete
         tc_fence_after();
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (p.debug && st == 0 && split == 0 && hg == 0 && b == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            reinterpret_cast<unsigned long long*>(p.debug + 2048)[2] = t;
+        }
         if (st < kHG && h0 + st < p.num_heads) lse_out[st] = misc.m[st] + log2f(misc.l[st]);
+        if (st < kHG) misc.alpha[st] = 1.f / misc.l[st];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
-        for (int q = 0; q < 8; q++) {
-            uint32_t ov[32];
-            tmem_ld32(tmem + lane_base + kColO + q * 32, ov);
-            tmem_wait_ld();
-            const int latent = (q >> 1) * 128 + 32 * sp + lane;
+        for (int half = 0; half < 2; half++) {
+            float inv[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const int hh = (q & 1) * 32 + i;
-                if (h0 + hh < p.num_heads) o_out[(long)hh * kDV + latent] = __uint_as_float(ov[i]) / misc.l[hh];
+            for (int i = 0; i < 32; i++) inv[i] = misc.alpha[half * 32 + i];
+            const int nh = min(32, p.num_heads - h0 - half * 32);   // valid heads of this half
+#pragma unroll 1
+            for (int blk = 0; blk < 4; blk++) {
+                uint32_t ov[32];
+                tmem_ld32(tmem + lane_base + kColO + blk * kHG + half * 32, ov);
+                tmem_wait_ld();
+                float* dst = o_out + (long)(half * 32) * kDV + blk * 128 + 32 * sp + lane;
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if (i < nh) dst[(long)i * kDV] = __uint_as_float(ov[i]) * inv[i];
             }
         }
         tc_fence_before();
+        if (p.debug && st == 0 && split == 0 && hg == 0 && b == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            reinterpret_cast<unsigned long long*>(p.debug + 2048)[3] = t;
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -424,7 +519,10 @@ int ktb200_mla_decode(const ktb200_mla_params* q, void* stream) {
 }
 
 // Diagnostics: while set, CTA (split 0, head group 0, sequence 0) of ktb200_mla_decode writes the raw fp32 scores of its
-// first tile (S[64 heads][32 tokens], before scaling) to debug_dev (>= 2048 floats).
+// first tile (S[64 heads][32 tokens], before scaling) to debug_dev[0..2048) and %globaltimer stamps (uint64) to
+// debug_dev + 2048: [0] kernel start, [1] setup done, [2] last PV complete, [3] epilogue stored, [4 + j] tile j's P ready
+// [64 + j] tile j's S seen
+// by the softmax warps, [128 + j] PV(j) issued, [192 + j] tile j's TMA issued (debug_dev must hold >= 2048 floats + 256 uint64).
 void ktb200_debug_mla(float* debug_dev) { ktb::g_mla_debug = debug_dev; }
 
 int ktb200_mla_kv_write(void* kv_cache, int page_size, const void* ckv, const void* k_pe, const int* page_idx,
