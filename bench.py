@@ -42,6 +42,16 @@ BYTES_DOWN_PER_EXPERT = H * I * 210 // 256                  # 12,042,240
 BYTES_PER_EXPERT = BYTES_GATE_UP_PER_EXPERT + BYTES_DOWN_PER_EXPERT   # 28,557,312
 
 
+def committed_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu summary
+    (profiles/traffic.json, written by profiles/summarize.py from an `ncu --set full` capture); None when absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d.get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -109,7 +119,7 @@ class RefCpuMoe:
     """The reference's own CPU MoE (oracle/_ref: unmodified moe.cpp + llamafile + ggml) on synthetic weights of
     the real per-expert shapes.  `n_experts` experts are resident in host RAM (bounded sample of the 256)."""
 
-    def __init__(self, n_experts=32, threads=None):
+    def __init__(self, n_experts=32, threads=None, tokens=1):
         import numpy as np
         import torch
 
@@ -131,12 +141,13 @@ class RefCpuMoe:
             self.port = Oracle()
             self.isa = "plain C (oracle/ktoracle.c, OpenMP)"
         rng = np.random.default_rng(0)
-        self.x = (rng.standard_normal((1, H)) / 100).astype(np.float32)
+        self.tokens = tokens          # tokens per layer-forward (the --gpus N arm decodes N tokens per step)
+        self.x = (rng.standard_normal((tokens, H)) / 100).astype(np.float32)
         from oracle.bindings import f32_to_bf16_bits
         self.xb = f32_to_bf16_bits(self.x)
-        self.ids = [np.stack([rng.permutation(n_experts)[:K]]).astype(np.uint64) for _ in range(N_MOE_LAYERS)]
-        self.w = rng.random((1, K)).astype(np.float32)
-        self.out = np.zeros((1, H), np.uint16)
+        self.ids = [np.stack([rng.permutation(n_experts)[:K] for _ in range(tokens)]).astype(np.uint64) for _ in range(N_MOE_LAYERS)]
+        self.w = rng.random((tokens, K)).astype(np.float32)
+        self.out = np.zeros((tokens, H), np.uint16)
         self.tuned = None
         if self.kind == "reference" and threads is None:
             self.tune_threads()
@@ -178,24 +189,25 @@ class RefCpuMoe:
     def describe(self, layers_timed):
         tuned = f" (thread ladder ms/layer: {self.tuned})" if self.tuned else ""
         return (f"{self.kind} CPU MoE ({self.isa}), {self.threads} host threads{tuned}: routed experts only (the reference keeps "
-                f"router/shared experts on the GPU), {layers_timed} layer-forwards of 8-of-{self.n} resident experts at real shapes; "
-                f"tok/s = 1/(58 x mean layer time)")
+                f"router/shared experts on the GPU), {layers_timed} layer-forwards of {self.tokens} token(s) x 8-of-{self.n} resident experts "
+                f"at real shapes; tok/s = tokens/(58 x mean layer time)")
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    cpu = RefCpuMoe()
+    world = max(1, args.gpus)
+    cpu = RefCpuMoe(tokens=world)            # same config as the B200 arm: `world` tokens per step
     for _ in range(args.warmup):
         cpu.token()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu.token()
     dt = (time.perf_counter() - t0) / args.steps
-    v = 1.0 / dt
+    v = world / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8xint4->int32, fp32 scales (llamafile Q8_K x Q4_K/Q6_K)", "data": "synthetic", "config": workload_config(args, 1),
+            "dtype": "int8xint4->int32, fp32 scales (llamafile Q8_K x Q4_K/Q6_K)", "data": "synthetic", "config": workload_config(args, world),
             "cpu_baseline": {"value": v, "unit": "tok/s", "cores": cpu.threads, "kind": cpu.kind, "sample": cpu.describe(args.steps * N_MOE_LAYERS)},
             "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -211,7 +223,7 @@ def workload_config(args, world):
             "resident_layer_sets": args.resident_layers, "layers_per_step": N_MOE_LAYERS, "tokens_per_step": world,
             "parallelism": f"ep{world}" if world > 1 else "single",
             "block_launch": ("plain grid + programmatic dependent launch" if os.environ.get("KTB200_BLK_COOP", "1") == "0"
-                             else "cooperative + programmatic dependent launch") if world == 1 else "separate kernels (expert-parallel shard)",
+                             else "cooperative + programmatic dependent launch"),
             "l2": "inputs larger than L2: each layer set is 7.4 GB and is revisited after >= 2 other sets",
             "note": "layer inputs are not chained (random-init weights overflow bf16 within a few layers); every layer routes and computes on the step's hidden state with its own router/expert weights"}
 
@@ -258,23 +270,56 @@ def main():
 
     E_local = E // world
     L = args.resident_layers
-    hid = BF16 if world == 1 else F32        # EP: fp32 partial sums are reduce-scattered, then rounded once
-    hid_torch = torch.bfloat16 if world == 1 else torch.float32
+
+    # ---- expert-parallel exchange buffers (world > 1): one symmetric allocation per rank holds the message buffer
+    # ({x, ids, weights} rows), the fp32 partial buffer and the flag block of ktb200_moe_ep_block_forward; torch's symmetric
+    # memory maps the peers' copies.  KTB200_EP_P2P=0 (or a failing rendezvous) keeps NCCL collectives + separate kernels.
+    T = world                                                  # tokens in flight per layer (one per GPU)
+    ep = None
+    ep_mode = "nccl all_gather + reduce_scatter, separate kernels"
+    if world > 1 and os.environ.get("KTB200_EP_P2P", "1") != "0":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            msg_b, part_b, flag_b = T * lib.ktb200_ep_msg_bytes(H, BF16), T * H * 4, 4 * (2 * T + 2)
+            o_part = (msg_b + 255) // 256 * 256
+            o_flag = o_part + (part_b + 255) // 256 * 256
+            total_b = o_flag + (flag_b + 255) // 256 * 256
+            sym = symm_mem.empty(total_b, dtype=torch.uint8, device=dev)
+            sym.zero_()
+            hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+            base = [int(p_) for p_ in hdl.buffer_ptrs]
+            ep = native.EpComm.make(rank, world, H, BF16, base, [b + o_part for b in base], [b + o_flag for b in base])
+            ep_flags = sym[o_flag:o_flag + flag_b].view(torch.int32)
+            torch.cuda.synchronize(); dist.barrier()
+            ep_mode = "ONE launch per layer (ktb200_moe_ep_block_forward): router of the own token, NVLink peer-memory push of {x, ids, w}, owned (token, expert) pairs, push of partial sums, combine"
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                print(f"# symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            ep = None
+        ok = torch.tensor([1 if ep is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)               # all ranks or none
+        if int(ok.item()) == 0:
+            ep, ep_mode = None, "nccl all_gather + reduce_scatter, separate kernels"
+    hid = BF16 if (world == 1 or ep is not None) else F32      # NCCL route: fp32 partial sums are reduce-scattered, then rounded once
+    hid_torch = torch.bfloat16 if hid == BF16 else torch.float32
 
     # ---- resident weight sets ---------------------------------------------------------------------------------
     layers = []
+    raw0 = None                                                 # layer 0's down tensor before the in-place Q6_K re-tiling (parity check)
     for l in range(L):
         seed = 1000 * l + 17 * rank
         gate = synth_blocks(Q4_K, E_local * I * H, dev, seed + 1)
         up = synth_blocks(Q4_K, E_local * I * H, dev, seed + 2)
         down = synth_blocks(Q6_K, E_local * H * I, dev, seed + 3)
+        sg, su, sd = (synth_blocks(Q4_K, I * H, dev, 1000 * l + 5), synth_blocks(Q4_K, I * H, dev, 1000 * l + 6),
+                      synth_blocks(Q6_K, H * I, dev, 1000 * l + 7))
+        if l == 0:
+            raw0 = dict(down=down.clone(), sg=sg.cpu().numpy(), su=su.cpu().numpy(), sd=sd.cpu().numpy())
         cfg = native.MoeConfig(E_local, K, H, I, 64, 10, max(8, world), 1, gate.data_ptr(), up.data_ptr(), down.data_ptr(),
                                Q4_K, Q4_K, Q6_K, hid, rank * E_local)
         h = C.c_void_p()
         native.check(lib.ktb200_moe_create(C.byref(cfg), local_rank, C.byref(h)))
         native.check(lib.ktb200_moe_load_weights(h, S()))
-        sg, su, sd = (synth_blocks(Q4_K, I * H, dev, 1000 * l + 5), synth_blocks(Q4_K, I * H, dev, 1000 * l + 6),
-                      synth_blocks(Q6_K, H * I, dev, 1000 * l + 7))
         mh = C.c_void_p()
         native.check(lib.ktb200_mlp_create(H, I, sg.data_ptr(), su.data_ptr(), sd.data_ptr(), Q4_K, Q4_K, Q6_K, BF16, 8, local_rank, C.byref(mh)))
         native.check(lib.ktb200_mlp_load_weights(mh, S()))
@@ -286,54 +331,19 @@ def main():
     torch.cuda.synchronize()
 
     # ---- static buffers ---------------------------------------------------------------------------------------
-    T = world                                                  # tokens in flight per layer (one per GPU)
     x_own = torch.zeros((1, H), dtype=torch.bfloat16, device=dev)          # this GPU's token
     x_all = torch.zeros((T, H), dtype=torch.bfloat16, device=dev)
     x_all_f32 = torch.zeros((T, H), dtype=torch.float32, device=dev)
     ids = torch.zeros((T, K), dtype=torch.int64, device=dev)
     wts = torch.zeros((T, K), dtype=torch.float32, device=dev)
-    part = torch.zeros((T, H), dtype=hid_torch, device=dev)                # routed output (EP: fp32 partial)
+    part = torch.zeros((T, H), dtype=hid_torch, device=dev)                # NCCL route: fp32 partial sums
     own_f32 = torch.zeros((1, H), dtype=torch.float32, device=dev)
     y = torch.zeros((1, H), dtype=torch.bfloat16, device=dev)              # layer output for this GPU's token
-    acc = torch.zeros((1, H), dtype=torch.float32, device=dev)             # something that depends on every layer
     x_host = torch.zeros((1, H), dtype=torch.bfloat16).pin_memory()
-    y_host = torch.zeros((1, H), dtype=torch.float32).pin_memory()
-    ids_host = torch.zeros((1, K), dtype=torch.int64).pin_memory()
-    w_host = torch.zeros((1, K), dtype=torch.float32).pin_memory()
+    y_host = torch.zeros((1, H), dtype=torch.bfloat16).pin_memory()
     out_host = torch.zeros((1, H), dtype=torch.bfloat16).pin_memory()
-
     side_stream = torch.cuda.Stream() if world > 1 else None
     y_sh = torch.zeros((1, H), dtype=torch.bfloat16, device=dev)
-
-    # expert-parallel exchange over NVLink peer memory (ktb200_ep_*): one symmetric allocation per rank holds the
-    # token buffer, the fp32 partial buffer and the flag block; torch's symmetric memory maps the peers' copies.
-    # KTB200_EP_P2P=0 (or a failing rendezvous) keeps the NCCL collectives.
-    ep = None
-    ep_mode = "nccl all_gather + reduce_scatter"
-    if world > 1 and os.environ.get("KTB200_EP_P2P", "1") != "0":
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            tok_b, part_b, flag_b = T * H * 2, T * H * 4, 4 * (2 * T + 2)
-            o_part = (tok_b + 255) // 256 * 256
-            o_flag = o_part + (part_b + 255) // 256 * 256
-            total_b = o_flag + (flag_b + 255) // 256 * 256
-            sym = symm_mem.empty(total_b, dtype=torch.uint8, device=dev)
-            sym.zero_()
-            hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
-            base = [int(p_) for p_ in hdl.buffer_ptrs]
-            ep = native.EpComm.make(rank, world, H, BF16, base, [b + o_part for b in base], [b + o_flag for b in base])
-            part = sym[o_part:o_part + part_b].view(torch.float32).view(T, H)      # the shard's kernels write the symmetric copy
-            torch.cuda.synchronize(); dist.barrier()
-            ep_mode = "hand-written NVLink peer-memory exchange (ktb200_ep_all_gather_tokens / ktb200_ep_reduce_own_token)"
-        except Exception as e:  # pragma: no cover
-            if rank == 0:
-                print(f"# symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
-            ep = None
-        ok = torch.tensor([1 if ep is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)               # all ranks or none
-        if int(ok.item()) == 0:
-            ep, ep_mode = None, "nccl all_gather + reduce_scatter"
-            part = torch.zeros((T, H), dtype=hid_torch, device=dev)
 
     def layer_device(l):
         Lr = layers[l % L]
@@ -342,26 +352,19 @@ def main():
             native.check(lib.ktb200_moe_block_forward(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], 1, x_own.data_ptr(), y.data_ptr(),
                                                       ids.data_ptr(), wts.data_ptr(), None, S()))
             return
-        main = torch.cuda.current_stream()
         if ep is not None:
-            # expert-parallel layer in 5 launches: peer-memory all-gather (+ fp32 rows), router, the shard's two expert
-            # launches (the shared expert of this GPU's own token rides along as an extra slot), peer-memory reduction
-            # with the epilogue y = round(sum of partials) + round(shared)   (KDeepseekV3MoE.forward, experts.py:984-1011)
-            native.check(lib.ktb200_ep_all_gather_tokens(C.byref(ep), x_own.data_ptr(), x_all_f32.data_ptr(), S()))
-            native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, ep._keep[0][rank], ids.data_ptr(), wts.data_ptr(), None, None, S()))
-            native.check(lib.ktb200_moe_forward_ep(Lr["moe"], Lr["mlp"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(),
-                                                   rank, y_sh.data_ptr(), None, S()))
-            native.check(lib.ktb200_ep_reduce_own_token(C.byref(ep), y.data_ptr(), y_sh.data_ptr(), S()))
+            native.check(lib.ktb200_moe_ep_block_forward(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], C.byref(ep), x_own.data_ptr(), y.data_ptr(),
+                                                         ids.data_ptr(), wts.data_ptr(), 7, S()))
             return
+        main = torch.cuda.current_stream()
         # NCCL route: the shared expert of this GPU's own token needs no communication: it runs on a side stream under the
         # all-gather, and joins as the second rounded term
         side_stream.wait_stream(main)
         with torch.cuda.stream(side_stream):
             native.check(lib.ktb200_mlp_forward(Lr["mlp"], 1, x_own.data_ptr(), y_sh.data_ptr(), 0, None, S()))
         dist.all_gather_into_tensor(x_all, x_own)
-        xin = x_all
-        native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, xin.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))
-        x_all_f32.copy_(xin)
+        native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), T, x_all.data_ptr(), ids.data_ptr(), wts.data_ptr(), None, None, S()))
+        x_all_f32.copy_(x_all)
         native.check(lib.ktb200_moe_forward(Lr["moe"], T, K, ids.data_ptr(), wts.data_ptr(), x_all_f32.data_ptr(), part.data_ptr(), None, S()))
         dist.reduce_scatter_tensor(own_f32, part)
         y.copy_(own_f32)
@@ -371,6 +374,69 @@ def main():
     def step_device():
         for l in range(N_MOE_LAYERS):
             layer_device(l)
+
+    rng = np.random.default_rng(1234 + rank)
+
+    def fresh_input():
+        x_host.copy_(torch.from_numpy((rng.standard_normal((1, H)) / 100).astype(np.float32)).to(torch.bfloat16))
+
+    # ---- parity check (outside every timed region): layer 0's output for this step's token against the CPU oracle ------
+    parity = None
+    try:
+        from oracle.bindings import Oracle, bf16_to_f32
+        from oracle import gate_oracle
+        orc = Oracle()
+        fresh_input(); x_own.copy_(x_host); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        layer_device(0)
+        torch.cuda.synchronize()
+        Lr = layers[0]
+        gate_t, up_t = Lr["keep"][0], Lr["keep"][1]
+        gbytes, dbytes = gate_t.numel() // E_local, raw0["down"].numel() // E_local
+        bits = lambda t: t.detach().cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+        if world > 1:
+            xs_all = torch.zeros((T, H), dtype=torch.bfloat16, device=dev); dist.all_gather_into_tensor(xs_all, x_own)
+            ids_all = torch.zeros((T, K), dtype=torch.int64, device=dev); dist.all_gather_into_tensor(ids_all, ids[:1].contiguous())
+            w_all = torch.zeros((T, K), dtype=torch.float32, device=dev); dist.all_gather_into_tensor(w_all, wts[:1].contiguous())
+        else:
+            xs_all, ids_all, w_all = x_own, ids[:1], wts[:1]
+        ids_np, w_np, xs_bits = ids_all.cpu().numpy(), w_all.cpu().numpy(), bits(xs_all)
+        # routing of the own token vs the float64 router restatement
+        Wr, br = Lr["keep"][6].cpu().numpy(), Lr["keep"][7].cpu().numpy()
+        oidx, _, margin, _ = gate_oracle.route(bf16_to_f32(xs_bits[rank:rank + 1]), Wr, br, top_k=K, n_group=N_GROUP, topk_group=TOPK_GROUP,
+                                               routed_scaling_factor=ROUTED_SCALE, dtype=np.float64)
+        ids_equal = bool(np.array_equal(np.sort(ids_np[rank]), np.sort(oidx[0])))
+        # routed experts: the oracle over the experts THIS rank owns, for all `world` tokens, in fp32; ranks are summed
+        own = (ids_np >= rank * E_local) & (ids_np < (rank + 1) * E_local)
+        sel = sorted(set(ids_np[own].tolist()))
+        remap = {e: i for i, e in enumerate(sel)}
+        loc = np.vectorize(lambda e: remap.get(int(e), -1))(ids_np).astype(np.int64)
+        if sel:
+            g_np = torch.cat([gate_t[(e - rank * E_local) * gbytes:(e - rank * E_local + 1) * gbytes] for e in sel]).cpu().numpy()
+            u_np = torch.cat([up_t[(e - rank * E_local) * gbytes:(e - rank * E_local + 1) * gbytes] for e in sel]).cpu().numpy()
+            d_np = torch.cat([raw0["down"][(e - rank * E_local) * dbytes:(e - rank * E_local + 1) * dbytes] for e in sel]).cpu().numpy()
+            routed = orc.moe_forward(len(sel), H, I, g_np, u_np, d_np, Q4_K, Q4_K, Q6_K, F32, loc, w_np, bf16_to_f32(xs_bits))
+        else:
+            routed = np.zeros((T, H), np.float32)
+        routed_t = torch.from_numpy(routed).to(dev)
+        if world > 1:
+            dist.all_reduce(routed_t)
+        shared = orc.mlp_forward(H, I, raw0["sg"], raw0["su"], raw0["sd"], Q4_K, Q4_K, Q6_K, BF16, xs_bits[rank:rank + 1])
+        want = (routed_t[rank:rank + 1].to(torch.bfloat16).cpu() + torch.from_numpy(shared.view(np.int16)).view(torch.bfloat16)).float().numpy()
+        got = y.float().cpu().numpy()
+        max_rel = float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+        stat = torch.tensor([max_rel, 0.0 if ids_equal else 1.0, float(margin[0] < 1e-5)], device=dev)
+        if world > 1:
+            dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+        parity = {"layer": 0, "checked_against": "oracle/ktoracle.c (routed experts, fp32 partial sums summed over ranks) + gate_oracle (float64 router)",
+                  "max_rel": float(stat[0]), "ids_equal": bool(stat[1] == 0.0), "knife_edge_token": bool(stat[2] > 0), "tolerance": "2^-7 (1 bf16 ulp of the two rounded terms) + 1e-3"}
+        if ep is not None:
+            parity["ep_wait_timeouts"] = int(ep_flags[2 * T + 1].item())
+    except Exception as e:  # pragma: no cover  (the checker must never take the bench down)
+        parity = {"error": f"{type(e).__name__}: {e}"}
+    raw0 = None
+    torch.cuda.empty_cache()
 
     # warm (allocations inside the library happen here, before capture)
     n0 = native.launch_count()
@@ -407,11 +473,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    rng = np.random.default_rng(1234 + rank)
-
-    def fresh_input():
-        x_host.copy_(torch.from_numpy((rng.standard_normal((1, H)) / 100).astype(np.float32)).to(torch.bfloat16))
-
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
         fresh_input(); x_own.copy_(x_host, non_blocking=True); run_step()
@@ -446,13 +507,15 @@ def main():
         d2h = N_MOE_LAYERS * H * 2
         e2e_api = "per layer: ktb200_moe_block_forward_host(pinned host token -> pinned host output): H2D, one launch, D2H, sync"
     else:
+        # same shape as N=1: every layer is one plugin call with HOST buffers (token up, layer, output back, synchronise)
         def e2e_step():
-            x_own.copy_(x_host, non_blocking=True)
-            run_step()
-            y_host.copy_(y, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        h2d, d2h = H * 2, H * 4
-        e2e_api = "pinned host token -> H2D -> 58-layer EP step -> D2H of the step's result"
+            for l in range(N_MOE_LAYERS):
+                x_own.copy_(x_host, non_blocking=True)
+                layer_device(l)
+                y_host.copy_(y, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        h2d, d2h = N_MOE_LAYERS * H * 2, N_MOE_LAYERS * H * 2
+        e2e_api = "per layer and rank: pinned host token -> H2D -> expert-parallel layer (one launch, NVLink exchange inside) -> D2H -> sync"
     for _ in range(3):
         fresh_input(); e2e_step()
     barrier()
@@ -491,13 +554,12 @@ def main():
             roof_block = {"kernel": "moe_block_kernel<BulkQ6K4T> (router GEMV + top-k + gate/up + SiLU*mul + down + combine, 1 launch/layer)",
                           "bound": "hbm", "achieved": bytes_b / (ms_b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": bytes_b / (ms_b * 1e-3) / 1e9 / peak, "peak_source": how,
-                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01g_kernels.md)
-                          "traffic": 266_550_272 + 6_998_784,
+                          "traffic": committed_traffic("moe_block_kernel"),
                           "bytes_per_launch": bytes_b, "ms_per_launch": ms_b}
-    if rank == 0:
+    if rank == 0 and hid == BF16:
         gu, dn = [], []
         a, b = C.c_float(), C.c_float()
-        xin = x_own if world == 1 else x_all_f32
+        xin = x_own
         for rep in range(2):
             for l in range(N_MOE_LAYERS):
                 Lr = layers[l % L]
@@ -539,6 +601,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
                 "gpu_launches": launches_per_step * args.steps, "cuda_graph": graph is not None,
                 "roofline": roof_block if roof_block else roof, "roofline_gate_up": roof, "roofline_down": roof_down, "cpu_baseline": cpu_baseline,
+                "parity_check": parity,
                 "step_hbm": {"algorithmic_bytes_per_token_per_gpu": step_bytes, "achieved_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac_of_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / measured_peak_gbs()[0]}}
         print(json.dumps(line), flush=True)

@@ -150,11 +150,13 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
     {
         constexpr int kPieces = kHG * (kDK / 8), kIter = kPieces / kMlaThreads;   // 4608 = 24 x 192
         static_assert(kPieces % kMlaThreads == 0, "Q pieces");
+        constexpr int kB = 12;
+        static_assert(kIter % kB == 0, "Q batches");
 #pragma unroll
-        for (int i0 = 0; i0 < kIter; i0 += 8) {
-            uint4 v[8];
+        for (int i0 = 0; i0 < kIter; i0 += kB) {
+            uint4 v[kB];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {   // 8 independent 16-byte loads in flight per thread
+            for (int u = 0; u < kB; u++) {   // 12 independent 16-byte loads in flight per thread
                 const int i = tid + (i0 + u) * kMlaThreads, r = i / (kDK / 8), j = i - r * (kDK / 8);
                 v[u] = make_uint4(0, 0, 0, 0);
                 if (h0 + r < p.num_heads) {
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < kB; u++) {
                 const int i = tid + (i0 + u) * kMlaThreads, r = i / (kDK / 8), j = i - r * (kDK / 8);
                 const int c = j >> 3, jj = j & 7;
                 *reinterpret_cast<uint4*>(smem + kOffQ + c * kQRegion + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
@@ -199,8 +201,8 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ================================================================ tensor-core issuer
-        if (lane == 0) {
+        // ================================================================ tensor-core issuer (converged warp, see mma_f16)
+        {
             constexpr uint32_t idesc_qk = instr_desc(1, 1, 1, 0, 0, kHG, kLT);    // f32 += bf16 . bf16, A K-major, B K-major, 64 x 32
             constexpr uint32_t idesc_pv = instr_desc(1, 1, 1, 1, 0, 128, kHG);    // A MN-major (V^T from the [token][latent] tile), 128 x 64
             auto issue_qk = [&](int j) {
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
                                 smem_desc(pb + k * 256, 128, 512, kLayoutNone), idesc_pv, (j | k) != 0);
                 mma_commit(smem_u32(&misc.k_empty[s]));
                 mma_commit(smem_u32(&misc.p_free[j & 1]));
-                if (p.debug && split == 0 && hg == 0 && b == 0 && j < 60) reinterpret_cast<unsigned long long*>(p.debug + 2048)[128 + j] = gtime();
+                if (p.debug && lane == 0 && split == 0 && hg == 0 && b == 0 && j < 60) reinterpret_cast<unsigned long long*>(p.debug + 2048)[128 + j] = gtime();
             }
         }
         __syncwarp();
@@ -396,30 +398,50 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
 // out[b][h][:] = sum_s w_s * o_part[b][s][h][:],  w_s = 2^(lse_s - max) / sum ; lse (natural log) optional
 __global__ void __launch_bounds__(128) mla_merge_kernel(const float* o_part, const float* lse_part, int num_splits, int num_heads,
                                                         __nv_bfloat16* out, float* lse_out) {
+    __shared__ float ws[128];
+    __shared__ float red[8];
     const int bh = blockIdx.x, b = bh / num_heads, h = bh % num_heads;
-    float mx = -INFINITY;
-    for (int s = 0; s < num_splits; s++) mx = fmaxf(mx, lse_part[((long)b * num_splits + s) * num_heads + h]);
-    const int c = threadIdx.x * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float my = tid < num_splits ? lse_part[((long)b * num_splits + tid) * num_heads + h] : -INFINITY;   // num_splits <= 128
+    float mx = my;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    const int c = tid * 4;
     __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(out + ((long)b * num_heads + h) * kDV + c);
     if (mx == -INFINITY) {   // kv_len == 0 (e.g. a padded CUDA-graph batch slot): zeros, lse = -inf
         o2[0] = __floats2bfloat162_rn(0.f, 0.f);
         o2[1] = __floats2bfloat162_rn(0.f, 0.f);
-        if (lse_out && threadIdx.x == 0) lse_out[(long)b * num_heads + h] = -INFINITY;
+        if (lse_out && tid == 0) lse_out[(long)b * num_heads + h] = -INFINITY;
         return;
     }
-    float den = 0.f;
-    for (int s = 0; s < num_splits; s++) den += exp2f(lse_part[((long)b * num_splits + s) * num_heads + h] - mx);
+    const float e = tid < num_splits ? exp2f(my - mx) : 0.f;
+    float den = warp_sum(e);
+    if (lane == 0) red[4 + warp] = den;
+    __syncthreads();
+    den = (red[4] + red[5]) + (red[6] + red[7]);
+    ws[tid] = e / den;
+    __syncthreads();
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int s = 0; s < num_splits; s++) {
-        const float w = exp2f(lse_part[((long)b * num_splits + s) * num_heads + h] - mx) / den;
-        if (w != 0.f) {
-            const float4 v = *reinterpret_cast<const float4*>(o_part + (((long)b * num_splits + s) * num_heads + h) * kDV + c);
-            acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
-        }
+    const float* src = o_part + ((long)b * num_splits * num_heads + h) * kDV + c;
+    const long sstride = (long)num_heads * kDV;
+    for (int s0 = 0; s0 < num_splits; s0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (s0 + u < num_splits) v[u] = __ldcs(reinterpret_cast<const float4*>(src + (s0 + u) * sstride));
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (s0 + u < num_splits) {
+                const float w = ws[s0 + u];
+                acc.x += w * v[u].x; acc.y += w * v[u].y; acc.z += w * v[u].z; acc.w += w * v[u].w;
+            }
     }
     o2[0] = __floats2bfloat162_rn(acc.x, acc.y);
     o2[1] = __floats2bfloat162_rn(acc.z, acc.w);
-    if (lse_out && threadIdx.x == 0) lse_out[(long)b * num_heads + h] = (mx + log2f(den)) * 0.6931471805599453f;
+    if (lse_out && tid == 0) lse_out[(long)b * num_heads + h] = (mx + log2f(den)) * 0.6931471805599453f;
 }
 
 // StaticCache.update (archive/ktransformers/models/custom_cache.py:147-200): one CTA per token

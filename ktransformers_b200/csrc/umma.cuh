@@ -108,13 +108,18 @@ __host__ __device__ constexpr uint32_t instr_desc(int c_fmt, int a_fmt, int b_fm
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] . B[smem]; issued by ONE thread for the whole CTA.  bf16/f16 inputs: K = 16 per instruction.
+// D[tmem] (+)= A[smem] . B[smem].  Called by ALL lanes of a converged warp with warp-uniform operands; ONE elected lane
+// issues the instruction for the whole CTA.  (Issuing from inside `if (lane == 0)` makes the compiler treat every operand
+// as per-thread: each MMA then costs ~20 SASS instructions — register -> uniform-register moves and an ELECT loop —
+// and a dependent ~100-cycle issue chain; measured in profiles/mla_trace_r02.txt.)  bf16/f16 inputs: K = 16 per instruction.
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 r;\n"
+        "elect.sync r|q, 0xffffffff;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -123,16 +128,26 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 r;\n"
+        "elect.sync r|q, 0xffffffff;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// makes `bar` complete (one arrival) when all tcgen05 operations issued so far by this thread have finished
+// makes `bar` complete (one arrival) when all tcgen05 operations issued so far have finished; called by a converged
+// warp like mma_f16 (the same elected lane issues it)
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .b32 r;\n"
+        "elect.sync r|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(bar)
+        : "memory");
 }
 
 }  // namespace umma

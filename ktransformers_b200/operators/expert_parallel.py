@@ -27,6 +27,48 @@ def shard_range(n_experts: int, rank: int, world: int) -> tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+class PeerExchange:
+    """Peer-mapped buffers of the ONE-launch expert-parallel MoE block (`ktb200_moe_ep_block_forward`, include/ktb200.h):
+    one symmetric allocation per rank (torch.distributed._symmetric_memory) holding the message rows {x, ids, weights},
+    the fp32 partial rows and the flag block.  One instance serves every MoE layer of a model: layers run one after the
+    other on the same stream and the epochs live in the flag block.  `KDeepseekV3MoE.forward` takes this path when its
+    experts are sharded (expert_parallel_size > 1) and `module.ep_exchange` is set (see `attach_expert_parallel`)."""
+
+    def __init__(self, hidden_size: int, hidden_type: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from .. import native
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lib = native.lib()
+        msg_b = self.world * lib.ktb200_ep_msg_bytes(hidden_size, hidden_type)
+        part_b, flag_b = self.world * hidden_size * 4, 4 * (2 * self.world + 2)
+        o_part = (msg_b + 255) // 256 * 256
+        o_flag = o_part + (part_b + 255) // 256 * 256
+        self.buf = symm_mem.empty(o_flag + (flag_b + 255) // 256 * 256, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        hdl = symm_mem.rendezvous(self.buf, self.group)
+        base = [int(p) for p in hdl.buffer_ptrs]
+        self.comm = native.EpComm.make(self.rank, self.world, hidden_size, hidden_type, base, [b + o_part for b in base],
+                                       [b + o_flag for b in base])
+        self.flags = self.buf[o_flag:o_flag + flag_b].view(torch.int32)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def timed_out(self) -> bool:
+        """True when a peer wait inside a kernel gave up (a rank did not take part in a layer)."""
+        return bool(self.flags[2 * self.world + 1].item())
+
+
+def attach_expert_parallel(model: torch.nn.Module, hidden_size: int, hidden_type: int, device, group=None) -> PeerExchange:
+    """Give every injected MoE block of `model` whose experts are sharded the same PeerExchange."""
+    ex = PeerExchange(hidden_size, hidden_type, device, group)
+    for m in model.modules():
+        if hasattr(m, "_block_handles"):
+            m.ep_exchange = ex
+    return ex
+
+
 class ExpertParallelCombine:
     """local_forward(x_all[T,H] (fp32), ids_all[T,k], w_all[T,k], out_partial[T,H] fp32) computes this rank's share."""
 

@@ -118,7 +118,9 @@ class KExpertsB200(KExpertsBase):
             a = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a)).view(np.uint8).reshape(-1))
             a = a.reshape(-1)
             nb = a.numel() // E
-            return a[lo * nb:(lo + per) * nb].to(device).contiguous()
+            sl = a[lo * nb:(lo + per) * nb]
+            # load_weights re-tiles Q6_K bytes IN PLACE: never hand it memory the caller still owns
+            return sl.clone() if sl.device == torch.device(device) else sl.to(device).contiguous()
 
         self.gate, self.up, self.down = upload(w["gate"]), upload(w["up"]), upload(w["down"])
         dev = torch.device(device)
@@ -329,7 +331,9 @@ class _KDeepseekMoEMixin:
     def _block_handles(self, x):
         """(gate_cfg, moe_handle, mlp_handle_or_None) when the single-launch path applies, else None."""
         gate, gen = getattr(self, "gate", None), getattr(getattr(self, "experts", None), "generate_experts", None)
-        if not (isinstance(gen, KExpertsB200) and gen.handle is not None and gen.ep_size == 1 and x.is_cuda):
+        if not (isinstance(gen, KExpertsB200) and gen.handle is not None and x.is_cuda):
+            return None
+        if gen.ep_size > 1 and getattr(self, "ep_exchange", None) is None:
             return None
         if getattr(self.experts, "mode", None) != InferenceState.GENERATE or getattr(gate, "_w", None) is None:
             return None
@@ -373,7 +377,22 @@ class _KDeepseekMoEMixin:
         orig_shape = hidden_states.shape
         sequence_length = orig_shape[1]
         n_tok = hidden_states.numel() // orig_shape[-1]
-        if n_tok <= self.BLOCK_MAX_TOKENS:
+        gen0 = getattr(getattr(self, "experts", None), "generate_experts", None)
+        if getattr(gen0, "ep_size", 1) > 1 and n_tok == 1:
+            # expert-parallel decode, one token per GPU: router, NVLink exchange, owned experts and combine in ONE launch
+            hs = self._block_handles(hidden_states)
+            if hs is not None:
+                cfg, moe, mlp = hs
+                x = hidden_states.reshape(1, orig_shape[-1]).contiguous()
+                capturing = torch.cuda.is_current_stream_capturing()
+                y = KExpertsB200.output_gpu_map[gen0.out_device][:1] if capturing else torch.empty_like(x)
+                idx = torch.empty((1, cfg.top_k), dtype=torch.int64, device=x.device)
+                wt = torch.empty((1, cfg.top_k), dtype=torch.float32, device=x.device)
+                native.check(native.lib().ktb200_moe_ep_block_forward(C.byref(cfg), moe, mlp, C.byref(self.ep_exchange.comm), x.data_ptr(),
+                                                                      y.data_ptr(), idx.data_ptr(), wt.data_ptr(), 7, _stream(x.device)))
+                self.last_topk = (idx, wt)
+                return y.view(*orig_shape)
+        if n_tok <= self.BLOCK_MAX_TOKENS and getattr(gen0, "ep_size", 1) == 1:
             hs = self._block_handles(hidden_states)
             if hs is not None:
                 cfg, moe, mlp = hs
