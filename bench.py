@@ -70,7 +70,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -225,6 +225,7 @@ def workload_config(args, world):
             "block_launch": ("plain grid + programmatic dependent launch" if os.environ.get("KTB200_BLK_COOP", "1") == "0"
                              else "cooperative + programmatic dependent launch"),
             "l2": "inputs larger than L2: each layer set is 7.4 GB and is revisited after >= 2 other sets",
+            "next_layer_prefetch": os.environ.get("KTB200_BENCH_PREFETCH", "0") != "0" and world == 1,
             "note": "layer inputs are not chained (random-init weights overflow bf16 within a few layers); every layer routes and computes on the step's hidden state with its own router/expert weights"}
 
 
@@ -328,6 +329,14 @@ def main():
         br = torch.randn((E,), device=dev, generator=g, dtype=torch.float32)
         gcfg = native.GateConfig(E, H, K, N_GROUP, TOPK_GROUP, 0, 0, 1, ROUTED_SCALE, Wr.data_ptr(), br.data_ptr(), BF16)
         layers.append(dict(moe=h, mlp=mh, gcfg=gcfg, keep=(gate, up, down, sg, su, sd, Wr, br)))
+    if world == 1 and os.environ.get("KTB200_BENCH_PREFETCH", "0") != "0":
+        # chain the layers: while layer i streams its down projection it pulls layer i+1's router rows and shared-expert
+        # gate/up rows into L2 (ktb200_moe_block_prefetch_hint) — the same bytes, requested earlier
+        for i, Lr in enumerate(layers):
+            nxt = layers[(i + 1) % L]["keep"]
+            ptrs = (C.c_void_p * 3)(nxt[6].data_ptr(), nxt[3].data_ptr(), nxt[4].data_ptr())
+            sizes = (C.c_size_t * 3)(nxt[6].numel() * 4, nxt[3].numel(), nxt[4].numel())
+            native.check(lib.ktb200_moe_block_prefetch_hint(Lr["moe"], ptrs, sizes, 3))
     torch.cuda.synchronize()
 
     # ---- static buffers ---------------------------------------------------------------------------------------
@@ -474,10 +483,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # sampling spans the warm-up steps too: the same work, enough samples
     for _ in range(max(3, args.warmup)):
         fresh_input(); x_own.copy_(x_host, non_blocking=True); run_step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     fresh_input(); x_own.copy_(x_host); barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

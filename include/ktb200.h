@@ -226,6 +226,10 @@ int ktb200_moe_forward_ep(ktb200_moe* moe, ktb200_mlp* shared, int qlen, int k, 
 int ktb200_moe_block_forward(const ktb200_gate_config* gate, ktb200_moe* moe, ktb200_mlp* shared, int qlen,
                              const void* input_dev, void* output_dev, int64_t* idx_dev, float* w_dev,
                              const int* bsz_tensor_dev, void* stream);
+/* Optional chaining hint for back-to-back layers: during this handle's down-projection phase the block kernel also pulls up
+ * to 3 byte ranges (16-byte aligned) into L2 — pass what the NEXT layer's launch reads first (its router weight, its shared
+ * expert's gate and up tensors), so that the next launch's latency-bound first microseconds hit L2.  n = 0 clears it. */
+int ktb200_moe_block_prefetch_hint(ktb200_moe* moe, const void* const* ptrs, const size_t* bytes, int n);
 /* HOST-buffer form (pinned host tensors in / out like the reference's CPU operator, experts.py:293-318): copies the
  * tokens up, runs the block, copies output (+ routing when idx_host / w_host are non-NULL) back, synchronises. */
 int ktb200_moe_block_forward_host(const ktb200_gate_config* gate, ktb200_moe* moe, ktb200_mlp* shared, int qlen,

@@ -44,6 +44,8 @@ struct ktb200_moe {
     float* blk_partial;
     unsigned* blk_sync;
     unsigned blk_flip;
+    const void* pf[3];       // ktb200_moe_block_prefetch_hint: ranges the block kernel pulls into L2 during its down phase
+    size_t pf_bytes[3];
 };
 
 struct DeviceGuard {

@@ -473,6 +473,7 @@ int ktb200_moe_create(const ktb200_moe_config* c, int device, ktb200_moe** out) 
     m->down_layout = LAYOUT_RAW;
     m->inter = nullptr; m->ids_d = nullptr; m->w_d = nullptr; m->in_d = nullptr; m->out_d = nullptr;
     m->blk_partial = nullptr; m->blk_sync = nullptr; m->blk_flip = 0;
+    for (int r = 0; r < 3; r++) { m->pf[r] = nullptr; m->pf_bytes[r] = 0; }
     const size_t slots = (size_t)c->group_max_len * c->routed_expert_num;
     const size_t hid = (size_t)c->group_max_len * c->hidden_size * type_size(c->hidden_type);
     // +1 slot per token: the optionally fused shared expert (ktb200_moe_forward_shared)

@@ -49,6 +49,8 @@ struct BlockParams {
     int ring_bytes;                      // per-warp ring
     int prime_u, prime_d;                // rows / tiles every warp requests BEFORE the router's / the second grid barrier
     unsigned long long* trace;           // debug: [grid][16] globaltimer stamps of the phase boundaries (null: off)
+    const uint8_t* pf[3];                // ranges to pull into L2 while the down phase streams (the NEXT layer's router rows and
+    unsigned pf_bytes[3];                // shared-expert gate/up rows: ktb200_moe_block_prefetch_hint); null: none
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -478,6 +480,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1) moe_block_kernel(const BlockPara
         blk_quantize_a<DownFmt::kBs>(t);
 #pragma unroll
         for (int s = 0; s < SD; s++) issue_d();
+        if (t == Teff - 1 && warp == W - 1) {
+            // the next layer's first bytes (ktb200_moe_block_prefetch_hint) -> L2, this CTA's 1/grid slice of each range in
+            // 4 KB pieces: no registers or shared memory held, the down stream keeps its ring
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                if (p.pf[r]) {
+                    const unsigned per = ((p.pf_bytes[r] / gridDim.x) + 15u) & ~15u;
+                    const unsigned lo = per * blockIdx.x, hi = min(p.pf_bytes[r], lo + per);
+                    for (unsigned o = lo + lane * 4096u; o < hi; o += 32u * 4096u) prefetch_l2_bulk(p.pf[r] + o, min(4096u, hi - o) & ~15u);
+                }
+            }
+        }
         __syncthreads();
         block_stamp(p, 7);
 
@@ -958,6 +972,7 @@ __global__ void __launch_bounds__(kBlockWarpsLo * 32, 1) moe_ep_block_kernel(con
             if (has_shared) v += round_hidden(__ldcg(pp.x.shared_out + row), p.hidden_type);
             store_hidden(p.out, row, p.hidden_type, v);
         }
+        block_stamp(p, 10);
     }
 
     __syncthreads();
@@ -1053,6 +1068,7 @@ extern "C" int ktb200_moe_block_forward(const ktb200_gate_config* gc, ktb200_moe
     p.n_local = c.expert_num; p.id_offset = c.expert_id_offset;
     p.H = c.hidden_size; p.I = c.intermediate_size; p.k = k; p.hidden_type = c.hidden_type; p.use_silu = c.use_silu;
     p.inter = m->inter; p.out = output; p.sync = m->blk_sync + 2 * (m->blk_flip++ & 1u); p.trace = g_btrace;
+    for (int r = 0; r < 3; r++) { p.pf[r] = (const uint8_t*)m->pf[r]; p.pf_bytes[r] = (unsigned)m->pf_bytes[r]; }
     static const int prime_u = [] { const char* e = getenv("KTB200_BLK_PRIME_U"); return e ? atoi(e) : 3; }();
     static const int prime_d = [] { const char* e = getenv("KTB200_BLK_PRIME_D"); return e ? atoi(e) : 2; }();
     p.prime_u = prime_u; p.prime_d = prime_d;
@@ -1219,6 +1235,20 @@ extern "C" int ktb200_moe_ep_block_forward(const ktb200_gate_config* gc, ktb200_
     }
     if (le != cudaSuccess) { set_error("ep_block launch failed: %s", cudaGetErrorString(le)); return KTB200_ECUDA; }
     count_launch(1);
+    return KTB200_OK;
+}
+
+// Prefetch hint: while this handle's block kernel streams its down projection, pull up to three byte ranges into L2 — the
+// caller passes what the NEXT layer's launch reads first (its router weight, its shared expert's gate / up tensors).
+// Measured at DeepSeek-V3 shapes (profiles/r02_block_experiments.md): no gain while the down stream already saturates HBM
+// (the prefetch competes with it), so bench.py leaves it off; kept for callers whose next layer is not back to back.
+extern "C" int ktb200_moe_block_prefetch_hint(ktb200_moe* m, const void* const* ptrs, const size_t* bytes, int n) {
+    if (!m || n < 0 || n > 3 || (n && (!ptrs || !bytes))) { set_error("prefetch_hint: up to 3 ranges"); return KTB200_EINVAL; }
+    for (int r = 0; r < 3; r++) {
+        m->pf[r] = r < n ? ptrs[r] : nullptr;
+        m->pf_bytes[r] = r < n ? (bytes[r] > 0xfffffff0u ? 0xfffffff0u : bytes[r]) : 0;
+        if (r < n && ((uintptr_t)ptrs[r] & 15)) { set_error("prefetch_hint: ranges must be 16-byte aligned"); m->pf[r] = nullptr; return KTB200_EINVAL; }
+    }
     return KTB200_OK;
 }
 

@@ -81,6 +81,7 @@ SYMBOLS = {
     "ktb200_moe_forward_ep": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "ktb200_ep_all_gather_tokens": (_I, [_VP, _VP, _VP, _VP]),
     "ktb200_ep_reduce_own_token": (_I, [_VP, _VP, _VP, _VP]),
+    "ktb200_moe_block_prefetch_hint": (_I, [_VP, _VP, _VP, _I]),
     "ktb200_ep_msg_bytes": (_L, [_I, _I]),
     "ktb200_moe_ep_block_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "ktb200_debug_block_trace": (None, [_VP]),

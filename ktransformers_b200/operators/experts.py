@@ -431,6 +431,25 @@ class _KDeepseekMoEMixin:
         return self.experts(x, topk_ids, topk_weight)
 
 
+def chain_moe_prefetch(model: "torch.nn.Module") -> int:
+    """Link consecutive injected MoE blocks: while block i streams its down projection, its kernel pulls block i+1's router
+    weight and shared-expert gate / up tensors into L2 (ktb200_moe_block_prefetch_hint).  Returns the number of links.
+    Call after `optimize_and_load_gguf` / `load()`; a no-op for blocks that do not take the single-launch path."""
+    blocks = [m for m in model.modules() if isinstance(m, _KDeepseekMoEMixin)]
+    n = 0
+    for cur, nxt in zip(blocks, blocks[1:]):
+        gen = getattr(getattr(cur, "experts", None), "generate_experts", None)
+        gate = getattr(nxt, "gate", None)
+        if not (isinstance(gen, KExpertsB200) and gen.handle is not None and getattr(gate, "_w", None) is not None):
+            continue
+        bufs = [gate._w] + list(getattr(nxt, "_ktb_mlp_raw", [])[:2])
+        ptrs = (C.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+        sizes = (C.c_size_t * len(bufs))(*[b.numel() * b.element_size() for b in bufs])
+        native.check(native.lib().ktb200_moe_block_prefetch_hint(gen.handle, ptrs, sizes, len(bufs)))
+        n += 1
+    return n
+
+
 def _moe_bases():
     from ..models.modeling_deepseek_v3 import DeepseekV3MoE
     from ..models.modeling_deepseek import DeepseekV2MoE
