@@ -138,3 +138,46 @@ def test_kt_moe_wrapper_serves_a_layer_from_gguf(tmp_path):
     assert y.dtype == torch.bfloat16 and tuple(y.shape) == (n_tok, H)
     assert (y.float() - ref).abs().max() <= 0.05 * ref.abs().max()
     assert torch.equal(w.forward(x, ids, wt, None), y)                        # forward == submit + sync
+
+
+def test_pybind_extension_runs_the_reference_submit_sync_sequence(oracle):
+    """The compiled pybind module driven the way kt-kernel/python/experts_base.py drives kt_kernel_ext:
+    CPUInfer.submit(moe.load_weights_task()); sync(); per step submit_with_cuda_stream(stream, moe.forward_task(qlen_ptr, k,
+    ids, w, in, out)); sync_with_cuda_stream(stream) — output vs the CPU oracle."""
+    import importlib
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ktransformers_b200"))
+    ext = importlib.import_module("kt_kernel_ext_b200")
+    from ktransformers_b200.util.synth import synth_blocks
+    from oracle.bindings import BF16, Q4_K, Q6_K, f32_to_bf16_bits
+    E, k, H, I = 8, 4, 4096, 512
+    gate, up, down = (synth_blocks(Q4_K, E * I * H, "cuda", 1), synth_blocks(Q4_K, E * I * H, "cuda", 2), synth_blocks(Q6_K, E * H * I, "cuda", 3))
+    g_np, u_np, d_np = gate.cpu().numpy(), up.cpu().numpy(), down.cpu().numpy()
+    cfg = ext.moe.MOEConfig(E, k, H, I)
+    cfg.gate_proj, cfg.up_proj, cfg.down_proj = gate.data_ptr(), up.data_ptr(), down.data_ptr()
+    cfg.gate_type, cfg.up_type, cfg.down_type, cfg.hidden_type, cfg.max_len = Q4_K, Q4_K, Q6_K, BF16, 16
+    moe = ext.moe.B200_MOE(cfg)
+    cpuinfer = ext.CPUInfer(1)
+    with pytest.raises(RuntimeError, match="Not Loaded"):
+        moe.forward(torch.tensor([1], dtype=torch.int32).data_ptr(), k, 0, 0, 0, 0, False)
+    cpuinfer.submit(moe.load_weights_task())
+    cpuinfer.sync()
+    rng = np.random.default_rng(0)
+    qlen = 3
+    x = f32_to_bf16_bits((rng.standard_normal((qlen, H)) / 100).astype(np.float32))
+    ids = np.stack([rng.permutation(E)[:k] for _ in range(qlen)]).astype(np.int64)
+    w = rng.random((qlen, k)).astype(np.float32)
+    x_d = torch.from_numpy(x.view(np.int16)).view(torch.bfloat16).cuda()
+    ids_d, w_d = torch.from_numpy(ids).cuda(), torch.from_numpy(w).cuda()
+    out_d = torch.zeros((qlen, H), dtype=torch.bfloat16, device="cuda")
+    bsz = torch.tensor([qlen], dtype=torch.int32).pin_memory()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    cpuinfer.submit_with_cuda_stream(side.cuda_stream, moe.forward_task(bsz.data_ptr(), k, ids_d.data_ptr(), w_d.data_ptr(), x_d.data_ptr(), out_d.data_ptr()))
+    cpuinfer.sync_with_cuda_stream(side.cuda_stream)
+    side.synchronize()
+    want = oracle.moe_forward(E, H, I, g_np, u_np, d_np, Q4_K, Q4_K, Q6_K, BF16, ids, w, x)
+    got = out_d.cpu().view(torch.int16).numpy().view(np.uint16)
+    from oracle.bindings import bf16_to_f32
+    a, b = bf16_to_f32(got), bf16_to_f32(want)
+    assert (np.abs(a - b) <= 2.0 ** -7 * np.maximum(np.abs(a), np.abs(b)) + 1e-3 * np.abs(b).max()).all()

@@ -278,3 +278,27 @@ def test_ep_comm_argument_checks_need_no_gpu():
             native.check(lib.ktb200_ep_reduce_own_token(C.byref(bad), 16, None, None))
     with pytest.raises(ValueError):
         native.check(lib.ktb200_ep_all_gather_tokens(C.byref(ok), None, None, None))       # null token
+
+
+def test_pybind_module_exposes_the_reference_extension_surface():
+    """kt_kernel_ext_b200 (csrc/ext_bindings.cpp) — the compiled pybind boundary: names and call shapes of
+    kt-kernel/ext_bindings.cpp (MOEConfig :746-831, bind_moe_module :447-471, CPUInfer :554-565)."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "ktransformers_b200"))
+    ext = importlib.import_module("kt_kernel_ext_b200")
+    assert "sm_100a" in ext.version()
+    cfg = ext.moe.MOEConfig(8, 2, 512, 256)
+    for f in ("expert_num", "num_experts_per_tok", "hidden_size", "intermediate_size", "layer_idx", "max_len", "group_min_len",
+              "group_max_len", "gate_type", "up_type", "down_type", "hidden_type", "gate_proj", "up_proj", "down_proj",
+              "physical_to_logical_map", "gpu_experts_mask", "pool"):
+        assert hasattr(cfg, f), f
+    cfg.gate_proj = 4096
+    assert cfg.gate_proj == 4096 and cfg.expert_num == 8 and cfg.num_experts_per_tok == 2
+    assert ext.moe.MOEConfig(8, 2, 512, 256, 0).gpu_experts_mask == 0
+    for meth in ("warm_up_task", "load_weights_task", "forward_task", "warm_up", "load_weights", "forward"):
+        assert hasattr(ext.moe.B200_MOE, meth), meth
+    for meth in ("submit", "sync", "submit_with_cuda_stream", "sync_with_cuda_stream"):
+        assert hasattr(ext.CPUInfer, meth), meth
+    with pytest.raises(RuntimeError, match="null weight pointer"):       # C++ exception -> Python, like the reference
+        ext.moe.B200_MOE(ext.moe.MOEConfig(8, 2, 512, 256))
