@@ -229,6 +229,141 @@ def workload_config(args, world):
             "note": "layer inputs are not chained (random-init weights overflow bf16 within a few layers); every layer routes and computes on the step's hidden state with its own router/expert weights"}
 
 
+
+# ----------------------------------------------------------------------------------------------- whole decode step
+def full_decode_leg(args, lib, native, dev, local_rank, layers, L, moe_layer_call, world):
+    """The WHOLE DeepSeek-V3 decode step (BASELINE config 2: "... decode bs=1 ... MLA path"), one CUDA graph:
+    61 x [input RMSNorm -> q_a / kv_a (Q4_K, ktb200_linear) -> q_a norm -> q_b -> kv norm + RoPE + paged cache write
+    (ktb200_mla_prep) -> W_UK absorb (bmm) -> MLA paged decode over `ctx` cached tokens (ktb200_mla_decode, tcgen05) -> W_UV
+    (bmm) -> o_proj -> residual + post RMSNorm -> dense MLP (3 layers) | MoE block (58 layers)] -> final norm -> lm_head.
+    Weights synthetic at the real shapes and all resident and distinct except the MoE sets (the resident `layers`)."""
+    import ctypes as C
+
+    import torch
+
+    from ktransformers_b200.util.synth import synth_blocks
+    ctx = args.ctx
+    NL, NH, QL, KVL, ROPE, NOPE, VD, DI, VOCAB = 61, 128, 1536, 512, 64, 128, 128, 18432, 129280
+    PAGE = 64
+    S = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    g = torch.Generator(device=dev); g.manual_seed(4242)
+    bf = torch.bfloat16
+
+    def linear(inf, outf, t, seed):
+        w = synth_blocks(t, outf * inf, dev, seed)
+        h = C.c_void_p()
+        native.check(lib.ktb200_linear_create(inf, outf, w.data_ptr(), t, BF16, 8, local_rank, C.byref(h)))
+        native.check(lib.ktb200_linear_load_weights(h, S()))
+        return h, w
+
+    def normw(n):
+        return (1.0 + 0.1 * torch.randn(n, device=dev, generator=g)).to(bf)
+
+    pages = (ctx + PAGE) // PAGE + 1
+    att = []
+    for l in range(NL):
+        d = dict(q_a=linear(H, QL, Q4_K, 9000 + 10 * l), kv_a=linear(H, KVL + ROPE, Q4_K, 9001 + 10 * l), q_b=linear(QL, NH * (NOPE + ROPE), Q4_K, 9002 + 10 * l),
+                 o=linear(NH * VD, H, Q4_K, 9003 + 10 * l),
+                 w_uk=(torch.randn(NH, NOPE, KVL, device=dev, generator=g) * 0.05).to(bf), w_uv=(torch.randn(NH, VD, KVL, device=dev, generator=g) * 0.05).to(bf),
+                 ln_in=normw(H), ln_qa=normw(QL), ln_kv=normw(KVL), ln_post=normw(H),
+                 cache=(torch.randn(pages, PAGE, KVL + ROPE, device=dev, generator=g) * 0.5).to(bf))
+        att.append(d)
+    dense = []
+    for l in range(3):
+        gw, uw, dw = synth_blocks(Q4_K, DI * H, dev, 7000 + l), synth_blocks(Q4_K, DI * H, dev, 7100 + l), synth_blocks(Q6_K, H * DI, dev, 7200 + l)
+        mh = C.c_void_p()
+        native.check(lib.ktb200_mlp_create(H, DI, gw.data_ptr(), uw.data_ptr(), dw.data_ptr(), Q4_K, Q4_K, Q6_K, BF16, 8, local_rank, C.byref(mh)))
+        native.check(lib.ktb200_mlp_load_weights(mh, S()))
+        dense.append((mh, gw, uw, dw))
+    lm_head = linear(H, VOCAB, Q6_K, 6000)
+    ln_final = normw(H)
+    # static buffers
+    x = torch.zeros(1, H, dtype=bf, device=dev); hbuf = torch.zeros(1, H, dtype=bf, device=dev); y = torch.zeros(1, H, dtype=bf, device=dev)
+    qa = torch.zeros(1, QL, dtype=bf, device=dev); qan = torch.zeros(1, QL, dtype=bf, device=dev); kva = torch.zeros(1, KVL + ROPE, dtype=bf, device=dev)
+    q = torch.zeros(1, NH * (NOPE + ROPE), dtype=bf, device=dev); q_pe = torch.zeros(NH, ROPE, dtype=bf, device=dev)
+    q_abs = torch.zeros(NH, 1, KVL, dtype=bf, device=dev); lat = torch.zeros(1, NH, KVL, dtype=bf, device=dev)
+    o_in = torch.zeros(NH, 1, VD, dtype=bf, device=dev); attn_out = torch.zeros(1, H, dtype=bf, device=dev)
+    logits = torch.zeros(1, VOCAB, dtype=bf, device=dev)
+    ids = torch.zeros(1, K, dtype=torch.int64, device=dev); wts = torch.zeros(1, K, dtype=torch.float32, device=dev)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, ROPE, 2, device=dev).float() / ROPE))
+    ang = torch.cat([inv * ctx, inv * ctx])[None]
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    pidx = torch.tensor([ctx // PAGE], dtype=torch.int32, device=dev); poff = torch.tensor([ctx % PAGE], dtype=torch.int32, device=dev)
+    ptab = torch.arange(pages, dtype=torch.int32, device=dev)[None].contiguous()
+    klen = torch.tensor([ctx + 1], dtype=torch.int32, device=dev)
+    wsb = lib.ktb200_mla_workspace_bytes(1, NH, 0)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    mla = [native.MlaParams(1, NH, PAGE, pages, 0, float((NOPE + ROPE) ** -0.5), q_abs.data_ptr(), q_pe.data_ptr(), a["cache"].data_ptr(), ptab.data_ptr(),
+                            klen.data_ptr(), lat.data_ptr(), None, ws.data_ptr(), wsb, pages * PAGE) for a in att]
+    eps = 1e-6
+
+    def lin(hd, src, dst):
+        native.check(lib.ktb200_linear_forward(hd[0], 1, src.data_ptr(), dst.data_ptr(), None, None, S()))
+
+    def step(with_moe=True, with_attn=True):
+        delta = None
+        for l in range(NL):
+            a = att[l]
+            native.check(lib.ktb200_add_rmsnorm(x.data_ptr(), delta.data_ptr() if delta is not None else None, a["ln_in"].data_ptr(), eps, hbuf.data_ptr(), 1, H, S()))
+            if with_attn:
+                lin(a["q_a"], hbuf, qa); lin(a["kv_a"], hbuf, kva)
+                native.check(lib.ktb200_add_rmsnorm(qa.data_ptr(), None, a["ln_qa"].data_ptr(), eps, qan.data_ptr(), 1, QL, S()))
+                lin(a["q_b"], qan, q)
+                native.check(lib.ktb200_mla_prep(q.data_ptr(), NH, NOPE, kva.data_ptr(), a["ln_kv"].data_ptr(), eps, cos.data_ptr(), sin.data_ptr(),
+                                                 a["cache"].data_ptr(), PAGE, pidx.data_ptr(), poff.data_ptr(), q_pe.data_ptr(), 1, S()))
+                torch.bmm(q.view(NH, 1, NOPE + ROPE)[:, :, :NOPE], a["w_uk"], out=q_abs)
+                native.check(lib.ktb200_mla_decode(C.byref(mla[l]), S()))
+                torch.bmm(lat.view(NH, 1, KVL), a["w_uv"].transpose(1, 2), out=o_in)
+                lin(a["o"], o_in.view(1, NH * VD), attn_out)
+                native.check(lib.ktb200_add_rmsnorm(x.data_ptr(), attn_out.data_ptr(), a["ln_post"].data_ptr(), eps, hbuf.data_ptr(), 1, H, S()))
+            if l < 3:
+                native.check(lib.ktb200_mlp_forward(dense[l][0], 1, hbuf.data_ptr(), y.data_ptr(), 0, None, S()))
+            elif with_moe:
+                moe_layer_call(l - 3, hbuf, y, ids, wts)
+            delta = y
+        native.check(lib.ktb200_add_rmsnorm(x.data_ptr(), y.data_ptr(), ln_final.data_ptr(), eps, hbuf.data_ptr(), 1, H, S()))
+        lin(lm_head, hbuf, logits)
+
+    def timed(fn, steps):
+        n0 = native.launch_count()
+        fn(); torch.cuda.synchronize()
+        launches = native.launch_count() - n0
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        for _ in range(3):
+            x.normal_(0, 0.02); gr.replay()
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            gr.replay()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, launches
+
+    steps = max(5, min(args.steps, 20))
+    ms_full, launches = timed(lambda: step(True, True), steps)
+    ms_noattn, _ = timed(lambda: step(True, False), steps)
+    attn_bytes = NL * ((H * QL + H * (KVL + ROPE) + QL * NH * (NOPE + ROPE) + NH * VD * H) * 144 // 256 + 2 * NH * NOPE * KVL * 2 + (ctx + 1) * (KVL + ROPE) * 2)
+    moe_bytes = N_MOE_LAYERS * ((K + 1) * BYTES_PER_EXPERT + E * H * 4) // (1 if world == 1 else 1)
+    other_bytes = 3 * (2 * DI * H * 144 // 256 + H * DI * 210 // 256) + VOCAB * H * 210 // 256
+    total = attn_bytes + moe_bytes + other_bytes
+    peak = measured_peak_gbs()[0]
+    x_host = torch.zeros(1, H, dtype=bf).pin_memory(); lg_host = torch.zeros(1, VOCAB, dtype=bf).pin_memory()
+    return {"what": "whole DeepSeek-V3 decode step per GPU (61 attention + 3 dense + 58 MoE layers + lm_head), one CUDA graph", "ctx": ctx,
+            "tok_s": world * 1000.0 / ms_full, "ms_per_token": ms_full, "ms_without_attention": ms_noattn, "ms_attention_61_layers": ms_full - ms_noattn,
+            "our_launches_per_token": launches, "algorithmic_bytes_per_token": {"attention": attn_bytes, "moe": moe_bytes, "dense_mlp_lm_head": other_bytes, "total": total},
+            "achieved_GBps": total / (ms_full * 1e-3) / 1e9, "frac_of_peak": total / (ms_full * 1e-3) / 1e9 / peak,
+            "attention_GBps": attn_bytes / ((ms_full - ms_noattn) * 1e-3) / 1e9,
+            "note": "absorb products are cuBLAS bmm (plain library GEMMs, as in the reference); everything else is this repo's kernels"}
+
 # ----------------------------------------------------------------------------------------------- B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -239,6 +374,8 @@ def main():
     ap.add_argument("--resident-layers", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ctx", type=int, default=4096, help="cached tokens per sequence in the whole-step leg")
+    ap.add_argument("--no-full-step", action="store_true")
     args = ap.parse_args()
     # This process owns the GPU and decodes on ONE stream: the persistent MoE-block kernel is launched as a plain grid
     # with programmatic dependent launch (its 148 CTAs become co-resident as the previous layer's CTAs exit) instead of
@@ -587,6 +724,26 @@ def main():
         roof_down = {"kernel": "reduce_bulk_kernel<BulkQ6K4T> (down GEMV + weighted sum; separate-launch path)", "bound": "hbm", "achieved": achd, "peak": peak, "unit": "GB/s",
                      "frac": achd / peak, "bytes_per_launch": K * BYTES_DOWN_PER_EXPERT, "ms_per_launch": ms_dn}
 
+    # ---- the whole decode step (attention + dense + MoE + lm_head), every rank its own token ------------------------
+    full = None
+    if not args.no_full_step:
+        try:
+            def moe_call(i, xin, yout, ids_, wts_):
+                Lr = layers[i % L]
+                if world == 1:
+                    native.check(lib.ktb200_moe_block_forward(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], 1, xin.data_ptr(), yout.data_ptr(),
+                                                              ids_.data_ptr(), wts_.data_ptr(), None, S()))
+                elif ep is not None:
+                    native.check(lib.ktb200_moe_ep_block_forward(C.byref(Lr["gcfg"]), Lr["moe"], Lr["mlp"], C.byref(ep), xin.data_ptr(), yout.data_ptr(),
+                                                                 ids_.data_ptr(), wts_.data_ptr(), 7, S()))
+                else:
+                    raise RuntimeError("whole-step leg needs the peer-memory EP path")
+            full = full_decode_leg(args, lib, native, dev, local_rank, layers, L, moe_call, world)
+        except Exception as e:  # pragma: no cover
+            full = {"error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            dist.barrier()
+
     # ---- CPU baseline (rank 0, N=1 only): the reference's CPU MoE on this box's host cores ---------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -610,7 +767,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
                 "gpu_launches": launches_per_step * args.steps, "cuda_graph": graph is not None,
                 "roofline": roof_block if roof_block else roof, "roofline_gate_up": roof, "roofline_down": roof_down, "cpu_baseline": cpu_baseline,
-                "parity_check": parity,
+                "parity_check": parity, "full_decode": full,
                 "step_hbm": {"algorithmic_bytes_per_token_per_gpu": step_bytes, "achieved_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac_of_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / measured_peak_gbs()[0]}}
         print(json.dumps(line), flush=True)

@@ -301,6 +301,22 @@ int ktb200_mla_decode(const ktb200_mla_params* p, void* stream);
 /* Diagnostics: while non-NULL, one CTA of ktb200_mla_decode dumps the raw scores of its first tile (>= 2048 floats). */
 void ktb200_debug_mla(float* debug_dev);
 
+/* ------------------------------------------------------------------------------------------
+ * The memory-bound steps between the projections of a DeepSeek decode layer (bf16), fused:
+ *   ktb200_add_rmsnorm: residual[t] += delta[t] (delta may be NULL); out[t] = DeepseekV3RMSNorm(residual[t]) * weight
+ *     (archive/ktransformers/models/modeling_deepseek_v3.py:65-80 and the residual adds of DeepseekV3DecoderLayer.forward;
+ *      operators/layernorm.py).  Also used for q_a_layernorm (delta NULL, residual == the projection output, untouched).
+ *   ktb200_mla_prep: after the q_b and kv_a projections of MLA — kv_a_layernorm on the 512 latent columns, RoPE
+ *     (de-interleaved pairs, modeling_deepseek_v3.py:339-373) on k_pe and on every head's q_pe, and the paged cache write
+ *     (custom_cache.py:147-193): q [T][heads][nope+64], kv_a_out [T][576], cos/sin fp32 [T][64], page_idx/page_offset
+ *     int32 [T]; q_pe_out [T][heads][64].
+ * ------------------------------------------------------------------------------------------ */
+int ktb200_add_rmsnorm(void* residual_dev, const void* delta_dev, const void* weight_dev, float eps, void* out_dev, int n_tokens,
+                       int hidden, void* stream);
+int ktb200_mla_prep(const void* q_dev, int num_heads, int qk_nope_head_dim, const void* kv_a_out_dev, const void* kv_a_norm_weight_dev,
+                    float eps, const float* cos_dev, const float* sin_dev, void* kv_cache_dev, int page_size, const int* page_idx_dev,
+                    const int* page_offset_dev, void* q_pe_out_dev, int n_tokens, void* stream);
+
 /* paged latent KV write: StaticCache.update (archive/ktransformers/models/custom_cache.py:147-200)
  * kv_cache[page_idx[t]][page_offset[t]][0:512] = ckv[t], [512:576] = k_pe[t] */
 int ktb200_mla_kv_write(void* kv_cache, int page_size, const void* ckv, const void* k_pe, const int* page_idx,

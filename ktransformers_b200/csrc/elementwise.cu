@@ -1,0 +1,116 @@
+// The small memory-bound steps between the projections of a DeepSeek decode layer, fused so that a layer is ~14 launches
+// instead of ~40 ATen kernels (archive/ktransformers/operators/layernorm.py, RoPE.py and the residual adds of
+// models/modeling_deepseek_v3.py DeepseekV3DecoderLayer.forward :1086-1140):
+//   ktb200_add_rmsnorm   residual += delta ; out = RMSNorm(residual) * weight          (input_layernorm / post_attention_layernorm)
+//   ktb200_mla_prep      q_a / kv_a layernorms are ktb200_add_rmsnorm calls; this kernel does what follows the q_b and kv_a
+//                        projections of MLA: kv_a_layernorm on the 512 latent columns, RoPE on k_pe and on every head's
+//                        q_pe (de-interleaved pairs, modeling_deepseek_v3.py:339-373), and the paged cache write
+//                        (StaticCache.update, custom_cache.py:147-193) — one launch.
+// RMSNorm follows DeepseekV3RMSNorm (modeling_deepseek_v3.py:65-80): variance in fp32, normalised value rounded to the
+// input dtype, then multiplied by the weight in that dtype.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ktb {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < nw; w++) s += red[w];
+    __syncthreads();
+    return s;
+}
+__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+
+// one CTA per row; H <= 8 * 1024 elements per thread loop
+__global__ void __launch_bounds__(256) add_rmsnorm_kernel(__nv_bfloat16* resid, const __nv_bfloat16* delta, const __nv_bfloat16* weight, float eps,
+                                                          __nv_bfloat16* out, int H, long resid_stride, long delta_stride, long out_stride) {
+    __shared__ float red[8];
+    const long t = blockIdx.x;
+    __nv_bfloat16* r = resid + t * resid_stride;
+    const __nv_bfloat16* d = delta ? delta + t * delta_stride : nullptr;
+    float ss = 0.f;
+    for (int i = threadIdx.x * 2; i < H; i += blockDim.x * 2) {
+        __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(r + i);
+        if (d) {
+            v = __hadd2(v, *reinterpret_cast<const __nv_bfloat162*>(d + i));   // the residual stream itself is bf16 (x = x + attn_out)
+            *reinterpret_cast<__nv_bfloat162*>(r + i) = v;
+        }
+        const float2 f = __bfloat1622float2(v);
+        ss += f.x * f.x + f.y * f.y;
+    }
+    const float inv = rsqrtf(block_sum(ss, red) / (float)H + eps);
+    __nv_bfloat16* o = out + t * out_stride;
+    for (int i = threadIdx.x * 2; i < H; i += blockDim.x * 2) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + i));
+        const __nv_bfloat162 hn = __floats2bfloat162_rn(f.x * inv, f.y * inv);
+        *reinterpret_cast<__nv_bfloat162*>(o + i) = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(weight + i), hn);
+    }
+}
+
+// grid (tokens), 256 threads: threads 0..63 of warps handle heads round-robin for q_pe; the latent norm uses the whole CTA
+__global__ void __launch_bounds__(256) mla_prep_kernel(const __nv_bfloat16* q, int num_heads, int q_head_dim, int nope_dim, const __nv_bfloat16* kva,
+                                                       const __nv_bfloat16* kv_norm_w, float eps, const float* cos_t, const float* sin_t,
+                                                       __nv_bfloat16* kv_cache, int page_size, const int* page_idx, const int* page_off,
+                                                       __nv_bfloat16* q_pe_out) {
+    constexpr int R = 64, LAT = 512;
+    __shared__ float red[8];
+    const long t = blockIdx.x;
+    const float* cs = cos_t + t * R;
+    const float* sn = sin_t + t * R;
+    // y[i] = x'[i] * cos[i] + rot(x')[i] * sin[i],  x'[i] = x[2i] (i < 32) | x[2(i-32)+1] ;  rot(x')[i] = -x'[i+32] | x'[i-32]
+    auto rope = [&](const __nv_bfloat16* x, int i) -> float {
+        const int half = R / 2;
+        const float a = bf(x[i < half ? 2 * i : 2 * (i - half) + 1]);
+        const float b = i < half ? -bf(x[2 * i + 1]) : bf(x[2 * (i - half)]);
+        // the reference computes (q * cos) + (rotate_half(q) * sin) in the tensor dtype: each product rounded to bf16, then the sum
+        const float p0 = __bfloat162float(__float2bfloat16_rn(a * cs[i])), p1 = __bfloat162float(__float2bfloat16_rn(b * sn[i]));
+        return p0 + p1;
+    };
+    for (int u = threadIdx.x; u < num_heads * R; u += blockDim.x) {
+        const int h = u / R, i = u - h * R;
+        q_pe_out[(t * num_heads + h) * R + i] = __float2bfloat16_rn(rope(q + (t * num_heads + h) * q_head_dim + nope_dim, i));
+    }
+    __nv_bfloat16* dst = kv_cache + ((long)page_idx[t] * page_size + page_off[t]) * (LAT + R);
+    const __nv_bfloat16* row = kva + t * (LAT + R);
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < LAT; i += blockDim.x) { const float f = bf(row[i]); ss += f * f; }
+    const float inv = rsqrtf(block_sum(ss, red) / (float)LAT + eps);
+    for (int i = threadIdx.x; i < LAT; i += blockDim.x) {
+        const __nv_bfloat16 hn = __float2bfloat16_rn(bf(row[i]) * inv);
+        dst[i] = __hmul(kv_norm_w[i], hn);
+    }
+    if (threadIdx.x < R) dst[LAT + threadIdx.x] = __float2bfloat16_rn(rope(row + LAT, threadIdx.x));
+}
+
+}  // namespace ktb
+
+using namespace ktb;
+
+extern "C" int ktb200_add_rmsnorm(void* residual, const void* delta, const void* weight, float eps, void* out, int n_tokens, int hidden, void* stream) {
+    if (!residual || !weight || !out || n_tokens < 0 || hidden <= 0 || hidden % 2) { set_error("add_rmsnorm: bad argument (bf16, even hidden)"); return KTB200_EINVAL; }
+    if (n_tokens == 0) return KTB200_OK;
+    add_rmsnorm_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)residual, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, eps,
+                                                                   (__nv_bfloat16*)out, hidden, hidden, hidden, hidden);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+extern "C" int ktb200_mla_prep(const void* q, int num_heads, int qk_nope_head_dim, const void* kv_a_out, const void* kv_a_norm_weight, float eps,
+                               const float* cos, const float* sin, void* kv_cache, int page_size, const int* page_idx, const int* page_offset,
+                               void* q_pe_out, int n_tokens, void* stream) {
+    if (!q || !kv_a_out || !kv_a_norm_weight || !cos || !sin || !kv_cache || !page_idx || !page_offset || !q_pe_out || num_heads <= 0 || qk_nope_head_dim <= 0) {
+        set_error("mla_prep: null pointer / bad shape");
+        return KTB200_EINVAL;
+    }
+    if (n_tokens <= 0) return KTB200_OK;
+    mla_prep_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)q, num_heads, qk_nope_head_dim + 64, qk_nope_head_dim,
+                                                                (const __nv_bfloat16*)kv_a_out, (const __nv_bfloat16*)kv_a_norm_weight, eps, cos, sin,
+                                                                (__nv_bfloat16*)kv_cache, page_size, page_idx, page_offset, (__nv_bfloat16*)q_pe_out);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}

@@ -142,6 +142,118 @@ class DeepseekV3MoE(nn.Module):
         return y
 
 
+class DeepseekV3RMSNorm(nn.Module):
+    """modeling_deepseek_v3.py:65-80: fp32 variance, weight applied in the input dtype."""
+
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, hidden_states):
+        input_dtype = hidden_states.dtype
+        h = hidden_states.to(torch.float32)
+        h = h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
+        return self.weight * h.to(input_dtype)
+
+
+def yarn_get_mscale(scale=1.0, mscale=1.0):
+    return 1.0 if scale <= 1 else 0.1 * mscale * math.log(scale) + 1.0
+
+
+class DeepseekV3RotaryEmbedding(nn.Module):
+    """Plain RoPE tables (modeling_deepseek_v3.py:100-140); `forward(x, position_ids)` returns (cos, sin) [bsz, q_len, dim]
+    the way the injected YarnRotaryEmbeddingV3 does (operators/RoPE.py:222-326)."""
+
+    def __init__(self, dim, max_position_embeddings=163840, base=10000.0):
+        super().__init__()
+        self.dim, self.base = dim, base
+        inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2).float() / dim))
+        self.register_buffer("inv_freq", inv_freq, persistent=False)
+
+    @torch.no_grad()
+    def forward(self, x, position_ids):
+        freqs = position_ids[:, :, None].float() * self.inv_freq.to(position_ids.device)[None, None, :]
+        emb = torch.cat((freqs, freqs), dim=-1)
+        return emb.cos().to(x.dtype), emb.sin().to(x.dtype)
+
+
+def rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rotary_pos_emb(q, k, cos, sin, unsqueeze_dim=1):
+    """modeling_deepseek_v3.py:339-373, including the de-interleaving permutation of the rope dims."""
+    cos, sin = cos.unsqueeze(unsqueeze_dim), sin.unsqueeze(unsqueeze_dim)
+    b, s, h, d = q.shape
+    q = q.view(b, s, h, d // 2, 2).transpose(4, 3).reshape(b, s, h, d)
+    b, s, h, d = k.shape
+    k = k.view(b, s, h, d // 2, 2).transpose(4, 3).reshape(b, s, h, d)
+    return (q * cos) + (rotate_half(q) * sin), (k * cos) + (rotate_half(k) * sin)
+
+
+class DeepseekV3Attention(nn.Module):
+    """Multi-head latent attention, modeling_deepseek_v3.py:619-800: the injection target of KDeepseekV2Attention.  `forward`
+    here is the plain (non-absorbed, full-precision) formulation over an explicit list of past latents — the restatement
+    the operator tests compare the absorbed paged decode against."""
+
+    def __init__(self, config, layer_idx: int = 0):
+        super().__init__()
+        self.config, self.layer_idx = config, layer_idx
+        self.hidden_size, self.num_heads = config.hidden_size, config.num_attention_heads
+        self.q_lora_rank, self.kv_lora_rank = config.q_lora_rank, config.kv_lora_rank
+        self.qk_rope_head_dim, self.qk_nope_head_dim, self.v_head_dim = config.qk_rope_head_dim, config.qk_nope_head_dim, config.v_head_dim
+        self.q_head_dim = self.qk_nope_head_dim + self.qk_rope_head_dim
+        if self.q_lora_rank is None:
+            self.q_proj = nn.Linear(self.hidden_size, self.num_heads * self.q_head_dim, bias=False)
+        else:
+            self.q_a_proj = nn.Linear(self.hidden_size, self.q_lora_rank, bias=False)
+            self.q_a_layernorm = DeepseekV3RMSNorm(self.q_lora_rank, config.rms_norm_eps)
+            self.q_b_proj = nn.Linear(self.q_lora_rank, self.num_heads * self.q_head_dim, bias=False)
+        self.kv_a_proj_with_mqa = nn.Linear(self.hidden_size, self.kv_lora_rank + self.qk_rope_head_dim, bias=False)
+        self.kv_a_layernorm = DeepseekV3RMSNorm(self.kv_lora_rank, config.rms_norm_eps)
+        self.kv_b_proj = nn.Linear(self.kv_lora_rank, self.num_heads * (self.qk_nope_head_dim + self.v_head_dim), bias=False)
+        self.o_proj = nn.Linear(self.num_heads * self.v_head_dim, self.hidden_size, bias=False)
+        self.rotary_emb = DeepseekV3RotaryEmbedding(self.qk_rope_head_dim, base=getattr(config, "rope_theta", 10000.0))
+        self.softmax_scale = self.q_head_dim ** (-0.5)
+        rs = getattr(config, "rope_scaling", None)
+        if rs is not None and rs.get("mscale_all_dim", 0):
+            m = yarn_get_mscale(rs["factor"], rs["mscale_all_dim"])
+            self.softmax_scale = self.softmax_scale * m * m
+
+    def project(self, hidden_states, position_ids):
+        """(q_nope [b,s,h,128], q_pe [b,s,h,64] roped, ckv [b,s,1,512] normed, k_pe [b,s,1,64] roped)"""
+        bsz, q_len, _ = hidden_states.size()
+        q = self.q_proj(hidden_states) if self.q_lora_rank is None else self.q_b_proj(self.q_a_layernorm(self.q_a_proj(hidden_states)))
+        q = q.view(bsz, q_len, self.num_heads, self.q_head_dim)
+        q_nope, q_pe = torch.split(q, [self.qk_nope_head_dim, self.qk_rope_head_dim], dim=-1)
+        ckv = self.kv_a_proj_with_mqa(hidden_states)
+        ckv, k_pe = torch.split(ckv, [self.kv_lora_rank, self.qk_rope_head_dim], dim=-1)
+        ckv = self.kv_a_layernorm(ckv).view(bsz, q_len, 1, self.kv_lora_rank)
+        k_pe = k_pe.view(bsz, q_len, 1, self.qk_rope_head_dim)
+        cos, sin = self.rotary_emb(q_pe, position_ids)
+        q_pe, k_pe = apply_rotary_pos_emb(q_pe, k_pe, cos, sin, unsqueeze_dim=2)
+        return q_nope, q_pe, ckv, k_pe
+
+    def forward(self, hidden_states, position_ids, past_latents=None):
+        """past_latents: optional (ckv [b, L, 512], k_pe [b, L, 64]) of the earlier tokens; causal within the new tokens."""
+        bsz, q_len, _ = hidden_states.size()
+        q_nope, q_pe, ckv, k_pe = self.project(hidden_states, position_ids)
+        ckv, k_pe = ckv.squeeze(2), k_pe.squeeze(2)
+        if past_latents is not None:
+            ckv, k_pe = torch.cat([past_latents[0], ckv], 1), torch.cat([past_latents[1], k_pe], 1)
+        L = ckv.shape[1]
+        kv = self.kv_b_proj(ckv).view(bsz, L, self.num_heads, self.qk_nope_head_dim + self.v_head_dim)
+        k_nope, v = torch.split(kv, [self.qk_nope_head_dim, self.v_head_dim], dim=-1)
+        s = torch.einsum("bqhd,bkhd->bhqk", q_nope.float(), k_nope.float()) + torch.einsum("bqhd,bkd->bhqk", q_pe.float(), k_pe.float())
+        s = s * self.softmax_scale
+        mask = torch.arange(L, device=s.device)[None, :] > (L - q_len + torch.arange(q_len, device=s.device))[:, None]
+        s = s.masked_fill(mask[None, None], float("-inf"))
+        o = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v.float()).to(hidden_states.dtype)
+        return self.o_proj(o.reshape(bsz, q_len, self.num_heads * self.v_head_dim)), (ckv, k_pe)
+
+
 class DeepseekV3DecoderLayerMoEOnly(nn.Module):
     """A decoder layer reduced to its MoE block (what the hot path covers)."""
 
