@@ -262,7 +262,7 @@ def full_decode_leg(args, lib, native, dev, local_rank, layers, L, moe_layer_cal
     pages = (ctx + PAGE) // PAGE + 1
     att = []
     for l in range(NL):
-        d = dict(q_a=linear(H, QL, Q4_K, 9000 + 10 * l), kv_a=linear(H, KVL + ROPE, Q4_K, 9001 + 10 * l), q_b=linear(QL, NH * (NOPE + ROPE), Q4_K, 9002 + 10 * l),
+        d = dict(qkv_a=linear(H, QL + KVL + ROPE, Q4_K, 9000 + 10 * l), q_b=linear(QL, NH * (NOPE + ROPE), Q4_K, 9002 + 10 * l),
                  o=linear(NH * VD, H, Q4_K, 9003 + 10 * l),
                  w_uk=(torch.randn(NH, NOPE, KVL, device=dev, generator=g) * 0.05).to(bf), w_uv=(torch.randn(NH, VD, KVL, device=dev, generator=g) * 0.05).to(bf),
                  ln_in=normw(H), ln_qa=normw(QL), ln_kv=normw(KVL), ln_post=normw(H),
@@ -279,7 +279,9 @@ def full_decode_leg(args, lib, native, dev, local_rank, layers, L, moe_layer_cal
     ln_final = normw(H)
     # static buffers
     x = torch.zeros(1, H, dtype=bf, device=dev); hbuf = torch.zeros(1, H, dtype=bf, device=dev); y = torch.zeros(1, H, dtype=bf, device=dev)
-    qa = torch.zeros(1, QL, dtype=bf, device=dev); qan = torch.zeros(1, QL, dtype=bf, device=dev); kva = torch.zeros(1, KVL + ROPE, dtype=bf, device=dev)
+    qkva = torch.zeros(1, QL + KVL + ROPE, dtype=bf, device=dev)          # q_a and kv_a share their input: one projection, rows stacked
+    qa, kva = qkva[:, :QL], qkva[:, QL:]
+    qan = torch.zeros(1, QL, dtype=bf, device=dev)
     q = torch.zeros(1, NH * (NOPE + ROPE), dtype=bf, device=dev); q_pe = torch.zeros(NH, ROPE, dtype=bf, device=dev)
     q_abs = torch.zeros(NH, 1, KVL, dtype=bf, device=dev); lat = torch.zeros(1, NH, KVL, dtype=bf, device=dev)
     o_in = torch.zeros(NH, 1, VD, dtype=bf, device=dev); attn_out = torch.zeros(1, H, dtype=bf, device=dev)
@@ -306,14 +308,14 @@ def full_decode_leg(args, lib, native, dev, local_rank, layers, L, moe_layer_cal
             a = att[l]
             native.check(lib.ktb200_add_rmsnorm(x.data_ptr(), delta.data_ptr() if delta is not None else None, a["ln_in"].data_ptr(), eps, hbuf.data_ptr(), 1, H, S()))
             if with_attn:
-                lin(a["q_a"], hbuf, qa); lin(a["kv_a"], hbuf, kva)
+                lin(a["qkv_a"], hbuf, qkva)
                 native.check(lib.ktb200_add_rmsnorm(qa.data_ptr(), None, a["ln_qa"].data_ptr(), eps, qan.data_ptr(), 1, QL, S()))
                 lin(a["q_b"], qan, q)
                 native.check(lib.ktb200_mla_prep(q.data_ptr(), NH, NOPE, kva.data_ptr(), a["ln_kv"].data_ptr(), eps, cos.data_ptr(), sin.data_ptr(),
                                                  a["cache"].data_ptr(), PAGE, pidx.data_ptr(), poff.data_ptr(), q_pe.data_ptr(), 1, S()))
-                torch.bmm(q.view(NH, 1, NOPE + ROPE)[:, :, :NOPE], a["w_uk"], out=q_abs)
+                native.check(lib.ktb200_mla_absorb_q(q.data_ptr(), NOPE + ROPE, NH * (NOPE + ROPE), a["w_uk"].data_ptr(), NH, NOPE, KVL, q_abs.data_ptr(), 1, S()))
                 native.check(lib.ktb200_mla_decode(C.byref(mla[l]), S()))
-                torch.bmm(lat.view(NH, 1, KVL), a["w_uv"].transpose(1, 2), out=o_in)
+                native.check(lib.ktb200_mla_absorb_o(lat.data_ptr(), a["w_uv"].data_ptr(), NH, VD, KVL, o_in.data_ptr(), 1, S()))
                 lin(a["o"], o_in.view(1, NH * VD), attn_out)
                 native.check(lib.ktb200_add_rmsnorm(x.data_ptr(), attn_out.data_ptr(), a["ln_post"].data_ptr(), eps, hbuf.data_ptr(), 1, H, S()))
             if l < 3:
@@ -362,7 +364,7 @@ def full_decode_leg(args, lib, native, dev, local_rank, layers, L, moe_layer_cal
             "our_launches_per_token": launches, "algorithmic_bytes_per_token": {"attention": attn_bytes, "moe": moe_bytes, "dense_mlp_lm_head": other_bytes, "total": total},
             "achieved_GBps": total / (ms_full * 1e-3) / 1e9, "frac_of_peak": total / (ms_full * 1e-3) / 1e9 / peak,
             "attention_GBps": attn_bytes / ((ms_full - ms_noattn) * 1e-3) / 1e9,
-            "note": "absorb products are cuBLAS bmm (plain library GEMMs, as in the reference); everything else is this repo's kernels"}
+            "note": "every kernel in the step is this repo's (no library GEMM); q_a and kv_a are one stacked projection"}
 
 # ----------------------------------------------------------------------------------------------- B200 arm
 def main():

@@ -317,6 +317,14 @@ int ktb200_mla_prep(const void* q_dev, int num_heads, int qk_nope_head_dim, cons
                     float eps, const float* cos_dev, const float* sin_dev, void* kv_cache_dev, int page_size, const int* page_idx_dev,
                     const int* page_offset_dev, void* q_pe_out_dev, int n_tokens, void* stream);
 
+/* The two absorb products of MLA decode (attention.py:428-431, 470-472): batches of one-row GEMVs over the per-head bf16
+ * halves of kv_b_proj — q_abs[t][h][:] = q_nope[t][h][:] . W_UK[h] ([heads][nope][512]; q addressed by element strides so the
+ * q_nope slice of the q_b output needs no copy) and out[t][h][:] = attn_latent[t][h][:] . W_UV[h]^T ([heads][v][512]). */
+int ktb200_mla_absorb_q(const void* q_dev, long q_head_stride, long q_token_stride, const void* w_uk_dev, int num_heads, int qk_nope_head_dim,
+                        int kv_lora_rank, void* q_abs_out_dev, int n_tokens, void* stream);
+int ktb200_mla_absorb_o(const void* attn_latent_dev, const void* w_uv_dev, int num_heads, int v_head_dim, int kv_lora_rank, void* out_dev,
+                        int n_tokens, void* stream);
+
 /* paged latent KV write: StaticCache.update (archive/ktransformers/models/custom_cache.py:147-200)
  * kv_cache[page_idx[t]][page_offset[t]][0:512] = ckv[t], [512:576] = k_pe[t] */
 int ktb200_mla_kv_write(void* kv_cache, int page_size, const void* ckv, const void* k_pe, const int* page_idx,

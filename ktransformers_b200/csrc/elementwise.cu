@@ -114,3 +114,75 @@ extern "C" int ktb200_mla_prep(const void* q, int num_heads, int qk_nope_head_di
     KTB_LAUNCH_CHECK();
     return KTB200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The two absorb products of MLA decode (archive/ktransformers/operators/attention.py:428-431, 470-472), batch of
+// one-row GEMVs over per-head bf16 weights — HBM-bound (16.8 MB each for DeepSeek-V3), fp32 accumulation:
+//   mode 0  q_abs[t][h][c] = sum_d q_nope[t][h][d] * W_UK[h][d][c]     W [heads][D][C] read along c (contiguous)
+//   mode 1  o[t][h][v]     = sum_c lat[t][h][c]   * W_UV[h][v][c]     W [heads][V][C] read along c (contiguous): one warp per (h, v)
+namespace ktb {
+
+// grid (C / 512, heads, tokens), 256 threads: thread owns columns c = 2 * tid + {0, 1} of this 512-column slab
+__global__ void __launch_bounds__(256) absorb_q_kernel(const __nv_bfloat16* q, long q_head_stride, long q_tok_stride, const __nv_bfloat16* W, int D, int Cc,
+                                                        __nv_bfloat16* out) {
+    __shared__ float qs[512];
+    const int h = blockIdx.y, t = blockIdx.z, heads = gridDim.y;
+    const __nv_bfloat16* qrow = q + t * q_tok_stride + h * q_head_stride;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = bf(qrow[i]);
+    __syncthreads();
+    const int c = blockIdx.x * 512 + threadIdx.x * 2;
+    if (c >= Cc) return;
+    const __nv_bfloat16* w = W + ((long)h * D) * Cc + c;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; d++) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(w + (long)d * Cc));
+        a0 = fmaf(qs[d], f.x, a0);
+        a1 = fmaf(qs[d], f.y, a1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + ((long)t * heads + h) * Cc + c) = __floats2bfloat162_rn(a0, a1);
+}
+
+// grid (V / 8, heads, tokens), 256 threads = 8 warps: warp w owns output v = 8 * blockIdx.x + w
+__global__ void __launch_bounds__(256) absorb_o_kernel(const __nv_bfloat16* lat, const __nv_bfloat16* W, int V, int Cc, __nv_bfloat16* out) {
+    const int h = blockIdx.y, t = blockIdx.z, heads = gridDim.y, lane = threadIdx.x & 31;
+    const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (v >= V) return;
+    const __nv_bfloat16* x = lat + ((long)t * heads + h) * Cc;
+    const __nv_bfloat16* w = W + ((long)h * V + v) * Cc;
+    float acc = 0.f;
+    for (int c = lane * 8; c < Cc; c += 256) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(w + c), xv = *reinterpret_cast<const uint4*>(x + c);
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 a = __bfloat1622float2(w2[i]), b = __bfloat1622float2(x2[i]);
+            acc = fmaf(a.x, b.x, acc);
+            acc = fmaf(a.y, b.y, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[((long)t * heads + h) * V + v] = __float2bfloat16_rn(acc);
+}
+
+}  // namespace ktb
+
+extern "C" int ktb200_mla_absorb_q(const void* q, long q_head_stride, long q_token_stride, const void* w_uk, int num_heads, int nope_dim, int kv_lora_rank,
+                                   void* q_abs_out, int n_tokens, void* stream) {
+    if (!q || !w_uk || !q_abs_out || num_heads <= 0 || nope_dim <= 0 || nope_dim > 512 || kv_lora_rank <= 0 || kv_lora_rank % 2) { set_error("mla_absorb_q: bad argument"); return KTB200_EINVAL; }
+    if (n_tokens <= 0) return KTB200_OK;
+    ktb::absorb_q_kernel<<<dim3((kv_lora_rank + 511) / 512, num_heads, n_tokens), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)q, q_head_stride, q_token_stride, (const __nv_bfloat16*)w_uk, nope_dim, kv_lora_rank, (__nv_bfloat16*)q_abs_out);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
+extern "C" int ktb200_mla_absorb_o(const void* attn_latent, const void* w_uv, int num_heads, int v_head_dim, int kv_lora_rank, void* out, int n_tokens, void* stream) {
+    if (!attn_latent || !w_uv || !out || num_heads <= 0 || v_head_dim <= 0 || kv_lora_rank <= 0 || kv_lora_rank % 8) { set_error("mla_absorb_o: bad argument"); return KTB200_EINVAL; }
+    if (n_tokens <= 0) return KTB200_OK;
+    ktb::absorb_o_kernel<<<dim3((v_head_dim + 7) / 8, num_heads, n_tokens), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn_latent, (const __nv_bfloat16*)w_uv,
+                                                                                                              v_head_dim, kv_lora_rank, (__nv_bfloat16*)out);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}

@@ -4,14 +4,15 @@ Mirrors archive/ktransformers/operators/attention.py:49-75 (`get_absorbed`) and 
 decode branch): q projections -> RoPE -> paged latent-cache update -> q_nope . W_UK (batched matmul) -> MLA paged decode
 over the 576-wide latents -> . W_UV^T -> o_proj.  The attention itself is `MLAWrapper.run` = ktb200_mla_decode (tcgen05 +
 TMEM + TMA, csrc/mla.cu); the cache write is ktb200_mla_kv_write; the projections are whatever modules the rules injected
-(KLinearB200 on raw GGUF blocks, or nn.Linear); the two absorb products are plain batched GEMMs (cuBLAS via torch.matmul,
-as in the reference).  Prefill (q_len > 1 without absorb) is outside this path and raises."""
+(KLinearB200 on raw GGUF blocks, or nn.Linear); the two absorb products are ktb200_mla_absorb_q / _o (HBM-bound batched
+GEMVs over the bf16 halves of kv_b_proj; torch.matmul for other dtypes).  Prefill (q_len > 1 without absorb) is outside this path and raises."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
 
 import torch
 
+from .. import native
 from ..models.modeling_deepseek_v3 import DeepseekV3Attention, apply_rotary_pos_emb
 from .base_operator import BaseInjectedModule
 from .flashinfer_wrapper import MLAWrapperSingleton
@@ -57,8 +58,16 @@ class KDeepseekV2Attention(BaseInjectedModule, DeepseekV3Attention):
         kpe_pages = kv_with_k_pe[:, :, :, self.kv_lora_rank:].view(-1, past_key_value.page_size, self.qk_rope_head_dim)
 
         q_absorb, out_absorb = self.get_absorbed()
-        q_nope = torch.matmul(q_nope.transpose(1, 2), q_absorb).transpose(1, 2).contiguous()     # [b, 1, h, 512]
-        q_nope, q_pe = q_nope.reshape(bsz * q_len, self.num_heads, self.kv_lora_rank), q_pe.reshape(bsz * q_len, self.num_heads, self.qk_rope_head_dim)
+        fused = (q.dtype == torch.bfloat16 and q_absorb.dtype == torch.bfloat16 and q.is_contiguous())
+        stream = torch.cuda.current_stream(hidden_states.device).cuda_stream
+        if fused:   # q_nope . W_UK straight from the q_b output (no slice copy): ktb200_mla_absorb_q
+            q_abs = torch.empty((bsz * q_len, self.num_heads, self.kv_lora_rank), dtype=q.dtype, device=q.device)
+            native.check(native.lib().ktb200_mla_absorb_q(q.data_ptr(), self.q_head_dim, self.num_heads * self.q_head_dim, q_absorb.data_ptr(), self.num_heads,
+                                                          self.qk_nope_head_dim, self.kv_lora_rank, q_abs.data_ptr(), bsz * q_len, stream))
+            q_nope = q_abs
+        else:
+            q_nope = torch.matmul(q_nope.transpose(1, 2), q_absorb).transpose(1, 2).contiguous().reshape(bsz * q_len, self.num_heads, self.kv_lora_rank)
+        q_pe = q_pe.reshape(bsz * q_len, self.num_heads, self.qk_rope_head_dim)
 
         if self.mla_wrapper is None:
             self.mla_wrapper = MLAWrapperSingleton.get_instance(str(hidden_states.device), bsz, past_key_value.max_pages * bsz, use_cuda_graph=True)
@@ -74,6 +83,12 @@ class KDeepseekV2Attention(BaseInjectedModule, DeepseekV3Attention):
         else:   # the plan is static (identity page table); only the lengths move from step to step (a captured device copy)
             w.kv_len_arr_buf[:bsz].copy_((position_ids.reshape(bsz, -1)[:, -1] + 1).to(torch.int32))
         attn = w.run(q_nope, q_pe.contiguous(), ckv_pages, kpe_pages).view(bsz, q_len, self.num_heads, self.kv_lora_rank)
-        attn = torch.matmul(attn.transpose(1, 2), out_absorb.mT).transpose(1, 2).contiguous()     # [b, 1, h, 128]
+        if fused:
+            o = torch.empty((bsz, q_len, self.num_heads, self.v_head_dim), dtype=attn.dtype, device=attn.device)
+            native.check(native.lib().ktb200_mla_absorb_o(attn.data_ptr(), out_absorb.data_ptr(), self.num_heads, self.v_head_dim, self.kv_lora_rank, o.data_ptr(),
+                                                          bsz * q_len, stream))
+            attn = o
+        else:
+            attn = torch.matmul(attn.transpose(1, 2), out_absorb.mT).transpose(1, 2).contiguous()     # [b, 1, h, 128]
         attn = self.o_proj(attn.reshape(bsz, q_len, self.num_heads * self.v_head_dim))
         return attn, None, past_key_value
