@@ -6,6 +6,7 @@
 #include <new>
 
 #include "gemv_bulk.cuh"
+#include "dense_bulk.cuh"
 #include "handles.cuh"
 
 namespace ktb {
@@ -240,10 +241,47 @@ static int launch_rows_bulk_q4k(const RowsParams& p, int T, int device, cudaStre
     return KTB200_OK;
 }
 
+// Dense Q4_K linear on the segment ring (dense_bulk.cuh).  Returns 1 when the shape does not suit it.
+static int launch_dense_q4k(const RowsParams& p, int T, int device, cudaStream_t stream) {
+    static const int on = env_int("KTB200_DENSE_BULK", 1);
+    if (!on || p.ids || p.slots != 1 || p.x0 || !p.out_hidden || p.out_f32 || T > kDenseMaxTokens) return 1;
+    const int nblk = p.ncols / QK_K;
+    DenseParams d{};
+    d.w = reinterpret_cast<const uint8_t*>(p.w0); d.x = p.x; d.out = p.out_hidden; d.bias = p.bias; d.bsz = p.bsz;
+    d.rows = p.rows; d.ncols = p.ncols; d.T = T; d.hidden_type = p.hidden_type;
+    if (nblk <= 16) { d.R = 32 / nblk; d.G = 1; d.segb = d.R * nblk; }
+    else if (nblk <= 32) { d.R = 1; d.G = 1; d.segb = nblk; }
+    else { d.R = 1; d.G = (nblk + 31) / 32; if (nblk % d.G) return 1; d.segb = nblk / d.G; }
+    d.act_tok = (nblk * kActBlkStride + nblk * 16 + nblk * 4 + 15) & ~15;
+    constexpr int SL = 4;
+    const size_t head = (((size_t)T * d.act_tok + 15) & ~(size_t)15);
+    const size_t seg = (size_t)d.segb * SZ_Q4_K;
+    if (head + 64 >= kSmemCap) return 1;
+    int W = (int)((kSmemCap - head - 16) / (SL * (seg + 8)));
+    if (W > kDenseWarps) W = kDenseWarps;
+    if (W < 4) return 1;
+    const size_t smem = head + (((size_t)W * SL * 8 + 15) & ~(size_t)15) + (size_t)W * SL * seg;
+    const int nunits = (p.rows + d.R - 1) / d.R;
+    int gx = num_sms(device);
+    if (gx > nunits) gx = nunits;
+    static size_t limit[64] = {};
+    if (limit[device & 63] < smem) {
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(dense_q4k_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        limit[device & 63] = smem;
+    }
+    dense_q4k_kernel<SL><<<gx, W * 32, smem, stream>>>(d);
+    KTB_LAUNCH_CHECK();
+    return KTB200_OK;
+}
+
 template <bool PAIR>
 static int launch_rows(FmtId f, const RowsParams& p_in, int T, int device, cudaStream_t stream) {
     RowsParams p = p_in;
     p.ntokens = T;
+    if (!PAIR && f == FMT_Q4K) {
+        const int rcd = launch_dense_q4k(p, T, device, stream);
+        if (rcd != 1) return rcd;
+    }
     if (f == FMT_Q4K) {
         const int rcb = launch_rows_bulk_q4k<PAIR>(p, T, device, stream);
         if (rcb != 1) return rcb;
