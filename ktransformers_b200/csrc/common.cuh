@@ -42,6 +42,21 @@ void count_launch(int n = 1);
 
 int num_sms(int device);
 
+#ifdef __CUDACC__
+// launch with the programmatic-stream-serialization attribute (KTB200_PDL=0 disables it library-wide)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 __host__ __device__ inline long type_size(int t) {
     switch (t) {
         case KTB200_TYPE_F32: return 4;
@@ -95,6 +110,12 @@ __device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream is
+// still running; everything it reads from — or writes over — what the predecessor touches must come after griddep_wait()
+// (which returns when the predecessor grid has completed and flushed).  griddep_launch_dependents() lets the successor's
+// launch processing begin.  Weight prefetches go before the wait, activations after it.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint16_t ldg_u16(const void* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
 __device__ __forceinline__ uint8_t ldg_u8(const void* p) { return __ldg(reinterpret_cast<const unsigned char*>(p)); }
 

@@ -30,8 +30,9 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kDenseWarps * 32, 1) dense_q4k_kernel(const DenseParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    griddep_launch_dependents();
     int T = p.T;
-    if (p.bsz) T = min(T, *p.bsz);
+    if (p.bsz) { griddep_wait(); T = min(T, *p.bsz); }
     const int nblk = p.ncols / QK_K;
     const int seg_bytes = p.segb * SZ_Q4_K;
     const size_t off = ((size_t)p.T * p.act_tok + 15) & ~(size_t)15;
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(kDenseWarps * 32, 1) dense_q4k_kernel(const De
         }
     };
 #pragma unroll
-    for (int s = 0; s < SLOTS; s++) issue_one();
+    for (int s = 0; s < SLOTS; s++) issue_one();   // weights do not depend on the previous kernel: requested before the wait
+    griddep_wait();
 
     {   // activations -> Q8_K, padded layout (as in rows_bulk_q4k_kernel): block g = (token, block of the row)
         float cur[8], nxt[8];

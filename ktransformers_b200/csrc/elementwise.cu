@@ -30,6 +30,8 @@ __device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162f
 __global__ void __launch_bounds__(256) add_rmsnorm_kernel(__nv_bfloat16* resid, const __nv_bfloat16* delta, const __nv_bfloat16* weight, float eps,
                                                           __nv_bfloat16* out, int H, long resid_stride, long delta_stride, long out_stride) {
     __shared__ float red[8];
+    griddep_launch_dependents();
+    griddep_wait();
     const long t = blockIdx.x;
     __nv_bfloat16* r = resid + t * resid_stride;
     const __nv_bfloat16* d = delta ? delta + t * delta_stride : nullptr;
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(256) mla_prep_kernel(const __nv_bfloat16* q, i
                                                        __nv_bfloat16* q_pe_out) {
     constexpr int R = 64, LAT = 512;
     __shared__ float red[8];
+    griddep_launch_dependents();
+    griddep_wait();
     const long t = blockIdx.x;
     const float* cs = cos_t + t * R;
     const float* sn = sin_t + t * R;
@@ -94,9 +98,9 @@ using namespace ktb;
 extern "C" int ktb200_add_rmsnorm(void* residual, const void* delta, const void* weight, float eps, void* out, int n_tokens, int hidden, void* stream) {
     if (!residual || !weight || !out || n_tokens < 0 || hidden <= 0 || hidden % 2) { set_error("add_rmsnorm: bad argument (bf16, even hidden)"); return KTB200_EINVAL; }
     if (n_tokens == 0) return KTB200_OK;
-    add_rmsnorm_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)residual, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, eps,
-                                                                   (__nv_bfloat16*)out, hidden, hidden, hidden, hidden);
-    KTB_LAUNCH_CHECK();
+    KTB_CUDA_CHECK(launch_pdl(add_rmsnorm_kernel, dim3(n_tokens), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)residual, (const __nv_bfloat16*)delta,
+                              (const __nv_bfloat16*)weight, eps, (__nv_bfloat16*)out, hidden, (long)hidden, (long)hidden, (long)hidden));
+    count_launch();
     return KTB200_OK;
 }
 
@@ -108,10 +112,10 @@ extern "C" int ktb200_mla_prep(const void* q, int num_heads, int qk_nope_head_di
         return KTB200_EINVAL;
     }
     if (n_tokens <= 0) return KTB200_OK;
-    mla_prep_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)q, num_heads, qk_nope_head_dim + 64, qk_nope_head_dim,
-                                                                (const __nv_bfloat16*)kv_a_out, (const __nv_bfloat16*)kv_a_norm_weight, eps, cos, sin,
-                                                                (__nv_bfloat16*)kv_cache, page_size, page_idx, page_offset, (__nv_bfloat16*)q_pe_out);
-    KTB_LAUNCH_CHECK();
+    KTB_CUDA_CHECK(launch_pdl(mla_prep_kernel, dim3(n_tokens), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)q, num_heads, qk_nope_head_dim + 64,
+                              qk_nope_head_dim, (const __nv_bfloat16*)kv_a_out, (const __nv_bfloat16*)kv_a_norm_weight, eps, cos, sin, (__nv_bfloat16*)kv_cache,
+                              page_size, page_idx, page_offset, (__nv_bfloat16*)q_pe_out));
+    count_launch();
     return KTB200_OK;
 }
 
@@ -126,6 +130,8 @@ namespace ktb {
 __global__ void __launch_bounds__(256) absorb_q_kernel(const __nv_bfloat16* q, long q_head_stride, long q_tok_stride, const __nv_bfloat16* W, int D, int Cc,
                                                         __nv_bfloat16* out) {
     __shared__ float qs[512];
+    griddep_launch_dependents();
+    griddep_wait();
     const int h = blockIdx.y, t = blockIdx.z, heads = gridDim.y;
     const __nv_bfloat16* qrow = q + t * q_tok_stride + h * q_head_stride;
     for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = bf(qrow[i]);
@@ -145,6 +151,8 @@ __global__ void __launch_bounds__(256) absorb_q_kernel(const __nv_bfloat16* q, l
 
 // grid (V / 8, heads, tokens), 256 threads = 8 warps: warp w owns output v = 8 * blockIdx.x + w
 __global__ void __launch_bounds__(256) absorb_o_kernel(const __nv_bfloat16* lat, const __nv_bfloat16* W, int V, int Cc, __nv_bfloat16* out) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int h = blockIdx.y, t = blockIdx.z, heads = gridDim.y, lane = threadIdx.x & 31;
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (v >= V) return;
@@ -172,17 +180,17 @@ extern "C" int ktb200_mla_absorb_q(const void* q, long q_head_stride, long q_tok
                                    void* q_abs_out, int n_tokens, void* stream) {
     if (!q || !w_uk || !q_abs_out || num_heads <= 0 || nope_dim <= 0 || nope_dim > 512 || kv_lora_rank <= 0 || kv_lora_rank % 2) { set_error("mla_absorb_q: bad argument"); return KTB200_EINVAL; }
     if (n_tokens <= 0) return KTB200_OK;
-    ktb::absorb_q_kernel<<<dim3((kv_lora_rank + 511) / 512, num_heads, n_tokens), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)q, q_head_stride, q_token_stride, (const __nv_bfloat16*)w_uk, nope_dim, kv_lora_rank, (__nv_bfloat16*)q_abs_out);
-    KTB_LAUNCH_CHECK();
+    KTB_CUDA_CHECK(launch_pdl(ktb::absorb_q_kernel, dim3((kv_lora_rank + 511) / 512, num_heads, n_tokens), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)q,
+                              q_head_stride, q_token_stride, (const __nv_bfloat16*)w_uk, nope_dim, kv_lora_rank, (__nv_bfloat16*)q_abs_out));
+    count_launch();
     return KTB200_OK;
 }
 
 extern "C" int ktb200_mla_absorb_o(const void* attn_latent, const void* w_uv, int num_heads, int v_head_dim, int kv_lora_rank, void* out, int n_tokens, void* stream) {
     if (!attn_latent || !w_uv || !out || num_heads <= 0 || v_head_dim <= 0 || kv_lora_rank <= 0 || kv_lora_rank % 8) { set_error("mla_absorb_o: bad argument"); return KTB200_EINVAL; }
     if (n_tokens <= 0) return KTB200_OK;
-    ktb::absorb_o_kernel<<<dim3((v_head_dim + 7) / 8, num_heads, n_tokens), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn_latent, (const __nv_bfloat16*)w_uv,
-                                                                                                              v_head_dim, kv_lora_rank, (__nv_bfloat16*)out);
-    KTB_LAUNCH_CHECK();
+    KTB_CUDA_CHECK(launch_pdl(ktb::absorb_o_kernel, dim3((v_head_dim + 7) / 8, num_heads, n_tokens), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)attn_latent,
+                              (const __nv_bfloat16*)w_uv, v_head_dim, kv_lora_rank, (__nv_bfloat16*)out));
+    count_launch();
     return KTB200_OK;
 }

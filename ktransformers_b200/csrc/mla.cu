@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(kMlaThreads, 1) mla_decode_tc_kernel(const __g
     const int split = blockIdx.x, hg = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h0 = hg * kHG;
+    griddep_launch_dependents();
+    griddep_wait();          // q, the newest cache row and kv_len come from the kernels before this one
     int L = p.kv_len[b];
     if (L > p.max_pages * p.page_size) L = p.max_pages * p.page_size;
     const int ntiles = (L + kLT - 1) / kLT;
@@ -400,6 +402,8 @@ __global__ void __launch_bounds__(128) mla_merge_kernel(const float* o_part, con
                                                         __nv_bfloat16* out, float* lse_out) {
     __shared__ float ws[128];
     __shared__ float red[8];
+    griddep_launch_dependents();
+    griddep_wait();
     const int bh = blockIdx.x, b = bh / num_heads, h = bh % num_heads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float my = tid < num_splits ? lse_part[((long)b * num_splits + tid) * num_heads + h] : -INFINITY;   // num_splits <= 128
@@ -533,10 +537,11 @@ int ktb200_mla_decode(const ktb200_mla_params* q, void* stream) {
         attr_set[dev & 63] = true;
     }
     const int head_groups = (q->num_heads + kHG - 1) / kHG;
-    mla_decode_tc_kernel<<<dim3(splits, head_groups, q->batch), kMlaThreads, kMlaSmem, s>>>(map, p);
-    KTB_LAUNCH_CHECK();
-    mla_merge_kernel<<<q->batch * q->num_heads, 128, 0, s>>>(p.o_part, p.lse_part, splits, q->num_heads, (__nv_bfloat16*)q->out, q->lse_out);
-    KTB_LAUNCH_CHECK();
+    KTB_CUDA_CHECK(launch_pdl(mla_decode_tc_kernel, dim3(splits, head_groups, q->batch), dim3(kMlaThreads), (size_t)kMlaSmem, s, map, p));
+    count_launch();
+    KTB_CUDA_CHECK(launch_pdl(mla_merge_kernel, dim3(q->batch * q->num_heads), dim3(128), 0, s, (const float*)p.o_part, (const float*)p.lse_part, splits, q->num_heads,
+                              (__nv_bfloat16*)q->out, q->lse_out));
+    count_launch();
     return KTB200_OK;
 }
 

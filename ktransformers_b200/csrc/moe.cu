@@ -269,8 +269,8 @@ static int launch_dense_q4k(const RowsParams& p, int T, int device, cudaStream_t
         KTB_CUDA_CHECK(cudaFuncSetAttribute(dense_q4k_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         limit[device & 63] = smem;
     }
-    dense_q4k_kernel<SL><<<gx, W * 32, smem, stream>>>(d);
-    KTB_LAUNCH_CHECK();
+    KTB_CUDA_CHECK(launch_pdl(dense_q4k_kernel<SL>, dim3(gx), dim3(W * 32), smem, stream, d));
+    count_launch();
     return KTB200_OK;
 }
 

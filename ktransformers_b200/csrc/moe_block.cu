@@ -80,8 +80,6 @@ __device__ __forceinline__ void grid_wait(unsigned* counter, unsigned gen) {
 
 // Programmatic dependent launch: the next layer's launch is processed, and its CTAs start on SMs as they free up,
 // while the tail of this one still runs; everything that depends on the previous kernel comes after griddep_wait().
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void block_stamp(const BlockParams& p, int i) {
     if (p.trace && threadIdx.x == 0) {

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Host-side plumbing shared by all translation units: error string, launch counter, SM count.
 #include <cstdarg>
 #include <cstdio>
@@ -6,6 +7,11 @@
 #include "gemv_bulk.cuh"
 
 namespace ktb {
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("KTB200_PDL"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
