@@ -193,6 +193,43 @@ class RefCpuMoe:
                 f"at real shapes; tok/s = tokens/(58 x mean layer time)")
 
 
+def amx_baseline(seconds=6.0):
+    """The reference's AMX INT4 MoE (kt_kernel_ext.moe.AMXInt4_MOE, the "CPU-AMX" path of north_star) through the shimmed
+    build oracle/_ref/libktamx.so — only on hosts with AMX; otherwise says why not.  Build-host numbers: profiles/."""
+    try:
+        import numpy as np
+
+        from oracle.bindings import AmxRef, f32_to_bf16_bits
+        if not AmxRef.available():
+            return {"unavailable": AmxRef.why_unavailable(), "build_host_measurement": "profiles/r02_amx_baseline_buildhost.json"}
+        En = 16
+        rng = np.random.default_rng(0)
+        mk = lambda shape: f32_to_bf16_bits(rng.standard_normal(shape, dtype=np.float32))  # noqa: E731
+        g, u, d = mk((En, I, H)), mk((En, I, H)), mk((En, H, I))
+        x = f32_to_bf16_bits((rng.standard_normal((1, H)) / 100).astype(np.float32))
+        w = rng.random((1, K)).astype(np.float32)
+        out = np.zeros((1, H), np.uint16)
+        best = None
+        cap = host_threads()
+        for th in sorted({n for n in (4, 8, 16, 32, 64, cap) if n <= cap}):
+            amx = AmxRef.get(th)
+            h = amx.moe_create(En, K, H, I, g, u, d)
+            ids = [np.stack([rng.permutation(En)[:K]]).astype(np.int64) for _ in range(16)]
+            for i in range(3):
+                amx.moe_forward(h, ids[i], w, x, out)
+            t0 = time.perf_counter(); n = 0
+            while time.perf_counter() - t0 < seconds / 4:
+                amx.moe_forward(h, ids[n % 16], w, x, out); n += 1
+            dt = (time.perf_counter() - t0) / n
+            amx.moe_destroy(h)
+            if best is None or dt < best[1]:
+                best = (th, dt)
+        return {"value": 1.0 / (N_MOE_LAYERS * best[1]), "unit": "tok/s", "cores": best[0], "kind": "reference (shimmed numa/hwloc build)",
+                "ms_per_layer": best[1] * 1e3, "sample": f"AMXInt4_MOE, 1 token x 8-of-{En} experts at real shapes"}
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -758,7 +795,7 @@ def main():
         t_layer = (time.perf_counter() - t0) / n
         cpu_baseline = {"value": 1.0 / (N_MOE_LAYERS * t_layer), "unit": "tok/s", "cores": cpu.threads, "kind": cpu.kind,
                         "sample": cpu.describe(n), "ms_per_layer": t_layer * 1e3,
-                        "gbs": K * BYTES_PER_EXPERT / t_layer / 1e9}
+                        "gbs": K * BYTES_PER_EXPERT / t_layer / 1e9, "amx": amx_baseline()}
 
     if rank == 0:
         step_bytes = N_MOE_LAYERS * ((K + 1) * BYTES_PER_EXPERT + E * H * 4)

@@ -237,3 +237,58 @@ def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
     nan = (i & 0x7FFFFFFF) > 0x7F800000
     r = np.where(nan, ((i >> 16) | 64).astype(np.uint16), r)
     return r.astype(np.uint16)
+
+
+class AmxRef:
+    """The reference's AMX MoE backend (kt_kernel_ext.moe.AMXInt4_MOE) compiled UNMODIFIED from /root/reference through the
+    single-node numa/hwloc shim (oracle/amx_shim.cpp, oracle/amx_shim/*.h): the "CPU-AMX" baseline of BASELINE.json.
+    A SHIMMED build; runs only on hosts whose /proc/cpuinfo shows amx_tile + amx_int8."""
+
+    _inst = None
+
+    @staticmethod
+    def path() -> str:
+        return os.path.join(HERE, "_ref", "libktamx.so")
+
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.path()) and {"amx_tile", "amx_int8", "amx_bf16"} <= _cpu_flags()
+
+    @classmethod
+    def why_unavailable(cls) -> str:
+        if not os.path.exists(cls.path()):
+            return "oracle/_ref/libktamx.so not built (needs /root/reference)"
+        return "host CPU has no AMX (amx_tile / amx_int8 / amx_bf16 absent from /proc/cpuinfo)"
+
+    @classmethod
+    def get(cls, threads: int) -> "AmxRef":
+        if cls._inst is None:
+            cls._inst = cls()
+        cls._inst.threads = cls._inst.lib.ktamx_init(int(threads))
+        return cls._inst
+
+    def __init__(self):
+        self.lib = C.CDLL(self.path())
+        self.lib.ktamx_moe_create.restype = C.c_void_p
+        self.lib.ktamx_moe_create.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
+        self.lib.ktamx_moe_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.ktamx_moe_destroy.argtypes = [C.c_void_p]
+        self.threads = 0
+
+    def moe_create(self, E, k, H, I, gate_bf16: np.ndarray, up_bf16: np.ndarray, down_bf16: np.ndarray, max_len: int = 64):
+        """gate/up [E][I][H], down [E][H][I] as bf16 bit patterns (uint16); the backend quantises them to INT4 at load."""
+        self._keep = (np.ascontiguousarray(gate_bf16), np.ascontiguousarray(up_bf16), np.ascontiguousarray(down_bf16))
+        return self.lib.ktamx_moe_create(E, k, H, I, max_len, _p(self._keep[0]), _p(self._keep[1]), _p(self._keep[2]))
+
+    def moe_forward(self, h, ids: np.ndarray, weights: np.ndarray, x_bf16: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        qlen, k = ids.shape
+        ids = np.ascontiguousarray(ids, np.int64)
+        weights = np.ascontiguousarray(weights, np.float32)
+        x_bf16 = np.ascontiguousarray(x_bf16, np.uint16)
+        if out is None:
+            out = np.zeros_like(x_bf16)
+        self.lib.ktamx_moe_forward(h, qlen, k, _p(ids), _p(weights), _p(x_bf16), _p(out))
+        return out
+
+    def moe_destroy(self, h):
+        self.lib.ktamx_moe_destroy(h)

@@ -149,3 +149,32 @@ def test_mla_oracle_matches_reference_attention_ref_torch(golden_dir, name):
     mag = np.abs(want).max()
     assert np.abs(out - want).max() <= 2.0 ** -8 * mag * 1.01          # the reference rounds its output to bf16
     np.testing.assert_allclose(lse / np.log(2.0), lse2, rtol=0, atol=1e-4)
+
+
+def test_shimmed_amx_backend_runs_the_reference_int4_moe():
+    """oracle/_ref/libktamx.so: the reference's AMXInt4_MOE (kt-kernel/operators/amx) built through the numa/hwloc shim.
+    Checked like the reference's own accuracy test (kt-kernel test_moe_amx_accuracy_int4: relative mean error vs the fp32
+    restatement below 0.35 for INT4)."""
+    from oracle.bindings import AmxRef
+    if not AmxRef.available():
+        pytest.skip(AmxRef.why_unavailable())
+    amx = AmxRef.get(4)
+    rng = np.random.default_rng(0)
+    E, k, H, I = 8, 4, 1024, 512
+    g, u, d = (rng.standard_normal((E, I, H)).astype(np.float32), rng.standard_normal((E, I, H)).astype(np.float32),
+               rng.standard_normal((E, H, I)).astype(np.float32))
+    gb, ub, db = f32_to_bf16_bits(g), f32_to_bf16_bits(u), f32_to_bf16_bits(d)
+    h = amx.moe_create(E, k, H, I, gb, ub, db)
+    x = f32_to_bf16_bits((rng.standard_normal((2, H)) / 100).astype(np.float32))
+    ids = np.stack([rng.permutation(E)[:k] for _ in range(2)]).astype(np.int64)
+    w = rng.random((2, k)).astype(np.float32)
+    out = bf16_to_f32(amx.moe_forward(h, ids, w, x))
+    xf, gf, uf, df = bf16_to_f32(x), bf16_to_f32(gb), bf16_to_f32(ub), bf16_to_f32(db)
+    ref = np.zeros_like(xf)
+    for t in range(2):
+        for j in range(k):
+            e = ids[t, j]
+            a = gf[e] @ xf[t]
+            ref[t] += ((a / (1 + np.exp(-a))) * (uf[e] @ xf[t])) @ df[e].T * w[t, j]
+    assert np.abs(out - ref).mean() / np.abs(ref).mean() < 0.35
+    amx.moe_destroy(h)
