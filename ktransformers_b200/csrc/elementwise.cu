@@ -14,43 +14,59 @@
 
 namespace ktb {
 
-__device__ __forceinline__ float block_sum(float v, float* red) {
+__device__ __forceinline__ float block_sum(float v, float* red) {   // red: >= blockDim.x / 32 floats
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (lane == 0) red[warp] = v;
     __syncthreads();
-    float s = 0.f;
-    for (int w = 0; w < nw; w++) s += red[w];
+    float s = lane < nw ? red[lane] : 0.f;   // every warp adds the per-warp sums in the same (butterfly) order
+    s = warp_sum(s);
     __syncthreads();
     return s;
 }
 __device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
 
-// one CTA per row; H <= 8 * 1024 elements per thread loop
-__global__ void __launch_bounds__(256) add_rmsnorm_kernel(__nv_bfloat16* resid, const __nv_bfloat16* delta, const __nv_bfloat16* weight, float eps,
-                                                          __nv_bfloat16* out, int H, long resid_stride, long delta_stride, long out_stride) {
-    __shared__ float red[8];
+// one CTA of 1024 threads per row, ONE pass: a thread keeps its <= 4 bf16 pairs in registers (H <= 8192), so the row is
+// read once and the kernel is a single load -> block reduction -> store chain (it is launch-latency bound: 14 KB)
+constexpr int kNormThreads = 1024, kNormPairs = 4;
+__global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(__nv_bfloat16* resid, const __nv_bfloat16* delta, const __nv_bfloat16* weight, float eps,
+                                                                   __nv_bfloat16* out, int H, long resid_stride, long delta_stride, long out_stride) {
+    __shared__ float red[32];
     griddep_launch_dependents();
+    __nv_bfloat162 wv[kNormPairs];
+#pragma unroll
+    for (int j = 0; j < kNormPairs; j++) {   // the norm weight does not depend on the previous kernel
+        const int i = (threadIdx.x + j * kNormThreads) * 2;
+        if (i < H) wv[j] = *reinterpret_cast<const __nv_bfloat162*>(weight + i);
+    }
     griddep_wait();
     const long t = blockIdx.x;
     __nv_bfloat16* r = resid + t * resid_stride;
     const __nv_bfloat16* d = delta ? delta + t * delta_stride : nullptr;
+    __nv_bfloat162 v[kNormPairs];
     float ss = 0.f;
-    for (int i = threadIdx.x * 2; i < H; i += blockDim.x * 2) {
-        __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(r + i);
-        if (d) {
-            v = __hadd2(v, *reinterpret_cast<const __nv_bfloat162*>(d + i));   // the residual stream itself is bf16 (x = x + attn_out)
-            *reinterpret_cast<__nv_bfloat162*>(r + i) = v;
+#pragma unroll
+    for (int j = 0; j < kNormPairs; j++) {
+        const int i = (threadIdx.x + j * kNormThreads) * 2;
+        if (i < H) {
+            v[j] = *reinterpret_cast<const __nv_bfloat162*>(r + i);
+            if (d) {
+                v[j] = __hadd2(v[j], *reinterpret_cast<const __nv_bfloat162*>(d + i));   // the residual stream itself is bf16 (x = x + attn_out)
+                *reinterpret_cast<__nv_bfloat162*>(r + i) = v[j];
+            }
+            const float2 f = __bfloat1622float2(v[j]);
+            ss += f.x * f.x + f.y * f.y;
         }
-        const float2 f = __bfloat1622float2(v);
-        ss += f.x * f.x + f.y * f.y;
     }
     const float inv = rsqrtf(block_sum(ss, red) / (float)H + eps);
     __nv_bfloat16* o = out + t * out_stride;
-    for (int i = threadIdx.x * 2; i < H; i += blockDim.x * 2) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(r + i));
-        const __nv_bfloat162 hn = __floats2bfloat162_rn(f.x * inv, f.y * inv);
-        *reinterpret_cast<__nv_bfloat162*>(o + i) = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(weight + i), hn);
+#pragma unroll
+    for (int j = 0; j < kNormPairs; j++) {
+        const int i = (threadIdx.x + j * kNormThreads) * 2;
+        if (i < H) {
+            const float2 f = __bfloat1622float2(v[j]);
+            *reinterpret_cast<__nv_bfloat162*>(o + i) = __hmul2(wv[j], __floats2bfloat162_rn(f.x * inv, f.y * inv));
+        }
     }
 }
 
@@ -96,9 +112,9 @@ __global__ void __launch_bounds__(256) mla_prep_kernel(const __nv_bfloat16* q, i
 using namespace ktb;
 
 extern "C" int ktb200_add_rmsnorm(void* residual, const void* delta, const void* weight, float eps, void* out, int n_tokens, int hidden, void* stream) {
-    if (!residual || !weight || !out || n_tokens < 0 || hidden <= 0 || hidden % 2) { set_error("add_rmsnorm: bad argument (bf16, even hidden)"); return KTB200_EINVAL; }
+    if (!residual || !weight || !out || n_tokens < 0 || hidden <= 0 || hidden % 2 || hidden > 2 * kNormPairs * kNormThreads) { set_error("add_rmsnorm: bad argument (bf16, even hidden <= 8192)"); return KTB200_EINVAL; }
     if (n_tokens == 0) return KTB200_OK;
-    KTB_CUDA_CHECK(launch_pdl(add_rmsnorm_kernel, dim3(n_tokens), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)residual, (const __nv_bfloat16*)delta,
+    KTB_CUDA_CHECK(launch_pdl(add_rmsnorm_kernel, dim3(n_tokens), dim3(kNormThreads), 0, (cudaStream_t)stream, (__nv_bfloat16*)residual, (const __nv_bfloat16*)delta,
                               (const __nv_bfloat16*)weight, eps, (__nv_bfloat16*)out, hidden, (long)hidden, (long)hidden, (long)hidden));
     count_launch();
     return KTB200_OK;
@@ -126,27 +142,46 @@ extern "C" int ktb200_mla_prep(const void* q, int num_heads, int qk_nope_head_di
 //   mode 1  o[t][h][v]     = sum_c lat[t][h][c]   * W_UV[h][v][c]     W [heads][V][C] read along c (contiguous): one warp per (h, v)
 namespace ktb {
 
-// grid (C / 512, heads, tokens), 256 threads: thread owns columns c = 2 * tid + {0, 1} of this 512-column slab
+// grid (C / 512, heads, tokens), 256 threads = 4 groups of 64: a group owns a quarter of the d range, a thread 8 columns of
+// the 512-column slab (16-byte loads, 8 rows in flight); the four partial sums meet in shared memory in group order
 __global__ void __launch_bounds__(256) absorb_q_kernel(const __nv_bfloat16* q, long q_head_stride, long q_tok_stride, const __nv_bfloat16* W, int D, int Cc,
                                                         __nv_bfloat16* out) {
     __shared__ float qs[512];
+    __shared__ float part[4][512];
     griddep_launch_dependents();
     griddep_wait();
     const int h = blockIdx.y, t = blockIdx.z, heads = gridDim.y;
     const __nv_bfloat16* qrow = q + t * q_tok_stride + h * q_head_stride;
     for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = bf(qrow[i]);
     __syncthreads();
-    const int c = blockIdx.x * 512 + threadIdx.x * 2;
-    if (c >= Cc) return;
-    const __nv_bfloat16* w = W + ((long)h * D) * Cc + c;
-    float a0 = 0.f, a1 = 0.f;
+    const int grp = threadIdx.x >> 6, ct = threadIdx.x & 63;
+    const int c = blockIdx.x * 512 + ct * 8;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < Cc) {
+        const int dper = (D + 3) / 4, d0 = grp * dper, d1 = min(D, d0 + dper);
+        const __nv_bfloat16* w = W + ((long)h * D) * Cc + c;
 #pragma unroll 8
-    for (int d = 0; d < D; d++) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(w + (long)d * Cc));
-        a0 = fmaf(qs[d], f.x, a0);
-        a1 = fmaf(qs[d], f.y, a1);
+        for (int d = d0; d < d1; d++) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(w + (long)d * Cc);
+            const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            const float qd = qs[d];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float2 f = __bfloat1622float2(w2[i]);
+                a[2 * i] = fmaf(qd, f.x, a[2 * i]);
+                a[2 * i + 1] = fmaf(qd, f.y, a[2 * i + 1]);
+            }
+        }
     }
-    *reinterpret_cast<__nv_bfloat162*>(out + ((long)t * heads + h) * Cc + c) = __floats2bfloat162_rn(a0, a1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) part[grp][ct * 8 + i] = a[i];
+    __syncthreads();
+    const int cc = threadIdx.x * 2;
+    if (blockIdx.x * 512 + cc < Cc) {
+        const float s0 = (part[0][cc] + part[1][cc]) + (part[2][cc] + part[3][cc]);
+        const float s1 = (part[0][cc + 1] + part[1][cc + 1]) + (part[2][cc + 1] + part[3][cc + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(out + ((long)t * heads + h) * Cc + blockIdx.x * 512 + cc) = __floats2bfloat162_rn(s0, s1);
+    }
 }
 
 // grid (V / 8, heads, tokens), 256 threads = 8 warps: warp w owns output v = 8 * blockIdx.x + w
@@ -178,7 +213,7 @@ __global__ void __launch_bounds__(256) absorb_o_kernel(const __nv_bfloat16* lat,
 
 extern "C" int ktb200_mla_absorb_q(const void* q, long q_head_stride, long q_token_stride, const void* w_uk, int num_heads, int nope_dim, int kv_lora_rank,
                                    void* q_abs_out, int n_tokens, void* stream) {
-    if (!q || !w_uk || !q_abs_out || num_heads <= 0 || nope_dim <= 0 || nope_dim > 512 || kv_lora_rank <= 0 || kv_lora_rank % 2) { set_error("mla_absorb_q: bad argument"); return KTB200_EINVAL; }
+    if (!q || !w_uk || !q_abs_out || num_heads <= 0 || nope_dim <= 0 || nope_dim > 512 || kv_lora_rank <= 0 || kv_lora_rank % 8) { set_error("mla_absorb_q: bad argument"); return KTB200_EINVAL; }
     if (n_tokens <= 0) return KTB200_OK;
     KTB_CUDA_CHECK(launch_pdl(ktb::absorb_q_kernel, dim3((kv_lora_rank + 511) / 512, num_heads, n_tokens), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)q,
                               q_head_stride, q_token_stride, (const __nv_bfloat16*)w_uk, nope_dim, kv_lora_rank, (__nv_bfloat16*)q_abs_out));
