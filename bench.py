@@ -502,7 +502,11 @@ def main():
         native.check(lib.ktb200_mlp_load_weights(mh, S()))
         g = torch.Generator(device=dev); g.manual_seed(1000 * l + 9)
         Wr = torch.randn((E, H), device=dev, generator=g, dtype=torch.float32)
-        br = torch.randn((E,), device=dev, generator=g, dtype=torch.float32)
+        # e_score_correction_bias: a trained model's bias keeps the experts balanced; a randn bias (std 1 against sigmoid
+        # scores in 0.3..0.7) would send EVERY token to the same few experts — harmless at N = 1, a pathological 2x load
+        # imbalance for expert-parallel shards (measured: profiles/ep_trace_n8_r02.txt).  The reference's own MoE bench routes
+        # uniformly at random (kt-kernel/bench/bench_moe.py:235-239); a small bias keeps the routing token-dependent.
+        br = 0.01 * torch.randn((E,), device=dev, generator=g, dtype=torch.float32)
         gcfg = native.GateConfig(E, H, K, N_GROUP, TOPK_GROUP, 0, 0, 1, ROUTED_SCALE, Wr.data_ptr(), br.data_ptr(), BF16)
         layers.append(dict(moe=h, mlp=mh, gcfg=gcfg, keep=(gate, up, down, sg, su, sd, Wr, br)))
     if world == 1 and os.environ.get("KTB200_BENCH_PREFETCH", "0") != "0":

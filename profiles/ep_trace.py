@@ -36,7 +36,7 @@ for l in range(3):
     mlp = C.c_void_p(); native.check(lib.ktb200_mlp_create(H, I, sg.data_ptr(), su.data_ptr(), sd.data_ptr(), Q4_K, Q4_K, Q6_K, BF16, 8, lr, C.byref(mlp)))
     native.check(lib.ktb200_mlp_load_weights(mlp, S()))
     gen = torch.Generator(device=dev); gen.manual_seed(1000 * l + 9)
-    W = torch.randn(E, H, device=dev, generator=gen); b = torch.randn(E, device=dev, generator=gen)
+    W = torch.randn(E, H, device=dev, generator=gen); b = 0.01 * torch.randn(E, device=dev, generator=gen)   # balanced routing (see bench.py)
     gc = native.GateConfig(E, H, K, 8, 4, 0, 0, 1, 2.5, W.data_ptr(), b.data_ptr(), BF16)
     layers.append((gc, moe, mlp, (g, u, d, sg, su, sd, W, b)))
 ex = PeerExchange(H, BF16, dev)
