@@ -678,6 +678,7 @@ __global__ void __launch_bounds__(kBlockWarpsLo * 32, 1) moe_ep_block_kernel(con
         for (int i = threadIdx.x; i < (int)(sizeof(EpExtra) / 4); i += blockDim.x) dst2[i] = src2[i];
     }
     if (threadIdx.x == 0 && has_shared) sh.vs[0] = k;
+    __syncthreads();   // the parameter copies in shared memory (read by blk_router & co through sh.prm) and the mbarriers are ready
     uint32_t phase = 0;
     unsigned gen = 0;
     const uint8_t* ring = smem + (ring_u32 - (uint32_t)__cvta_generic_to_shared(smem));
