@@ -25,3 +25,22 @@ for r in rows[2:]:
             print(f"| {m} | {r[idx[m]]} | {units[idx[m]]} |")
     st = sorted(((float(r[idx[h]] or 0), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for h in stalls), reverse=True)[:6]
     print("\nwarps stalled per issue (top): " + ", ".join(f"{n} {v:.2f}" for v, n in st) + "\n")
+
+# dram traffic per launch of every captured kernel -> profiles/traffic.json (bench.py reads it for `roofline.traffic`)
+import json
+import os
+tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
+try:
+    traffic = json.load(open(tj))
+except Exception:
+    traffic = {}
+def _bytes(v, u):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+for r in rows[2:]:
+    name = r[idx["Kernel Name"]].split("<")[0].split("(")[0].strip().split("::")[-1]
+    if "dram__bytes_read.sum" in idx and r[idx["dram__bytes_read.sum"]] != "":
+        rd = _bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+        wr = _bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        traffic[name] = {"dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "source": os.path.basename(rep)}
+json.dump(traffic, open(tj, "w"), indent=1)
