@@ -38,7 +38,7 @@ def _bytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 for r in rows[2:]:
-    name = r[idx["Kernel Name"]].split("<")[0].split("(")[0].strip().split("::")[-1]
+    name = r[idx["Kernel Name"]].split("<")[0].split("(")[0].strip().split("::")[-1].replace("void ", "")
     if "dram__bytes_read.sum" in idx and r[idx["dram__bytes_read.sum"]] != "":
         rd = _bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
         wr = _bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
