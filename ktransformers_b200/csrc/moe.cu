@@ -568,6 +568,17 @@ int ktb200_moe_load_weights(ktb200_moe* m, void* stream) {
 
 float* ktb200_moe_intermediate(ktb200_moe* m) { return m ? m->inter : nullptr; }
 
+namespace ktb {
+bool grouped_ok(const ktb200_moe* m, int k);
+int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input, void* output, const int* bsz, cudaStream_t s);
+}
+// qlen from which the per-expert tensor-core GEMMs (grouped.cu) replace the per-pair GEMV kernels: the reference makes the
+// same split between MOE::forward_one and MOE::forward_many (moe.cpp:367-377, threshold group_min_len)
+static int grouped_min_qlen() {
+    static const int v = [] { const char* e = getenv("KTB200_GROUPED_MIN"); return e ? atoi(e) : 48; }();
+    return v;
+}
+
 static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input,
                             void* output, const int* bsz, cudaStream_t s, cudaEvent_t mid, const ktb200_mlp* sh = nullptr,
                             int shared_token = -1, void* shared_out = nullptr) {
@@ -580,6 +591,11 @@ static int moe_forward_impl(ktb200_moe* m, int qlen, int k, const int64_t* ids, 
     if (!ids || !weights || !input || !output) { set_error("forward: null pointer"); return KTB200_EINVAL; }
     DeviceGuard g(m->device);
 
+    if (!mid && !shared_out && grouped_min_qlen() > 0 && qlen >= grouped_min_qlen() && grouped_ok(m, k)) {
+        int rc = moe_forward_grouped(m, qlen, k, ids, weights, input, output, bsz, s);
+        if (rc || !sh) return rc;
+        return ktb200_mlp_forward(const_cast<ktb200_mlp*>(sh), qlen, input, output, 1, bsz, (void*)s);
+    }
     FmtId fg = pick_fmt(c.gate_type, m->gu_soa), fu = pick_fmt(c.up_type, m->gu_soa);
     if (fg != fu) fg = fu = FMT_GENK;  // mixed gate/up types: the generic path reads the type per matrix
     RowsParams rp{};

@@ -664,3 +664,55 @@ def test_v3_full_shape_relu_scaling_is_bit_exact():
     c = m.forward(ids, 2 * w, x)
     assert np.array_equal(c, 2 * a)
     m.close()
+
+
+# ------------------------------------------------------------------------------------------ grouped (prefill) path
+@pytest.mark.parametrize("dt,E,k,H,I", [(Q6_K, 8, 4, 1024, 512), (Q4_K, 8, 4, 1024, 512), (Q6_K, 6, 6, 2048, 1536), (Q6_K, 16, 8, 7168, 2048)])
+@pytest.mark.parametrize("hid", [F32, BF16])
+def test_moe_grouped_tensor_core_path_vs_oracle(oracle, dt, E, k, H, I, hid):
+    """qlen >= KTB200_GROUPED_MIN takes MOE::forward_many's shape (moe.cpp:248-365): per-expert GEMMs on tcgen05 with operands
+    that hold the reference's integers exactly.  Same oracle, same tolerances as the per-pair kernels, and the launch count proves
+    the grouped kernels ran (8 per chunk)."""
+    gate, up, down = _synth(Q4_K, E * I * H, 21), _synth(Q4_K, E * I * H, 22), _synth(dt, E * H * I, 23)
+    g_np, u_np, d_np = gate.cpu().numpy(), up.cpu().numpy(), down.cpu().numpy()
+    m = G.Moe(E, k, H, I, gate, up, down, Q4_K, Q4_K, dt, hid, max_tokens=512)
+    rng = np.random.default_rng(E * 1000 + H + dt)
+    for qlen in ((101,) if H >= 7168 else (48, 131, 300)):
+        x = (rng.standard_normal((qlen, H)) / 100).astype(np.float32)
+        ids = np.stack([rng.permutation(E)[:k] for _ in range(qlen)]).astype(np.int64)
+        if qlen > 100:
+            ids[5:90, 0] = 1          # a crowded expert: several 32-token tiles, duplicates inside a token
+            ids[7, :] = [-1, E, 1 << 40, -7][:k] + [0] * max(0, k - 4)   # invalid ids are skipped
+            ids[ids == 2] = 3         # an expert nobody picks
+        w = rng.random((qlen, k)).astype(np.float32)
+        xin = x if hid == F32 else f32_to_bf16_bits(x)
+        n0 = native.launch_count()
+        got = m.forward(ids, w, xin)
+        assert native.launch_count() - n0 == 8, "the grouped path did not run"
+        want = oracle.moe_forward(E, H, I, g_np, u_np, d_np, Q4_K, Q4_K, dt, hid, ids, w, xin)
+        if hid == F32:
+            assert relmax(got, want) < FP_TOL, f"qlen={qlen}"
+        else:
+            assert_bf16_close(got, want)
+    # device-side batch size: rows >= bsz untouched, rows < bsz identical
+    sentinel = torch.full((qlen, H), 7.0, device="cuda", dtype=torch.float32 if hid == F32 else torch.bfloat16)
+    got3 = m.forward(ids, w, xin, bsz=50, out=sentinel)
+    assert np.array_equal(got3[:50], got[:50]) and (sentinel[50:] == 7.0).all()
+    m.close()
+
+
+def test_moe_grouped_matches_per_pair_kernels():
+    """The integer dot of a super-block is the same number whichever kernel computes it (Q4_K everywhere: no fp16 rounding can
+    occur below 2048); what differs is the fp32 order in which the per-block terms are added (lanes vs sequential)."""
+    E, k, H, I = 8, 4, 2048, 768
+    gate, up, down = _synth(Q4_K, E * I * H, 31), _synth(Q4_K, E * I * H, 32), _synth(Q4_K, E * H * I, 33)
+    m = G.Moe(E, k, H, I, gate, up, down, Q4_K, Q4_K, Q4_K, F32, max_tokens=256)
+    rng = np.random.default_rng(9)
+    qlen = 200
+    x = (rng.standard_normal((qlen, H)) / 100).astype(np.float32)
+    ids = np.stack([rng.permutation(E)[:k] for _ in range(qlen)]).astype(np.int64)
+    w = rng.random((qlen, k)).astype(np.float32)
+    big = m.forward(ids, w, x)
+    small = np.concatenate([m.forward(ids[i:i + 25], w[i:i + 25], x[i:i + 25]) for i in range(0, qlen, 25)])
+    assert relmax(big, small) < 1e-5
+    m.close()
