@@ -4,19 +4,22 @@
 //     per-expert GEMM (gate, up) -> silu * mul -> requantise -> per-expert GEMM (down) -> per-token weighted gather.
 // The decode kernels stream every (token, expert) pair's weights; here an expert's weights are read ONCE per 32-token tile.
 //
-// Arithmetic.  The reference's dot is an exact integer: sum_j sc_j * sum_{32} q * x8 per super-block, scaled in fp32.  The
-// tensor cores get operands that hold those integers EXACTLY in fp16: A = sc_j * q (<= 63 * 15 for Q4_K; sc * (q - 32) for
-// Q6_K), B = the Q8_K activation bytes; tcgen05.mma kind::f16 accumulates their products in fp32 (every product and every
-// partial sum of a 256-long block is an integer < 2^25: exact up to one final rounding), one accumulator per SUPER-BLOCK;
-// the epilogue applies (d_w * d_x) * isum - (dmin_w * d_x) * msum in fp32 exactly like the decode kernels.  msum (Q4_K mins x
-// activation block sums) is a second K = 16 MMA on [m_j] x [bsum16].  Q6_K: |sc * (q - 32)| can reach 4096 and fp16 holds
-// integers exactly to 2048 (even ones to 4096): the rare odd product above 2048 moves one element by 2^-12 relative.
+// Arithmetic: the reference's dot is an exact integer per super-block — sum_j sc_j * (sum over sub-block j of q * x8) — scaled in
+// fp32.  The integer tensor path (tcgen05.mma kind::i8, s32 accumulators in TMEM) computes the INNER sums exactly: one MMA of
+// K = 32 per Q4_K sub-block (A = the raw 4-bit quants as u8, B = the Q8_K activation bytes), its own accumulator per sub-block;
+// Q6_K sub-blocks are 16 long, so one K = 32 MMA covers two of them against a B operand of 64 rows — the 32 tokens with the odd
+// sub-block zeroed, then the 32 tokens with the even one zeroed.  The epilogue multiplies every accumulator by its 6/8-bit
+// sub-block scale in int32, converts ONCE per super-block and applies (d_w * d_x) * isum - (dmin_w * d_x) * msum in fp32, the
+// decode kernels' formula; msum (Q4_K mins x activation block sums) is one K = 16 fp16 MMA of exact small integers.
+// Nothing is rounded that the reference does not round.
 //
-// Kernel (grouped_gemm_kernel): persistent CTAs, tile = (expert, 128 weight rows, 32 tokens), 13 warps:
-//     warps 0-7   producers: weights (global, 16-byte loads) -> fp16 A tile in the K-major 128-byte-swizzle layout; activations
-//                 (int8 SoA rows gathered through the sorted pair list) -> fp16 B tile; mins / block sums -> the small A2 / B2 tiles
-//     warp  8     tcgen05 issuer: 16 MMAs (128 x 32 x 16) + 1 per super-block into TMEM, two stages
-//     warps 9-12  epilogue: tcgen05.ld of the two accumulators, fp32 scale-and-add into registers, store at the end of the tile
+// grouped_gemm_kernel: persistent CTAs, tile = (expert, 128 weight rows, 32 tokens), stage = half a super-block (128 of K):
+//     warps 0-3    producers (one weight row per thread): weights (global, 16-byte loads, next stage prefetched in registers) -> int8 A tile in the K-major
+//                  128-byte-swizzle layout (Q4_K: nibble split; Q6_K: 4 + 2 bit merge, -32); activation rows gathered through the
+//                  sorted pair list -> B tile; row headers (scales, d, dmin) and token scales for the epilogue
+//     warp  4      tcgen05 issuer: 4 integer MMAs per stage (+ the mins MMA on the second half), 4 shared-memory stages,
+//                  2 TMEM buffers of 256 columns
+//     warps 5-12   epilogue: tcgen05.ld, int32 scale-and-add, fp32 finish per super-block, stores at the end of the tile
 #include <cuda_fp16.h>
 
 #include "act_quant.cuh"
@@ -28,17 +31,18 @@ namespace ktb {
 
 using namespace umma;
 
-constexpr int kGM = 128, kGN = 32, kGThreads = 13 * 32, kGProd = 256;
-constexpr int kGA = 4 * kGM * 128;        // 65,536: 4 swizzle atoms of 128 rows x 128 B per super-block
-constexpr int kGB = 4 * kGN * 128;        // 16,384
+constexpr int kGM = 128, kGN = 32, kGStages = 4;
+constexpr int kGProdWarps = 4, kGEpiWarps = 8, kGThreads = (kGProdWarps + 1 + kGEpiWarps) * 32;   // 13 warps: at most 4 per scheduler, 128 registers each
+constexpr int kGA = kGM * 128;            // 16,384: 128 rows x 128 int8 of K, one swizzle atom column
+constexpr int kGB = 2 * kGN * 128;        //  8,192: 32 rows (Q4_K) or 64 rows (Q6_K even / odd variants)
 constexpr int kGA2 = kGM * 32, kGB2 = kGN * 32;
-constexpr int kOffB = 2 * kGA, kOffA2 = kOffB + 2 * kGB, kOffB2 = kOffA2 + 2 * kGA2, kOffMiscG = kOffB2 + 2 * kGB2;
+constexpr int kOffB = kGStages * kGA, kOffA2 = kOffB + kGStages * kGB, kOffB2 = kOffA2 + kGStages * kGA2, kOffMiscG = kOffB2 + kGStages * kGB2;
 
 struct GrpMisc {
-    unsigned long long ab_full[2], d_full[2], stage_free[2];
-    uint32_t tmem_base;
-    float dxs[2][kGN];
-    float2 rowsc[2][kGM];
+    unsigned long long ab_full[kGStages], smem_free[kGStages], tmem_full[2], tmem_free[2];
+    uint32_t tmem_base, pad[3];
+    float dxs[kGStages][kGN];
+    uint4 hdr[kGStages][kGM];   // Q4_K: the block header (d, dmin, 12 scale bytes); Q6_K: 8 scales of the half, d as f32
 };
 constexpr int kGSmem = kOffMiscG + (int)sizeof(GrpMisc) + 1024;
 
@@ -64,7 +68,164 @@ __device__ __forceinline__ uint32_t h2(int a, int b) {
     const __half2 v = __halves2half2(__int2half_rn(a), __int2half_rn(b));
     return *reinterpret_cast<const uint32_t*>(&v);
 }
+// the 6-bit (scale, min) pair j of a Q4_K header held as 4 words (get_scale_min_k4, ggml-quants.c)
+__device__ __forceinline__ void q4k_scale_min(const uint32_t* hw, int j, int& sc, int& mn) {
+    if (j < 4) { sc = ub(hw, 4 + j) & 63; mn = ub(hw, 8 + j) & 63; }
+    else { sc = (ub(hw, 8 + j) & 0xF) | ((ub(hw, j) >> 6) << 4); mn = (ub(hw, 8 + j) >> 4) | ((ub(hw, 4 + j) >> 6) << 4); }
+}
 
+// what one producer thread fetches for one stage
+template <int FMT>
+struct GrpFetch {
+    uint4 w[FMT == 0 ? 4 : 6];   // Q4_K: 64 bytes of qs;  Q6_K: 64 of ql, 32 of qh  (the row's share of this half super-block)
+    uint4 hdr;                   // Q4_K: block header;    Q6_K: .x.y = the 8 scales of this half, .z = d (fp16 bits)
+    uint4 b[2];                  // activation pieces
+};
+
+struct GrpTile {
+    int e, m0, p0, n_valid;
+    const uint8_t* we;
+};
+
+__device__ __forceinline__ GrpTile grp_tile(const GrpGemmParams& p, int tile, int MT) {
+    // tile -> (expert, row tile, token tile); token tile fastest: CTAs running side by side share the weight tile through L2
+    int lo = 0, hi = p.E;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.nt_prefix[mid] * MT <= tile) lo = mid; else hi = mid;
+    }
+    GrpTile t;
+    t.e = lo;
+    const int local = tile - p.nt_prefix[lo] * MT, ntile_e = p.nt_prefix[lo + 1] - p.nt_prefix[lo];
+    const int mt = local / ntile_e, nt = local - mt * ntile_e;
+    t.m0 = mt * kGM;
+    t.p0 = p.offsets[lo] + nt * kGN;
+    t.n_valid = min(kGN, p.offsets[lo + 1] - t.p0);
+    t.we = p.w + (long)lo * p.expert_bytes;
+    return t;
+}
+
+template <int FMT>
+__device__ __forceinline__ void grp_fetch(const GrpGemmParams& p, const GrpTile& t, int st, int r, int nblk, GrpFetch<FMT>& f) {
+    const int sb = st >> 1, hh = st & 1;
+    if (FMT == 0) {
+        const uint8_t* blk = t.we + ((long)(t.m0 + r) * nblk + sb) * SZ_Q4_K;
+        f.hdr = __ldg(reinterpret_cast<const uint4*>(blk));
+#pragma unroll
+        for (int i = 0; i < 4; i++) f.w[i] = ldg_stream16(blk + 16 + hh * 64 + i * 16);
+    } else {
+        const int row = t.m0 + r, rw = row & 3, nrb = 4 * nblk, fi = rw * nblk + sb;
+        const uint8_t* item = t.we + (long)(row >> 2) * nrb * SZ_Q6_K;
+#pragma unroll
+        for (int i = 0; i < 4; i++) f.w[i] = ldg_stream16(item + (long)(4 * hh + i) * nrb * 16 + fi * 16);
+#pragma unroll
+        for (int i = 0; i < 2; i++) f.w[4 + i] = ldg_stream16(item + (long)nrb * 128 + (long)(2 * hh + i) * nrb * 16 + fi * 16);
+        const uint2 sc = __ldg(reinterpret_cast<const uint2*>(item + (long)nrb * 192 + fi * 16 + hh * 8));
+        f.hdr = make_uint4(sc.x, sc.y, ldg_u16(item + (long)nrb * 208 + fi * 2), 0);
+    }
+    // activation pieces: 32 rows x 8 pieces of 16 bytes = 256 = two per thread
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int id = r + u * kGM, n = id >> 3, pc = id & 7;
+        f.b[u] = make_uint4(0, 0, 0, 0);
+        if (n < t.n_valid) {
+            const int row = p.rowmap ? p.rowmap[t.p0 + n] : t.p0 + n;
+            f.b[u] = *reinterpret_cast<const uint4*>(p.xq + (long)row * p.Kc + st * 128 + pc * 16);
+        }
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ void grp_store(const GrpGemmParams& p, const GrpTile& t, int st, int r, int nblk, const GrpFetch<FMT>& f, uint8_t* smem, GrpMisc& misc,
+                                          int stage) {
+    const int sb = st >> 1, hh = st & 1;
+    uint8_t* arow = smem + stage * kGA + r * 128;
+    const int sw = r & 7;
+    if (FMT == 0) {
+        // chunk c = 2 hh + part (32 bytes of qs): low nibbles = sub-block 2c (elements 64c .. 64c+31), high nibbles = sub-block 2c+1
+#pragma unroll
+        for (int part = 0; part < 2; part++) {
+            const uint4 q0 = f.w[2 * part], q1 = f.w[2 * part + 1];
+            const int pi = 4 * part;
+            *reinterpret_cast<uint4*>(arow + (((pi + 0) ^ sw) << 4)) = make_uint4(q0.x & 0x0F0F0F0Fu, q0.y & 0x0F0F0F0Fu, q0.z & 0x0F0F0F0Fu, q0.w & 0x0F0F0F0Fu);
+            *reinterpret_cast<uint4*>(arow + (((pi + 1) ^ sw) << 4)) = make_uint4(q1.x & 0x0F0F0F0Fu, q1.y & 0x0F0F0F0Fu, q1.z & 0x0F0F0F0Fu, q1.w & 0x0F0F0F0Fu);
+            *reinterpret_cast<uint4*>(arow + (((pi + 2) ^ sw) << 4)) =
+                make_uint4((q0.x >> 4) & 0x0F0F0F0Fu, (q0.y >> 4) & 0x0F0F0F0Fu, (q0.z >> 4) & 0x0F0F0F0Fu, (q0.w >> 4) & 0x0F0F0F0Fu);
+            *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) =
+                make_uint4((q1.x >> 4) & 0x0F0F0F0Fu, (q1.y >> 4) & 0x0F0F0F0Fu, (q1.z >> 4) & 0x0F0F0F0Fu, (q1.w >> 4) & 0x0F0F0F0Fu);
+        }
+        misc.hdr[stage][r] = f.hdr;
+        if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
+            const uint32_t hw[4] = {f.hdr.x, f.hdr.y, f.hdr.z, f.hdr.w};
+            int sc, mn[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) q4k_scale_min(hw, j, sc, mn[j]);
+            uint8_t* a2 = smem + kOffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(a2) = make_uint4(h2(mn[0], mn[0]), h2(mn[1], mn[1]), h2(mn[2], mn[2]), h2(mn[3], mn[3]));
+            *reinterpret_cast<uint4*>(a2 + 128) = make_uint4(h2(mn[4], mn[4]), h2(mn[5], mn[5]), h2(mn[6], mn[6]), h2(mn[7], mn[7]));
+        }
+    } else {
+        // element 32 g + l of the half (l = 16 part + 0..15): g = 0 ql[l] & 15 | (qh & 3) << 4, g = 1 ql[32 + l] & 15 | (qh >> 2 & 3) << 4,
+        // g = 2 ql[l] >> 4 | (qh >> 4 & 3) << 4, g = 3 ql[32 + l] >> 4 | (qh >> 6 & 3) << 4; stored as q - 32 in int8
+#pragma unroll
+        for (int part = 0; part < 2; part++) {
+            const uint4 wa = f.w[part], wb = f.w[2 + part], wh = f.w[4 + part];
+            const uint32_t a[4] = {wa.x, wa.y, wa.z, wa.w}, b[4] = {wb.x, wb.y, wb.z, wb.w}, h[4] = {wh.x, wh.y, wh.z, wh.w};
+            uint32_t v[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                v[0][i] = (a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u);
+                v[1][i] = (b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u);
+                v[2][i] = ((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u);
+                v[3][i] = ((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {   // q - 32 per byte: flip bit 5, then copy it into bits 6 and 7 (no carries between bytes)
+                    const uint32_t tt = v[g][i] ^ 0x20202020u;
+                    v[g][i] = tt + (tt & 0x20202020u) * 6u;
+                }
+                *reinterpret_cast<uint4*>(arow + (((2 * g + part) ^ sw) << 4)) = make_uint4(v[g][0], v[g][1], v[g][2], v[g][3]);
+            }
+        }
+        misc.hdr[stage][r] = make_uint4(f.hdr.x, f.hdr.y, __float_as_uint(fp16_bits_to_f32((uint16_t)f.hdr.z)), 0);
+    }
+    // activations
+    uint8_t* Bs = smem + kOffB + stage * kGB;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int id = r + u * kGM, n = id >> 3, pc = id & 7;
+        if (FMT == 0) {
+            *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = f.b[u];
+        } else {   // a 16-byte piece is one Q6_K sub-block: rows 0-31 keep the even pieces, rows 32-63 the odd ones
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? z : f.b[u];
+            *reinterpret_cast<uint4*>(Bs + (kGN + n) * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? f.b[u] : z;
+        }
+    }
+    if (hh == 1 && r < 64) {   // token scales, and (Q4_K) the sixteen 16-value sums of the super-block as fp16
+        const int n2 = r >> 1, kg = r & 1;
+        uint4 vv = make_uint4(0, 0, 0, 0);
+        float dx = 0.f;
+        if (n2 < t.n_valid) {
+            const int row = p.rowmap ? p.rowmap[t.p0 + n2] : t.p0 + n2;
+            dx = p.xd[(long)row * nblk + sb];
+            if (FMT == 0) {
+                const uint4 bv = *reinterpret_cast<const uint4*>(p.xbs + (long)row * (p.Kc / 16) + sb * 16 + kg * 8);
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#define KTB_S16(w, hi) ((int)(short)((hi) ? ((w) >> 16) : ((w) & 0xffffu)))
+                vv = make_uint4(h2(KTB_S16(bw[0], 0), KTB_S16(bw[0], 1)), h2(KTB_S16(bw[1], 0), KTB_S16(bw[1], 1)), h2(KTB_S16(bw[2], 0), KTB_S16(bw[2], 1)),
+                                h2(KTB_S16(bw[3], 0), KTB_S16(bw[3], 1)));
+#undef KTB_S16
+            }
+        }
+        if (kg == 0) misc.dxs[stage][n2] = dx;
+        if (FMT == 0) *reinterpret_cast<uint4*>(smem + kOffB2 + stage * kGB2 + (n2 >> 3) * 256 + kg * 128 + (n2 & 7) * 16) = vv;
+    }
+}
+
+template <int FMT>
 __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -72,210 +233,134 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
     uint8_t* smem = smem_raw + (base - raw);
     GrpMisc& misc = *reinterpret_cast<GrpMisc*>(smem + kOffMiscG);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nblk = p.Kc / QK_K, MT = p.R / kGM;
+    const int nblk = p.Kc / QK_K, nst = 2 * nblk, MT = p.R / kGM;
     if (tid == 0) {
-        for (int s = 0; s < 2; s++) { bar_init(smem_u32(&misc.ab_full[s]), 8); bar_init(smem_u32(&misc.d_full[s]), 1); bar_init(smem_u32(&misc.stage_free[s]), 4); }
+        for (int s = 0; s < kGStages; s++) { bar_init(smem_u32(&misc.ab_full[s]), kGProdWarps); bar_init(smem_u32(&misc.smem_free[s]), 1 + kGEpiWarps); }
+        for (int b = 0; b < 2; b++) { bar_init(smem_u32(&misc.tmem_full[b]), 1); bar_init(smem_u32(&misc.tmem_free[b]), kGEpiWarps); }
         bar_fence_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(&misc.tmem_base), 128);
+    if (warp == kGProdWarps) tmem_alloc(smem_u32(&misc.tmem_base), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = misc.tmem_base;
     const int total_tiles = p.nt_prefix[p.E] * MT;
-    unsigned it = 0;   // super-block iterations done by this CTA: stage = it & 1, use = it >> 1
+    unsigned it = 0;   // stages done by this CTA: smem stage = it % kGStages, TMEM buffer = it & 1
 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        // tile -> (expert, row tile, token tile); token tile fastest: concurrently running CTAs share the weight tile through L2
-        int lo = 0, hi = p.E;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (p.nt_prefix[mid] * MT <= tile) lo = mid; else hi = mid;
-        }
-        const int e = lo;
-        const int local = tile - p.nt_prefix[e] * MT, ntile_e = p.nt_prefix[e + 1] - p.nt_prefix[e];
-        const int mt = local / ntile_e, nt = local - mt * ntile_e;
-        const int m0 = mt * kGM;
-        const int p0 = p.offsets[e] + nt * kGN;
-        const int n_valid = min(kGN, p.offsets[e + 1] - p0);
-        const uint8_t* we = p.w + (long)e * p.expert_bytes;
-
-        if (warp < 8) {
+        const GrpTile t = grp_tile(p, tile, MT);
+        if (warp < kGProdWarps) {
             // ====================================================================== producers
-            const int pt = tid;
-            for (int sb = 0; sb < nblk; sb++, it++) {
-                const int stage = it & 1;
-                bar_wait(smem_u32(&misc.stage_free[stage]), ((it >> 1) & 1) ^ 1);
-                uint8_t* As = smem + stage * kGA;
-                uint8_t* Bs = smem + kOffB + stage * kGB;
-                const int r = pt >> 1;
-                if (p.fmt == 0) {
-                    // Q4_K: thread = (row, two 64-element chunks); chunk c is exactly one 128-byte swizzle row of atom c
-                    const uint8_t* blk = we + ((long)(m0 + r) * nblk + sb) * SZ_Q4_K;
-                    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(blk));
-                    const uint32_t hw[4] = {hdr.x, hdr.y, hdr.z, hdr.w};   // bytes 4..15: the 12 packed 6-bit scales / mins
-                    int sc[8], mn[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        if (j < 4) { sc[j] = ub(hw, 4 + j) & 63; mn[j] = ub(hw, 8 + j) & 63; }
-                        else { sc[j] = (ub(hw, 8 + j) & 0xF) | ((ub(hw, j) >> 6) << 4); mn[j] = (ub(hw, 8 + j) >> 4) | ((ub(hw, 4 + j) >> 6) << 4); }
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < 2; cc++) {
-                        const int c = (pt & 1) * 2 + cc;
-                        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(blk + 16 + c * 32)), q1 = __ldg(reinterpret_cast<const uint4*>(blk + 32 + c * 32));
-                        const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                        uint8_t* arow = As + c * (kGM * 128) + r * 128;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {   // piece i: elements 8i..8i+7 of the chunk; i < 4 low nibbles (sub-block 2c), else high (2c+1)
-                            const int s_ = sc[2 * c + (i >> 2)];
-                            const uint32_t w0 = qw[2 * (i & 3)], w1 = qw[2 * (i & 3) + 1];
-                            const int sh = (i >> 2) * 4;
-                            uint4 v;
-                            v.x = h2(s_ * (int)((w0 >> sh) & 15), s_ * (int)((w0 >> (8 + sh)) & 15));
-                            v.y = h2(s_ * (int)((w0 >> (16 + sh)) & 15), s_ * (int)((w0 >> (24 + sh)) & 15));
-                            v.z = h2(s_ * (int)((w1 >> sh) & 15), s_ * (int)((w1 >> (8 + sh)) & 15));
-                            v.w = h2(s_ * (int)((w1 >> (16 + sh)) & 15), s_ * (int)((w1 >> (24 + sh)) & 15));
-                            *reinterpret_cast<uint4*>(arow + ((i ^ (r & 7)) << 4)) = v;
-                        }
-                    }
-                    if ((pt & 1) == 0) {
-                        const __half2 dm = *reinterpret_cast<const __half2*>(&hdr.x);
-                        misc.rowsc[stage][r] = make_float2(__low2float(dm), __high2float(dm));
-                    } else {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
-                        uint8_t* a2 = smem + kOffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16;
-                        *reinterpret_cast<uint4*>(a2) = make_uint4(h2(mn[0], mn[0]), h2(mn[1], mn[1]), h2(mn[2], mn[2]), h2(mn[3], mn[3]));
-                        *reinterpret_cast<uint4*>(a2 + 128) = make_uint4(h2(mn[4], mn[4]), h2(mn[5], mn[5]), h2(mn[6], mn[6]), h2(mn[7], mn[7]));
-                    }
-                } else {
-                    // Q6_K in 4-row tiles: thread = (row, 128-element half)
-                    const int hh = pt & 1;
-                    const int row = m0 + r, rw = row & 3, nrb = 4 * nblk, f = rw * nblk + sb;
-                    const uint8_t* item = we + (long)(row >> 2) * nrb * SZ_Q6_K;
-                    uint32_t ql[16], qh[8];
-#pragma unroll
-                    for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(ql + 4 * c) = __ldg(reinterpret_cast<const uint4*>(item + (long)(4 * hh + c) * nrb * 16 + f * 16));
-#pragma unroll
-                    for (int c = 0; c < 2; c++) *reinterpret_cast<uint4*>(qh + 4 * c) = __ldg(reinterpret_cast<const uint4*>(item + (long)nrb * 128 + (long)(2 * hh + c) * nrb * 16 + f * 16));
-                    const uint4 scv = __ldg(reinterpret_cast<const uint4*>(item + (long)nrb * 192 + f * 16));
-                    const uint32_t scw[2] = {hh ? scv.z : scv.x, hh ? scv.w : scv.y};
-#pragma unroll
-                    for (int gq = 0; gq < 4; gq++) {
-#pragma unroll
-                        for (int l0 = 0; l0 < 32; l0 += 8) {
-                            const int s_ = sb8(scw, (l0 >> 4) + 2 * gq);
-                            int v[8];
-#pragma unroll
-                            for (int x = 0; x < 8; x++) {
-                                const int l = l0 + x;
-                                const int lowq = ub(ql, (gq & 1) * 32 + l);
-                                const int nib = (gq >> 1) ? (lowq >> 4) : (lowq & 15);
-                                const int hi2 = (ub(qh, l) >> (2 * gq)) & 3;
-                                v[x] = s_ * ((nib | (hi2 << 4)) - 32);
-                            }
-                            const int atom = 2 * hh + (gq >> 1), pi = (gq & 1) * 4 + (l0 >> 3);
-                            *reinterpret_cast<uint4*>(As + atom * (kGM * 128) + r * 128 + ((pi ^ (r & 7)) << 4)) =
-                                make_uint4(h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
-                        }
-                    }
-                    if (hh == 0) {
-                        const float d = __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(item + (long)nrb * 208 + f * 2))));
-                        misc.rowsc[stage][r] = make_float2(d, 0.f);
-                    }
-                }
-                // activations: 32 rows x 256 int8 -> fp16, 16 values per unit
-#pragma unroll
-                for (int uu = 0; uu < 2; uu++) {
-                    const int u = pt + uu * kGProd, n = u >> 4, pc = u & 15;
-                    uint4 lo4 = make_uint4(0, 0, 0, 0), hi4 = make_uint4(0, 0, 0, 0);
-                    if (n < n_valid) {
-                        const int row = p.rowmap ? p.rowmap[p0 + n] : p0 + n;
-                        const uint4 xv = *reinterpret_cast<const uint4*>(p.xq + (long)row * p.Kc + sb * QK_K + pc * 16);
-                        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                        lo4 = make_uint4(h2(sb8(xw, 0), sb8(xw, 1)), h2(sb8(xw, 2), sb8(xw, 3)), h2(sb8(xw, 4), sb8(xw, 5)), h2(sb8(xw, 6), sb8(xw, 7)));
-                        hi4 = make_uint4(h2(sb8(xw, 8), sb8(xw, 9)), h2(sb8(xw, 10), sb8(xw, 11)), h2(sb8(xw, 12), sb8(xw, 13)), h2(sb8(xw, 14), sb8(xw, 15)));
-                    }
-                    const int kp = 2 * pc, atom = kp >> 3, pi = kp & 7;
-                    uint8_t* brow = Bs + atom * (kGN * 128) + n * 128;
-                    *reinterpret_cast<uint4*>(brow + ((pi ^ (n & 7)) << 4)) = lo4;
-                    *reinterpret_cast<uint4*>(brow + (((pi + 1) ^ (n & 7)) << 4)) = hi4;
-                }
-                if (pt < 64) {   // B2: the sixteen 16-value sums of the block; dxs: the block scale
-                    const int n = pt >> 1, kg = pt & 1;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (n < n_valid) {
-                        const int row = p.rowmap ? p.rowmap[p0 + n] : p0 + n;
-                        const uint4 bv = *reinterpret_cast<const uint4*>(p.xbs + (long)row * (p.Kc / 16) + sb * 16 + kg * 8);
-                        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#define KTB_S16(w, hi) ((int)(short)((hi) ? ((w) >> 16) : ((w) & 0xffffu)))
-                        v = make_uint4(h2(KTB_S16(bw[0], 0), KTB_S16(bw[0], 1)), h2(KTB_S16(bw[1], 0), KTB_S16(bw[1], 1)), h2(KTB_S16(bw[2], 0), KTB_S16(bw[2], 1)),
-                                       h2(KTB_S16(bw[3], 0), KTB_S16(bw[3], 1)));
-#undef KTB_S16
-                        if (kg == 0) misc.dxs[stage][n] = p.xd[(long)row * nblk + sb];
-                    } else if (kg == 0) misc.dxs[stage][n] = 0.f;
-                    *reinterpret_cast<uint4*>(smem + kOffB2 + stage * kGB2 + (n >> 3) * 256 + kg * 128 + (n & 7) * 16) = v;
-                }
+            GrpFetch<FMT> cur, nxt;
+            grp_fetch<FMT>(p, t, 0, tid, nblk, cur);
+            for (int st = 0; st < nst; st++, it++) {
+                if (st + 1 < nst) grp_fetch<FMT>(p, t, st + 1, tid, nblk, nxt);
+                const int stage = it % kGStages;
+                bar_wait(smem_u32(&misc.smem_free[stage]), ((it / kGStages) & 1) ^ 1);
+                grp_store<FMT>(p, t, st, tid, nblk, cur, smem, misc, stage);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) bar_arrive(smem_u32(&misc.ab_full[stage]));
+                cur = nxt;
             }
-        } else if (warp == 8) {
+        } else if (warp == kGProdWarps) {
             // ====================================================================== tensor-core issuer (converged warp)
-            constexpr uint32_t idesc = instr_desc(1, 0, 0, 0, 0, kGM, kGN);   // f32 += f16 . f16, both K-major, 128 x 32
-            for (int sb = 0; sb < nblk; sb++, it++) {
-                const int stage = it & 1;
-                bar_wait(smem_u32(&misc.ab_full[stage]), (it >> 1) & 1);
+            constexpr uint32_t idesc_i8 = FMT == 0 ? instr_desc(2, 0, 1, 0, 0, kGM, kGN) : instr_desc(2, 1, 1, 0, 0, kGM, 2 * kGN);   // s32 += (u8 | s8) . s8
+            constexpr uint32_t idesc_f16 = instr_desc(1, 0, 0, 0, 0, kGM, kGN);
+            for (int st = 0; st < nst; st++, it++) {
+                const int stage = it % kGStages, buf = it & 1;
+                bar_wait(smem_u32(&misc.ab_full[stage]), (it / kGStages) & 1);
+                bar_wait(smem_u32(&misc.tmem_free[buf]), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t a = base + stage * kGA, b = base + kOffB + stage * kGB;
-                const uint32_t d1 = tmem + stage * 64, d2 = d1 + 32;
+                const uint32_t a = base + stage * kGA, b = base + kOffB + stage * kGB, d = tmem + buf * 256;
 #pragma unroll
-                for (int ks = 0; ks < 16; ks++)
-                    mma_f16(d1, smem_desc(a + (ks >> 2) * (kGM * 128) + (ks & 3) * 32, 16, 1024, kLayoutSw128),
-                            smem_desc(b + (ks >> 2) * (kGN * 128) + (ks & 3) * 32, 16, 1024, kLayoutSw128), idesc, ks != 0);
-                if (p.fmt == 0)
-                    mma_f16(d2, smem_desc(base + kOffA2 + stage * kGA2, 128, 256, kLayoutNone), smem_desc(base + kOffB2 + stage * kGB2, 128, 256, kLayoutNone), idesc, 0);
-                mma_commit(smem_u32(&misc.d_full[stage]));
+                for (int c = 0; c < 4; c++)
+                    mma_i8(d + c * (FMT == 0 ? 32 : 64), smem_desc(a + c * 32, 16, 1024, kLayoutSw128), smem_desc(b + c * 32, 16, 1024, kLayoutSw128), idesc_i8, 0);
+                if (FMT == 0 && (st & 1))
+                    mma_f16(d + 128, smem_desc(base + kOffA2 + stage * kGA2, 128, 256, kLayoutNone), smem_desc(base + kOffB2 + stage * kGB2, 128, 256, kLayoutNone), idesc_f16, 0);
+                mma_commit(smem_u32(&misc.smem_free[stage]));
+                mma_commit(smem_u32(&misc.tmem_full[buf]));
             }
         } else {
-            // ====================================================================== epilogue (4 warps = 128 rows)
-            const int sp = warp & 3, row = 32 * sp + lane;
-            const uint32_t lane_base = (uint32_t)(32 * sp) << 16;
-            float acc[kGN];
+            // ====================================================================== epilogue: 8 warps = 128 rows x 2 column halves
+            const int ew = warp - kGProdWarps - 1, sp = warp & 3, ch = ew >> 2, row = 32 * sp + lane;
+            const uint32_t tbase = tmem + ((uint32_t)(32 * sp) << 16) + 16 * ch;
+            float acc[16];
+            int isum[16];
 #pragma unroll
-            for (int n = 0; n < kGN; n++) acc[n] = 0.f;
-            for (int sb = 0; sb < nblk; sb++, it++) {
-                const int stage = it & 1;
-                bar_wait(smem_u32(&misc.d_full[stage]), (it >> 1) & 1);
+            for (int n = 0; n < 16; n++) { acc[n] = 0.f; isum[n] = 0; }
+            for (int st = 0; st < nst; st++, it++) {
+                const int stage = it % kGStages, buf = it & 1, hh = st & 1;
+                bar_wait(smem_u32(&misc.tmem_full[buf]), (it >> 1) & 1);
                 tc_fence_after();
-                uint32_t d1[32], d2[32];
-                tmem_ld32(tmem + lane_base + stage * 64, d1);
-                if (p.fmt == 0) tmem_ld32(tmem + lane_base + stage * 64 + 32, d2);
-                tmem_wait_ld();
-                const float2 rs = misc.rowsc[stage][row];
-                if (p.fmt == 0) {
+                const uint4 hd = misc.hdr[stage][row];
+                const uint32_t hw[4] = {hd.x, hd.y, hd.z, hd.w};
+                const uint32_t d = tbase + buf * 256;
+                if (FMT == 0) {
+                    int sc[4], mn;
+                    if (hh == 0) {
 #pragma unroll
-                    for (int n = 0; n < kGN; n++) {
-                        const float dx = misc.dxs[stage][n];
-                        acc[n] += (rs.x * dx) * __uint_as_float(d1[n]) - (rs.y * dx) * __uint_as_float(d2[n]);
+                        for (int c = 0; c < 4; c++) q4k_scale_min(hw, c, sc[c], mn);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) q4k_scale_min(hw, 4 + c, sc[c], mn);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; c += 2) {
+                        uint32_t v0[16], v1[16];
+                        tmem_ld16(d + 32 * c, v0);
+                        tmem_ld16(d + 32 * c + 32, v1);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int n = 0; n < 16; n++) isum[n] += sc[c] * (int)v0[n] + sc[c + 1] * (int)v1[n];
+                    }
+                    if (hh == 1) {
+                        uint32_t ms[16];
+                        tmem_ld16(d + 128, ms);
+                        const __half2 dm = *reinterpret_cast<const __half2*>(&hw[0]);
+                        const float dw = __low2float(dm), dmin = __high2float(dm);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int n = 0; n < 16; n++) {
+                            const float dx = misc.dxs[stage][16 * ch + n];
+                            acc[n] += (dw * dx) * (float)isum[n] - (dmin * dx) * __uint_as_float(ms[n]);
+                            isum[n] = 0;
+                        }
                     }
                 } else {
 #pragma unroll
-                    for (int n = 0; n < kGN; n++) acc[n] += (rs.x * misc.dxs[stage][n]) * __uint_as_float(d1[n]);
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t ve[16], vo[16];
+                        tmem_ld16(d + 64 * c, ve);
+                        tmem_ld16(d + 64 * c + 32, vo);
+                        const int se = sb8(hw, 2 * c), so = sb8(hw, 2 * c + 1);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int n = 0; n < 16; n++) isum[n] += se * (int)ve[n] + so * (int)vo[n];
+                    }
+                    if (hh == 1) {
+                        const float dw = __uint_as_float(hw[2]);
+#pragma unroll
+                        for (int n = 0; n < 16; n++) {
+                            acc[n] += (dw * misc.dxs[stage][16 * ch + n]) * (float)isum[n];
+                            isum[n] = 0;
+                        }
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) bar_arrive(smem_u32(&misc.stage_free[stage]));
+                if (lane == 0) { bar_arrive(smem_u32(&misc.tmem_free[buf])); bar_arrive(smem_u32(&misc.smem_free[stage])); }
             }
 #pragma unroll
-            for (int n = 0; n < kGN; n++)
-                if (n < n_valid) p.out[(long)(p0 + n) * p.R + m0 + row] = acc[n];
+            for (int n = 0; n < 16; n++)
+                if (16 * ch + n < t.n_valid) p.out[(long)(t.p0 + 16 * ch + n) * p.R + t.m0 + row] = acc[n];
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kGProdWarps) {
         tc_fence_after();
-        tmem_dealloc(tmem, 128);
+        tmem_dealloc(tmem, 512);
     }
 }
 
@@ -400,7 +485,8 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
     GrpScratch& g = g_grp[dev & 63];
     static bool attr[64] = {};
     if (!attr[dev & 63]) {
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem));
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem));
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem));
         attr[dev & 63] = true;
     }
     const FmtId fd = pick_fmt(c.down_type, m->down_layout);
@@ -421,18 +507,19 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
         gp.fmt = 0; gp.R = I; gp.Kc = H; gp.xq = g.xq; gp.xd = g.xd; gp.xbs = g.xbs; gp.rowmap = g.tokmap; gp.offsets = g.offsets; gp.nt_prefix = g.nt_prefix; gp.E = E;
         gp.expert_bytes = (long)I * (H / 256) * SZ_Q4_K;
         gp.w = reinterpret_cast<const uint8_t*>(c.gate_proj); gp.out = g.g;
-        grouped_gemm_kernel<<<grid, kGThreads, kGSmem, s>>>(gp);
+        grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
         gp.w = reinterpret_cast<const uint8_t*>(c.up_proj); gp.out = g.u;
-        grouped_gemm_kernel<<<grid, kGThreads, kGSmem, s>>>(gp);
+        grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
         grp_act_quant_kernel<<<(P * (I / 256) + 7) / 8, 256, 0, s>>>(g.g, g.u, g.offsets, E, I, c.use_silu, g.aq, g.ad, g.abs16);
         GrpGemmParams gd{};
         gd.fmt = fd == FMT_Q6K4T ? 1 : 0; gd.R = H; gd.Kc = I; gd.xq = g.aq; gd.xd = g.ad; gd.xbs = g.abs16; gd.rowmap = nullptr; gd.offsets = g.offsets; gd.nt_prefix = g.nt_prefix;
         gd.E = E; gd.expert_bytes = (long)H * (I / 256) * (fd == FMT_Q6K4T ? SZ_Q6_K : SZ_Q4_K);
         gd.w = reinterpret_cast<const uint8_t*>(c.down_proj); gd.out = g.dd;
-        grouped_gemm_kernel<<<grid, kGThreads, kGSmem, s>>>(gd);
+        if (gd.fmt) grouped_gemm_kernel<1><<<grid, kGThreads, kGSmem, s>>>(gd);
+        else grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gd);
         grp_combine_kernel<<<dim3((H + 255) / 256, T), 256, 0, s>>>(g.dd, g.pos, w_c, T, k, H, bsz, t0, o_c, c.hidden_type);
         KTB_LAUNCH_CHECK();
-        count_launch(8);
+        count_launch(7);   // + the one KTB_LAUNCH_CHECK counts = 8 launches per chunk
     }
     return KTB200_OK;
 }

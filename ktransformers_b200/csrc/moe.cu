@@ -568,9 +568,11 @@ int ktb200_moe_load_weights(ktb200_moe* m, void* stream) {
 
 float* ktb200_moe_intermediate(ktb200_moe* m) { return m ? m->inter : nullptr; }
 
+extern "C++" {
 namespace ktb {
 bool grouped_ok(const ktb200_moe* m, int k);
 int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input, void* output, const int* bsz, cudaStream_t s);
+}
 }
 // qlen from which the per-expert tensor-core GEMMs (grouped.cu) replace the per-pair GEMV kernels: the reference makes the
 // same split between MOE::forward_one and MOE::forward_many (moe.cpp:367-377, threshold group_min_len)
