@@ -31,12 +31,14 @@ namespace ktb {
 
 using namespace umma;
 
-constexpr int kGM = 128, kGN = 32, kGStages = 4;
+constexpr int kGM = 128, kGN = 32, kGStages = 3, kGRaw = 6;
 constexpr int kGProdWarps = 4, kGEpiWarps = 8, kGThreads = (kGProdWarps + 1 + kGEpiWarps) * 32;   // 13 warps: at most 4 per scheduler, 128 registers each
 constexpr int kGA = kGM * 128;            // 16,384: 128 rows x 128 int8 of K, one swizzle atom column
 constexpr int kGB = 2 * kGN * 128;        //  8,192: 32 rows (Q4_K) or 64 rows (Q6_K even / odd variants)
 constexpr int kGA2 = kGM * 32, kGB2 = kGN * 32;
-constexpr int kOffB = kGStages * kGA, kOffA2 = kOffB + kGStages * kGB, kOffB2 = kOffA2 + kGStages * kGA2, kOffMiscG = kOffB2 + kGStages * kGB2;
+constexpr int kRawPitch = 144, kRawSlot = kGM * kRawPitch;   // 9 x 16 bytes per producer thread and stage (odd pitch: conflict-free LDS.128)
+constexpr int kOffB = kGStages * kGA, kOffA2 = kOffB + kGStages * kGB, kOffB2 = kOffA2 + kGStages * kGA2, kOffRaw = kOffB2 + kGStages * kGB2,
+              kOffMiscG = kOffRaw + kGRaw * kRawSlot;
 
 struct GrpMisc {
     unsigned long long ab_full[kGStages], smem_free[kGStages], tmem_full[2], tmem_free[2];
@@ -45,17 +47,17 @@ struct GrpMisc {
     uint4 hdr[kGStages][kGM];   // Q4_K: the block header (d, dmin, 12 scale bytes); Q6_K: 8 scales of the half, d as f32
 };
 constexpr int kGSmem = kOffMiscG + (int)sizeof(GrpMisc) + 1024;
+static_assert(kGSmem <= 227 * 1024, "shared memory budget");
 
 struct GrpGemmParams {
     const uint8_t* w;          // expert weights
     long expert_bytes;         // bytes per expert
-    int fmt;                   // 0: raw Q4_K rows, 1: Q6_K 4-row tiles (repack_q6k4t)
     int R, Kc;                 // rows per expert, reduction length
     const int8_t* xq;          // activations: int8 [rows][Kc]
     const float* xd;           // [rows][Kc / 256]
     const int16_t* xbs;        // [rows][Kc / 16]
     const int* rowmap;         // sorted position -> activation row (null: identity)
-    const int* offsets;        // [E + 1] first sorted position of every expert
+    const int4* tinfo;         // [tiles] {expert, first weight row, first sorted position, valid tokens}
     const int* nt_prefix;      // [E + 1] 32-token tiles before every expert
     int E;
     float* out;                // [P][R] fp32
@@ -73,158 +75,32 @@ __device__ __forceinline__ void q4k_scale_min(const uint32_t* hw, int j, int& sc
     if (j < 4) { sc = ub(hw, 4 + j) & 63; mn = ub(hw, 8 + j) & 63; }
     else { sc = (ub(hw, 8 + j) & 0xF) | ((ub(hw, j) >> 6) << 4); mn = (ub(hw, 8 + j) >> 4) | ((ub(hw, 4 + j) >> 6) << 4); }
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// what one producer thread fetches for one stage
-template <int FMT>
-struct GrpFetch {
-    uint4 w[FMT == 0 ? 4 : 6];   // Q4_K: 64 bytes of qs;  Q6_K: 64 of ql, 32 of qh  (the row's share of this half super-block)
-    uint4 hdr;                   // Q4_K: block header;    Q6_K: .x.y = the 8 scales of this half, .z = d (fp16 bits)
-    uint4 b[2];                  // activation pieces
-};
-
-struct GrpTile {
-    int e, m0, p0, n_valid;
-    const uint8_t* we;
-};
-
-__device__ __forceinline__ GrpTile grp_tile(const GrpGemmParams& p, int tile, int MT) {
-    // tile -> (expert, row tile, token tile); token tile fastest: CTAs running side by side share the weight tile through L2
-    int lo = 0, hi = p.E;
+// tile table: tile -> (expert, row tile, token tile), token tile fastest so that CTAs running side by side share the weight tile
+// through L2.  One thread per tile; tiles beyond the data-dependent total are left alone.
+__global__ void grp_tiles_kernel(const int* nt_prefix, const int* offsets, int E, int MT, int4* tinfo) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= nt_prefix[E] * MT) return;
+    int lo = 0, hi = E;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (p.nt_prefix[mid] * MT <= tile) lo = mid; else hi = mid;
+        if (nt_prefix[mid] * MT <= tile) lo = mid; else hi = mid;
     }
-    GrpTile t;
-    t.e = lo;
-    const int local = tile - p.nt_prefix[lo] * MT, ntile_e = p.nt_prefix[lo + 1] - p.nt_prefix[lo];
+    const int local = tile - nt_prefix[lo] * MT, ntile_e = nt_prefix[lo + 1] - nt_prefix[lo];
     const int mt = local / ntile_e, nt = local - mt * ntile_e;
-    t.m0 = mt * kGM;
-    t.p0 = p.offsets[lo] + nt * kGN;
-    t.n_valid = min(kGN, p.offsets[lo + 1] - t.p0);
-    t.we = p.w + (long)lo * p.expert_bytes;
-    return t;
+    const int p0 = offsets[lo] + nt * kGN;
+    tinfo[tile] = make_int4(lo, mt * kGM, p0, min(kGN, offsets[lo + 1] - p0));
 }
 
-template <int FMT>
-__device__ __forceinline__ void grp_fetch(const GrpGemmParams& p, const GrpTile& t, int st, int r, int nblk, GrpFetch<FMT>& f) {
-    const int sb = st >> 1, hh = st & 1;
-    if (FMT == 0) {
-        const uint8_t* blk = t.we + ((long)(t.m0 + r) * nblk + sb) * SZ_Q4_K;
-        f.hdr = __ldg(reinterpret_cast<const uint4*>(blk));
-#pragma unroll
-        for (int i = 0; i < 4; i++) f.w[i] = ldg_stream16(blk + 16 + hh * 64 + i * 16);
-    } else {
-        const int row = t.m0 + r, rw = row & 3, nrb = 4 * nblk, fi = rw * nblk + sb;
-        const uint8_t* item = t.we + (long)(row >> 2) * nrb * SZ_Q6_K;
-#pragma unroll
-        for (int i = 0; i < 4; i++) f.w[i] = ldg_stream16(item + (long)(4 * hh + i) * nrb * 16 + fi * 16);
-#pragma unroll
-        for (int i = 0; i < 2; i++) f.w[4 + i] = ldg_stream16(item + (long)nrb * 128 + (long)(2 * hh + i) * nrb * 16 + fi * 16);
-        const uint2 sc = __ldg(reinterpret_cast<const uint2*>(item + (long)nrb * 192 + fi * 16 + hh * 8));
-        f.hdr = make_uint4(sc.x, sc.y, ldg_u16(item + (long)nrb * 208 + fi * 2), 0);
-    }
-    // activation pieces: 32 rows x 8 pieces of 16 bytes = 256 = two per thread
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        const int id = r + u * kGM, n = id >> 3, pc = id & 7;
-        f.b[u] = make_uint4(0, 0, 0, 0);
-        if (n < t.n_valid) {
-            const int row = p.rowmap ? p.rowmap[t.p0 + n] : t.p0 + n;
-            f.b[u] = *reinterpret_cast<const uint4*>(p.xq + (long)row * p.Kc + st * 128 + pc * 16);
-        }
-    }
-}
-
-template <int FMT>
-__device__ __forceinline__ void grp_store(const GrpGemmParams& p, const GrpTile& t, int st, int r, int nblk, const GrpFetch<FMT>& f, uint8_t* smem, GrpMisc& misc,
-                                          int stage) {
-    const int sb = st >> 1, hh = st & 1;
-    uint8_t* arow = smem + stage * kGA + r * 128;
-    const int sw = r & 7;
-    if (FMT == 0) {
-        // chunk c = 2 hh + part (32 bytes of qs): low nibbles = sub-block 2c (elements 64c .. 64c+31), high nibbles = sub-block 2c+1
-#pragma unroll
-        for (int part = 0; part < 2; part++) {
-            const uint4 q0 = f.w[2 * part], q1 = f.w[2 * part + 1];
-            const int pi = 4 * part;
-            *reinterpret_cast<uint4*>(arow + (((pi + 0) ^ sw) << 4)) = make_uint4(q0.x & 0x0F0F0F0Fu, q0.y & 0x0F0F0F0Fu, q0.z & 0x0F0F0F0Fu, q0.w & 0x0F0F0F0Fu);
-            *reinterpret_cast<uint4*>(arow + (((pi + 1) ^ sw) << 4)) = make_uint4(q1.x & 0x0F0F0F0Fu, q1.y & 0x0F0F0F0Fu, q1.z & 0x0F0F0F0Fu, q1.w & 0x0F0F0F0Fu);
-            *reinterpret_cast<uint4*>(arow + (((pi + 2) ^ sw) << 4)) =
-                make_uint4((q0.x >> 4) & 0x0F0F0F0Fu, (q0.y >> 4) & 0x0F0F0F0Fu, (q0.z >> 4) & 0x0F0F0F0Fu, (q0.w >> 4) & 0x0F0F0F0Fu);
-            *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) =
-                make_uint4((q1.x >> 4) & 0x0F0F0F0Fu, (q1.y >> 4) & 0x0F0F0F0Fu, (q1.z >> 4) & 0x0F0F0F0Fu, (q1.w >> 4) & 0x0F0F0F0Fu);
-        }
-        misc.hdr[stage][r] = f.hdr;
-        if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
-            const uint32_t hw[4] = {f.hdr.x, f.hdr.y, f.hdr.z, f.hdr.w};
-            int sc, mn[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) q4k_scale_min(hw, j, sc, mn[j]);
-            uint8_t* a2 = smem + kOffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16;
-            *reinterpret_cast<uint4*>(a2) = make_uint4(h2(mn[0], mn[0]), h2(mn[1], mn[1]), h2(mn[2], mn[2]), h2(mn[3], mn[3]));
-            *reinterpret_cast<uint4*>(a2 + 128) = make_uint4(h2(mn[4], mn[4]), h2(mn[5], mn[5]), h2(mn[6], mn[6]), h2(mn[7], mn[7]));
-        }
-    } else {
-        // element 32 g + l of the half (l = 16 part + 0..15): g = 0 ql[l] & 15 | (qh & 3) << 4, g = 1 ql[32 + l] & 15 | (qh >> 2 & 3) << 4,
-        // g = 2 ql[l] >> 4 | (qh >> 4 & 3) << 4, g = 3 ql[32 + l] >> 4 | (qh >> 6 & 3) << 4; stored as q - 32 in int8
-#pragma unroll
-        for (int part = 0; part < 2; part++) {
-            const uint4 wa = f.w[part], wb = f.w[2 + part], wh = f.w[4 + part];
-            const uint32_t a[4] = {wa.x, wa.y, wa.z, wa.w}, b[4] = {wb.x, wb.y, wb.z, wb.w}, h[4] = {wh.x, wh.y, wh.z, wh.w};
-            uint32_t v[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                v[0][i] = (a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u);
-                v[1][i] = (b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u);
-                v[2][i] = ((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u);
-                v[3][i] = ((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u);
-            }
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {   // q - 32 per byte: flip bit 5, then copy it into bits 6 and 7 (no carries between bytes)
-                    const uint32_t tt = v[g][i] ^ 0x20202020u;
-                    v[g][i] = tt + (tt & 0x20202020u) * 6u;
-                }
-                *reinterpret_cast<uint4*>(arow + (((2 * g + part) ^ sw) << 4)) = make_uint4(v[g][0], v[g][1], v[g][2], v[g][3]);
-            }
-        }
-        misc.hdr[stage][r] = make_uint4(f.hdr.x, f.hdr.y, __float_as_uint(fp16_bits_to_f32((uint16_t)f.hdr.z)), 0);
-    }
-    // activations
-    uint8_t* Bs = smem + kOffB + stage * kGB;
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        const int id = r + u * kGM, n = id >> 3, pc = id & 7;
-        if (FMT == 0) {
-            *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = f.b[u];
-        } else {   // a 16-byte piece is one Q6_K sub-block: rows 0-31 keep the even pieces, rows 32-63 the odd ones
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? z : f.b[u];
-            *reinterpret_cast<uint4*>(Bs + (kGN + n) * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? f.b[u] : z;
-        }
-    }
-    if (hh == 1 && r < 64) {   // token scales, and (Q4_K) the sixteen 16-value sums of the super-block as fp16
-        const int n2 = r >> 1, kg = r & 1;
-        uint4 vv = make_uint4(0, 0, 0, 0);
-        float dx = 0.f;
-        if (n2 < t.n_valid) {
-            const int row = p.rowmap ? p.rowmap[t.p0 + n2] : t.p0 + n2;
-            dx = p.xd[(long)row * nblk + sb];
-            if (FMT == 0) {
-                const uint4 bv = *reinterpret_cast<const uint4*>(p.xbs + (long)row * (p.Kc / 16) + sb * 16 + kg * 8);
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#define KTB_S16(w, hi) ((int)(short)((hi) ? ((w) >> 16) : ((w) & 0xffffu)))
-                vv = make_uint4(h2(KTB_S16(bw[0], 0), KTB_S16(bw[0], 1)), h2(KTB_S16(bw[1], 0), KTB_S16(bw[1], 1)), h2(KTB_S16(bw[2], 0), KTB_S16(bw[2], 1)),
-                                h2(KTB_S16(bw[3], 0), KTB_S16(bw[3], 1)));
-#undef KTB_S16
-            }
-        }
-        if (kg == 0) misc.dxs[stage][n2] = dx;
-        if (FMT == 0) *reinterpret_cast<uint4*>(smem + kOffB2 + stage * kGB2 + (n2 >> 3) * 256 + kg * 128 + (n2 & 7) * 16) = vv;
-    }
-}
-
+// The producer's share of one stage, as it sits in its raw-ring slot (16-byte units):
+//   Q4_K: 0-3 qs (64 bytes of the half), 4 block header, 5 token scale (4 bytes), 6-7 activation pieces, 8 activation 16-sums
+//   Q6_K: 0-3 ql, 4-5 qh, 6-7 activation pieces, 8 = 8 scales | d (2 of 4 bytes) | token scale
 template <int FMT>
 __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -247,26 +123,162 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
     const int total_tiles = p.nt_prefix[p.E] * MT;
     unsigned it = 0;   // stages done by this CTA: smem stage = it % kGStages, TMEM buffer = it & 1
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const GrpTile t = grp_tile(p, tile, MT);
-        if (warp < kGProdWarps) {
-            // ====================================================================== producers
-            GrpFetch<FMT> cur, nxt;
-            grp_fetch<FMT>(p, t, 0, tid, nblk, cur);
-            for (int st = 0; st < nst; st++, it++) {
-                if (st + 1 < nst) grp_fetch<FMT>(p, t, st + 1, tid, nblk, nxt);
-                const int stage = it % kGStages;
+    if (warp < kGProdWarps) {
+        // ========================================================================== producers: thread = weight row r of the tile
+        const int r = tid, sw = r & 7, pc = r & 7;
+        const uint32_t raw_dst = base + kOffRaw + r * kRawPitch;
+        const uint8_t* raw_src = smem + kOffRaw + r * kRawPitch;
+        // fetch cursor: runs kGRaw stages ahead of the conversion, across tile boundaries
+        int ftile = blockIdx.x, fst = 0, frow0 = -1, frow1 = -1, frow2 = -1, frw = 0;
+        const uint8_t* fw = nullptr;
+        auto enter_tile = [&]() {
+            if (ftile >= total_tiles) return;
+            const int4 ti = __ldg(p.tinfo + ftile);
+            const int n0 = r >> 3, n1 = 16 + (r >> 3), n2 = r >> 1;
+            frow0 = n0 < ti.w ? (p.rowmap ? __ldg(p.rowmap + ti.z + n0) : ti.z + n0) : -1;
+            frow1 = n1 < ti.w ? (p.rowmap ? __ldg(p.rowmap + ti.z + n1) : ti.z + n1) : -1;
+            frow2 = (r < 64 && n2 < ti.w) ? (p.rowmap ? __ldg(p.rowmap + ti.z + n2) : ti.z + n2) : -1;
+            const int row = ti.y + r;
+            frw = row & 3;
+            fw = p.w + (long)ti.x * p.expert_bytes + (FMT == 0 ? (long)row * nblk * SZ_Q4_K : (long)(row >> 2) * 4 * nblk * SZ_Q6_K);
+        };
+        auto issue = [&](int slot) {
+            if (ftile < total_tiles) {
+                const uint32_t dst = raw_dst + slot * kRawSlot;
+                const int sb = fst >> 1, hh = fst & 1;
+                if (FMT == 0) {
+                    const uint8_t* blk = fw + (long)sb * SZ_Q4_K;
+                    cp_async16(dst + 64, blk);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) cp_async16(dst + 16 * i, blk + 16 + hh * 64 + i * 16);
+                } else {
+                    const int nrb = 4 * nblk, fi = frw * nblk + sb;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) cp_async16(dst + 16 * i, fw + (long)(4 * hh + i) * nrb * 16 + fi * 16);
+#pragma unroll
+                    for (int i = 0; i < 2; i++) cp_async16(dst + 64 + 16 * i, fw + (long)nrb * 128 + (long)(2 * hh + i) * nrb * 16 + fi * 16);
+                    cp_async8(dst + 128, fw + (long)nrb * 192 + fi * 16 + hh * 8);
+                    cp_async4(dst + 136, fw + (long)nrb * 208 + (fi >> 1) * 4);
+                }
+                if (frow0 >= 0) cp_async16(dst + 96, p.xq + (long)frow0 * p.Kc + fst * 128 + pc * 16);
+                if (frow1 >= 0) cp_async16(dst + 112, p.xq + (long)frow1 * p.Kc + fst * 128 + pc * 16);
+                if (hh == 1 && frow2 >= 0) {
+                    if ((r & 1) == 0) cp_async4(dst + (FMT == 0 ? 80 : 140), p.xd + (long)frow2 * nblk + sb);
+                    if (FMT == 0) cp_async16(dst + 128, p.xbs + (long)frow2 * (p.Kc / 16) + sb * 16 + (r & 1) * 8);
+                }
+                if (++fst == nst) { fst = 0; ftile += gridDim.x; enter_tile(); }
+            }
+            cp_async_commit();
+        };
+        enter_tile();
+        for (int i = 0; i < kGRaw; i++) issue(i);
+        unsigned cc = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int4 ti = __ldg(p.tinfo + tile);
+            const int n_valid = ti.w;
+            for (int st = 0; st < nst; st++, it++, cc++) {
+                const int slot = cc % kGRaw, stage = it % kGStages, hh = st & 1;
+                cp_async_wait<kGRaw - 1>();
+                const uint4* rs = reinterpret_cast<const uint4*>(raw_src + slot * kRawSlot);
+                uint4 f[9];
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[i] = rs[i];
+                issue(slot);   // refill the slot just read (thread-private bytes: no barrier involved)
                 bar_wait(smem_u32(&misc.smem_free[stage]), ((it / kGStages) & 1) ^ 1);
-                grp_store<FMT>(p, t, st, tid, nblk, cur, smem, misc, stage);
+                uint8_t* arow = smem + stage * kGA + r * 128;
+                if (FMT == 0) {
+                    // chunk c = 2 hh + part (32 bytes of qs): low nibbles = sub-block 2c (elements 64c .. 64c+31), high nibbles = sub-block 2c+1
+#pragma unroll
+                    for (int part = 0; part < 2; part++) {
+                        const uint4 q0 = f[2 * part], q1 = f[2 * part + 1];
+                        const int pi = 4 * part;
+                        *reinterpret_cast<uint4*>(arow + (((pi + 0) ^ sw) << 4)) = make_uint4(q0.x & 0x0F0F0F0Fu, q0.y & 0x0F0F0F0Fu, q0.z & 0x0F0F0F0Fu, q0.w & 0x0F0F0F0Fu);
+                        *reinterpret_cast<uint4*>(arow + (((pi + 1) ^ sw) << 4)) = make_uint4(q1.x & 0x0F0F0F0Fu, q1.y & 0x0F0F0F0Fu, q1.z & 0x0F0F0F0Fu, q1.w & 0x0F0F0F0Fu);
+                        *reinterpret_cast<uint4*>(arow + (((pi + 2) ^ sw) << 4)) =
+                            make_uint4((q0.x >> 4) & 0x0F0F0F0Fu, (q0.y >> 4) & 0x0F0F0F0Fu, (q0.z >> 4) & 0x0F0F0F0Fu, (q0.w >> 4) & 0x0F0F0F0Fu);
+                        *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) =
+                            make_uint4((q1.x >> 4) & 0x0F0F0F0Fu, (q1.y >> 4) & 0x0F0F0F0Fu, (q1.z >> 4) & 0x0F0F0F0Fu, (q1.w >> 4) & 0x0F0F0F0Fu);
+                    }
+                    misc.hdr[stage][r] = f[4];
+                    if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
+                        const uint32_t hw[4] = {f[4].x, f[4].y, f[4].z, f[4].w};
+                        int sc, mn[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) q4k_scale_min(hw, j, sc, mn[j]);
+                        uint8_t* a2 = smem + kOffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16;
+                        *reinterpret_cast<uint4*>(a2) = make_uint4(h2(mn[0], mn[0]), h2(mn[1], mn[1]), h2(mn[2], mn[2]), h2(mn[3], mn[3]));
+                        *reinterpret_cast<uint4*>(a2 + 128) = make_uint4(h2(mn[4], mn[4]), h2(mn[5], mn[5]), h2(mn[6], mn[6]), h2(mn[7], mn[7]));
+                    }
+                } else {
+                    // element 32 g + l of the half (l = 16 part + 0..15): g = 0 ql[l] & 15 | (qh & 3) << 4, g = 1 ql[32 + l] & 15 | (qh >> 2 & 3) << 4,
+                    // g = 2 ql[l] >> 4 | (qh >> 4 & 3) << 4, g = 3 ql[32 + l] >> 4 | (qh >> 6 & 3) << 4; stored as q - 32 in int8
+#pragma unroll
+                    for (int part = 0; part < 2; part++) {
+                        const uint4 wa = f[part], wb = f[2 + part], wh = f[4 + part];
+                        const uint32_t a[4] = {wa.x, wa.y, wa.z, wa.w}, b[4] = {wb.x, wb.y, wb.z, wb.w}, h[4] = {wh.x, wh.y, wh.z, wh.w};
+                        uint32_t v[4][4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            v[0][i] = (a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u);
+                            v[1][i] = (b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u);
+                            v[2][i] = ((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u);
+                            v[3][i] = ((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u);
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {   // q - 32 per byte: flip bit 5, then copy it into bits 6 and 7 (no carries between bytes)
+                                const uint32_t tt = v[g][i] ^ 0x20202020u;
+                                v[g][i] = tt + (tt & 0x20202020u) * 6u;
+                            }
+                            *reinterpret_cast<uint4*>(arow + (((2 * g + part) ^ sw) << 4)) = make_uint4(v[g][0], v[g][1], v[g][2], v[g][3]);
+                        }
+                    }
+                    const int fi = ((ti.y + r) & 3) * nblk + (st >> 1);
+                    const uint32_t dbits = (fi & 1) ? (f[8].z >> 16) : (f[8].z & 0xffffu);
+                    misc.hdr[stage][r] = make_uint4(f[8].x, f[8].y, __float_as_uint(fp16_bits_to_f32((uint16_t)dbits)), 0);
+                }
+                // activations: pieces (n, pc) and (16 + n, pc)
+                uint8_t* Bs = smem + kOffB + stage * kGB;
+                const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int n = (r >> 3) + 16 * u;
+                    const uint4 bv = n < n_valid ? f[6 + u] : z;
+                    if (FMT == 0) {
+                        *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = bv;
+                    } else {   // a 16-byte piece is one Q6_K sub-block: rows 0-31 keep the even pieces, rows 32-63 the odd ones
+                        *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? z : bv;
+                        *reinterpret_cast<uint4*>(Bs + (kGN + n) * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? bv : z;
+                    }
+                }
+                if (hh == 1 && r < 64) {   // token scales, and (Q4_K) the sixteen 16-value sums of the super-block as fp16
+                    const int n2 = r >> 1, kg = r & 1;
+                    const bool ok = n2 < n_valid;
+                    if (kg == 0) misc.dxs[stage][n2] = ok ? __uint_as_float(FMT == 0 ? f[5].x : f[8].w) : 0.f;
+                    if (FMT == 0) {
+                        uint4 vv = z;
+                        if (ok) {
+                            const uint32_t bw[4] = {f[8].x, f[8].y, f[8].z, f[8].w};
+#define KTB_S16(w, hi) ((int)(short)((hi) ? ((w) >> 16) : ((w) & 0xffffu)))
+                            vv = make_uint4(h2(KTB_S16(bw[0], 0), KTB_S16(bw[0], 1)), h2(KTB_S16(bw[1], 0), KTB_S16(bw[1], 1)), h2(KTB_S16(bw[2], 0), KTB_S16(bw[2], 1)),
+                                            h2(KTB_S16(bw[3], 0), KTB_S16(bw[3], 1)));
+#undef KTB_S16
+                        }
+                        *reinterpret_cast<uint4*>(smem + kOffB2 + stage * kGB2 + (n2 >> 3) * 256 + kg * 128 + (n2 & 7) * 16) = vv;
+                    }
+                }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) bar_arrive(smem_u32(&misc.ab_full[stage]));
-                cur = nxt;
             }
-        } else if (warp == kGProdWarps) {
-            // ====================================================================== tensor-core issuer (converged warp)
-            constexpr uint32_t idesc_i8 = FMT == 0 ? instr_desc(2, 0, 1, 0, 0, kGM, kGN) : instr_desc(2, 1, 1, 0, 0, kGM, 2 * kGN);   // s32 += (u8 | s8) . s8
-            constexpr uint32_t idesc_f16 = instr_desc(1, 0, 0, 0, 0, kGM, kGN);
+        }
+        cp_async_wait<0>();
+    } else if (warp == kGProdWarps) {
+        // ========================================================================== tensor-core issuer (converged warp)
+        constexpr uint32_t idesc_i8 = FMT == 0 ? instr_desc(2, 0, 1, 0, 0, kGM, kGN) : instr_desc(2, 1, 1, 0, 0, kGM, 2 * kGN);   // s32 += (u8 | s8) . s8
+        constexpr uint32_t idesc_f16 = instr_desc(1, 0, 0, 0, 0, kGM, kGN);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int st = 0; st < nst; st++, it++) {
                 const int stage = it % kGStages, buf = it & 1;
                 bar_wait(smem_u32(&misc.ab_full[stage]), (it / kGStages) & 1);
@@ -281,10 +293,13 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 mma_commit(smem_u32(&misc.smem_free[stage]));
                 mma_commit(smem_u32(&misc.tmem_full[buf]));
             }
-        } else {
-            // ====================================================================== epilogue: 8 warps = 128 rows x 2 column halves
-            const int ew = warp - kGProdWarps - 1, sp = warp & 3, ch = ew >> 2, row = 32 * sp + lane;
-            const uint32_t tbase = tmem + ((uint32_t)(32 * sp) << 16) + 16 * ch;
+        }
+    } else {
+        // ========================================================================== epilogue: 8 warps = 128 rows x 2 column halves
+        const int ew = warp - kGProdWarps - 1, sp = warp & 3, ch = ew >> 2, row = 32 * sp + lane;
+        const uint32_t tbase = tmem + ((uint32_t)(32 * sp) << 16) + 16 * ch;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int4 ti = __ldg(p.tinfo + tile);
             float acc[16];
             int isum[16];
 #pragma unroll
@@ -353,7 +368,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
             }
 #pragma unroll
             for (int n = 0; n < 16; n++)
-                if (16 * ch + n < t.n_valid) p.out[(long)(t.p0 + 16 * ch + n) * p.R + t.m0 + row] = acc[n];
+                if (16 * ch + n < ti.w) p.out[(long)(ti.z + 16 * ch + n) * p.R + ti.y + row] = acc[n];
         }
     }
     tc_fence_before();
@@ -434,20 +449,24 @@ __global__ void __launch_bounds__(256) grp_combine_kernel(const float* dd, const
 struct GrpScratch {
     size_t cap_pairs = 0, cap_x = 0, cap_a = 0, cap_d = 0;   // pairs, tokens * H, pairs * I, pairs * H
     int *counts = nullptr, *offsets = nullptr, *nt_prefix = nullptr, *cursor = nullptr, *tokmap = nullptr, *pos = nullptr;
+    int4 *tinfo_gu = nullptr, *tinfo_d = nullptr;
+    size_t cap_tiles_gu = 0, cap_tiles_d = 0;
     int8_t *xq = nullptr, *aq = nullptr;
     float *xd = nullptr, *ad = nullptr, *g = nullptr, *u = nullptr, *dd = nullptr;
     int16_t *xbs = nullptr, *abs16 = nullptr;
 };
 static GrpScratch g_grp[64];   // one arena per device, shared by every handle (calls on one device are stream-ordered by the caller)
 
-static int grp_ensure(int dev, int tokens, int k, int H, int I) {
+static int grp_ensure(int dev, int tokens, int k, int E, int H, int I) {
     GrpScratch& s = g_grp[dev & 63];
     size_t P = (size_t)tokens * k, nx = (size_t)tokens * H, na = P * I, nd = P * H;
-    if (s.cap_pairs >= P && s.cap_x >= nx && s.cap_a >= na && s.cap_d >= nd) return KTB200_OK;
+    size_t tg = (P / kGN + E) * (size_t)(I / kGM), td = (P / kGN + E) * (size_t)(H / kGM);   // upper bounds of the tile counts
+    if (s.cap_pairs >= P && s.cap_x >= nx && s.cap_a >= na && s.cap_d >= nd && s.cap_tiles_gu >= tg && s.cap_tiles_d >= td) return KTB200_OK;
+    tg = tg > s.cap_tiles_gu ? tg : s.cap_tiles_gu; td = td > s.cap_tiles_d ? td : s.cap_tiles_d;
     P = P > s.cap_pairs ? P : s.cap_pairs; nx = nx > s.cap_x ? nx : s.cap_x; na = na > s.cap_a ? na : s.cap_a; nd = nd > s.cap_d ? nd : s.cap_d;   // grow only
     KTB_CUDA_CHECK(cudaDeviceSynchronize());   // earlier calls may still be using the arena
     cudaFree(s.counts); cudaFree(s.tokmap); cudaFree(s.pos); cudaFree(s.xq); cudaFree(s.xd); cudaFree(s.xbs); cudaFree(s.aq); cudaFree(s.ad); cudaFree(s.abs16);
-    cudaFree(s.g); cudaFree(s.u); cudaFree(s.dd);
+    cudaFree(s.g); cudaFree(s.u); cudaFree(s.dd); cudaFree(s.tinfo_gu); cudaFree(s.tinfo_d);
     s = GrpScratch();
     const size_t cp = P;
     KTB_CUDA_CHECK(cudaMalloc(&s.counts, (size_t)(4 * 1024 + 8) * sizeof(int)));
@@ -463,7 +482,9 @@ static int grp_ensure(int dev, int tokens, int k, int H, int I) {
     KTB_CUDA_CHECK(cudaMalloc(&s.g, na * sizeof(float)));
     KTB_CUDA_CHECK(cudaMalloc(&s.u, na * sizeof(float)));
     KTB_CUDA_CHECK(cudaMalloc(&s.dd, nd * sizeof(float)));
-    s.cap_pairs = cp; s.cap_x = nx; s.cap_a = na; s.cap_d = nd;
+    KTB_CUDA_CHECK(cudaMalloc(&s.tinfo_gu, tg * sizeof(int4)));
+    KTB_CUDA_CHECK(cudaMalloc(&s.tinfo_d, td * sizeof(int4)));
+    s.cap_pairs = cp; s.cap_x = nx; s.cap_a = na; s.cap_d = nd; s.cap_tiles_gu = tg; s.cap_tiles_d = td;
     return KTB200_OK;
 }
 
@@ -480,7 +501,7 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
     const int E = c.expert_num, H = c.hidden_size, I = c.intermediate_size, dev = m->device;
     static const int chunk_cap = [] { const char* e = getenv("KTB200_GROUPED_CHUNK"); return e ? atoi(e) : 1024; }();
     const int Tc = qlen < chunk_cap ? qlen : chunk_cap;
-    int rc = grp_ensure(dev, Tc, k, H, I);   // grow-only scratch: not capturable on first use (like ktb200_moe_gate_forward)
+    int rc = grp_ensure(dev, Tc, k, E, H, I);   // grow-only scratch: not capturable on first use (like ktb200_moe_gate_forward)
     if (rc) return rc;
     GrpScratch& g = g_grp[dev & 63];
     static bool attr[64] = {};
@@ -502,9 +523,12 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
         grp_count_kernel<<<(P + 255) / 256, 256, 0, s>>>(ids_c, P, k, c.expert_id_offset, E, bsz, t0, g.counts);
         grp_scan_kernel<<<1, 32, 0, s>>>(g.counts, E, g.offsets, g.nt_prefix, g.cursor);
         grp_scatter_kernel<<<(P + 255) / 256, 256, 0, s>>>(ids_c, P, k, c.expert_id_offset, E, bsz, t0, g.cursor, g.tokmap, g.pos);
+        const int ub_gu = (P / kGN + E) * (I / kGM), ub_d = (P / kGN + E) * (H / kGM);
+        grp_tiles_kernel<<<(ub_gu + 255) / 256, 256, 0, s>>>(g.nt_prefix, g.offsets, E, I / kGM, g.tinfo_gu);
+        grp_tiles_kernel<<<(ub_d + 255) / 256, 256, 0, s>>>(g.nt_prefix, g.offsets, E, H / kGM, g.tinfo_d);
         grp_quant_x_kernel<<<(T * (H / 256) + 7) / 8, 256, 0, s>>>(x_c, c.hidden_type, T, H, g.xq, g.xd, g.xbs);
         GrpGemmParams gp{};
-        gp.fmt = 0; gp.R = I; gp.Kc = H; gp.xq = g.xq; gp.xd = g.xd; gp.xbs = g.xbs; gp.rowmap = g.tokmap; gp.offsets = g.offsets; gp.nt_prefix = g.nt_prefix; gp.E = E;
+        gp.R = I; gp.Kc = H; gp.xq = g.xq; gp.xd = g.xd; gp.xbs = g.xbs; gp.rowmap = g.tokmap; gp.tinfo = g.tinfo_gu; gp.nt_prefix = g.nt_prefix; gp.E = E;
         gp.expert_bytes = (long)I * (H / 256) * SZ_Q4_K;
         gp.w = reinterpret_cast<const uint8_t*>(c.gate_proj); gp.out = g.g;
         grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
@@ -512,14 +536,14 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
         grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
         grp_act_quant_kernel<<<(P * (I / 256) + 7) / 8, 256, 0, s>>>(g.g, g.u, g.offsets, E, I, c.use_silu, g.aq, g.ad, g.abs16);
         GrpGemmParams gd{};
-        gd.fmt = fd == FMT_Q6K4T ? 1 : 0; gd.R = H; gd.Kc = I; gd.xq = g.aq; gd.xd = g.ad; gd.xbs = g.abs16; gd.rowmap = nullptr; gd.offsets = g.offsets; gd.nt_prefix = g.nt_prefix;
+        gd.R = H; gd.Kc = I; gd.xq = g.aq; gd.xd = g.ad; gd.xbs = g.abs16; gd.rowmap = nullptr; gd.tinfo = g.tinfo_d; gd.nt_prefix = g.nt_prefix;
         gd.E = E; gd.expert_bytes = (long)H * (I / 256) * (fd == FMT_Q6K4T ? SZ_Q6_K : SZ_Q4_K);
         gd.w = reinterpret_cast<const uint8_t*>(c.down_proj); gd.out = g.dd;
-        if (gd.fmt) grouped_gemm_kernel<1><<<grid, kGThreads, kGSmem, s>>>(gd);
+        if (fd == FMT_Q6K4T) grouped_gemm_kernel<1><<<grid, kGThreads, kGSmem, s>>>(gd);
         else grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gd);
         grp_combine_kernel<<<dim3((H + 255) / 256, T), 256, 0, s>>>(g.dd, g.pos, w_c, T, k, H, bsz, t0, o_c, c.hidden_type);
         KTB_LAUNCH_CHECK();
-        count_launch(7);   // + the one KTB_LAUNCH_CHECK counts = 8 launches per chunk
+        count_launch(9);   // + the one KTB_LAUNCH_CHECK counts = 10 launches per chunk
     }
     return KTB200_OK;
 }

@@ -13,7 +13,7 @@ h = C.c_void_p(); native.check(lib.ktb200_moe_create(C.byref(cfg), 0, C.byref(h)
 s = torch.cuda.current_stream().cuda_stream
 native.check(lib.ktb200_moe_load_weights(h, s))
 g = torch.Generator(device="cuda").manual_seed(0)
-for qlen in (64, 256, 1024, 4096):
+for qlen in [int(v) for v in os.environ.get("QLENS", "64,256,1024,4096").split(",")]:
     x = (torch.randn(qlen, H, device="cuda", generator=g) / 100).bfloat16()
     ids = torch.stack([torch.randperm(E, device="cuda", generator=g)[:k] for _ in range(qlen)]).long()
     w = torch.rand(qlen, k, device="cuda", generator=g)
