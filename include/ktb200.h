@@ -300,6 +300,9 @@ size_t ktb200_mla_workspace_bytes(int batch, int num_heads, int max_splits);
 int ktb200_mla_decode(const ktb200_mla_params* p, void* stream);
 /* Diagnostics: while non-NULL, one CTA of ktb200_mla_decode dumps the raw scores of its first tile (>= 2048 floats). */
 void ktb200_debug_mla(float* debug_dev);
+/* Debug aid of the grouped (prefill) expert GEMM: when non-null, CTA 0 of the gate and down GEMMs writes clock64 stamps of its
+ * first 96 stages, [kernel 2][role 3 = producer, issuer, epilogue][stage 96][4] int64 (tools/grouped_probe.py prints them). */
+void ktb200_debug_grouped(long long* trace_dev);
 
 /* ------------------------------------------------------------------------------------------
  * The memory-bound steps between the projections of a DeepSeek decode layer (bf16), fused:

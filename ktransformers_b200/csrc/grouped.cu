@@ -14,12 +14,12 @@
 // Nothing is rounded that the reference does not round.
 //
 // grouped_gemm_kernel: persistent CTAs, tile = (expert, 128 weight rows, 32 tokens), stage = half a super-block (128 of K):
-//     warps 0-3    producers (one weight row per thread): weights (global, 16-byte loads, next stage prefetched in registers) -> int8 A tile in the K-major
+//     warps 0-7    producers (half a weight row per thread): weights (global, 16-byte loads, next stage prefetched in registers) -> int8 A tile in the K-major
 //                  128-byte-swizzle layout (Q4_K: nibble split; Q6_K: 4 + 2 bit merge, -32); activation rows gathered through the
 //                  sorted pair list -> B tile; row headers (scales, d, dmin) and token scales for the epilogue
-//     warp  4      tcgen05 issuer: 4 integer MMAs per stage (+ the mins MMA on the second half), 4 shared-memory stages,
+//     warp  8      tcgen05 issuer: 4 integer MMAs per stage (+ the mins MMA on the second half), 4 shared-memory stages,
 //                  2 TMEM buffers of 256 columns
-//     warps 5-12   epilogue: tcgen05.ld, int32 scale-and-add, fp32 finish per super-block, stores at the end of the tile
+//     warps 9-16   epilogue: tcgen05.ld, int32 scale-and-add, fp32 finish per super-block, stores at the end of the tile
 #include <cuda_fp16.h>
 
 #include "act_quant.cuh"
@@ -32,11 +32,11 @@ namespace ktb {
 using namespace umma;
 
 constexpr int kGM = 128, kGN = 32, kGStages = 3, kGRaw = 6;
-constexpr int kGProdWarps = 4, kGEpiWarps = 8, kGThreads = (kGProdWarps + 1 + kGEpiWarps) * 32;   // 13 warps: at most 4 per scheduler, 128 registers each
+constexpr int kGProdWarps = 8, kGEpiWarps = 8, kGThreads = (kGProdWarps + 1 + kGEpiWarps) * 32;   // 17 warps: at most 5 per scheduler, 96 registers each
 constexpr int kGA = kGM * 128;            // 16,384: 128 rows x 128 int8 of K, one swizzle atom column
 constexpr int kGB = 2 * kGN * 128;        //  8,192: 32 rows (Q4_K) or 64 rows (Q6_K even / odd variants)
 constexpr int kGA2 = kGM * 32, kGB2 = kGN * 32;
-constexpr int kRawPitch = 144, kRawSlot = kGM * kRawPitch;   // 9 x 16 bytes per producer thread and stage (odd pitch: conflict-free LDS.128)
+constexpr int kRawPitch = 80, kRawSlot = 2 * kGM * kRawPitch;   // 5 x 16 bytes per producer thread and stage (odd pitch: conflict-free LDS.128)
 constexpr int kOffB = kGStages * kGA, kOffA2 = kOffB + kGStages * kGB, kOffB2 = kOffA2 + kGStages * kGA2, kOffRaw = kOffB2 + kGStages * kGB2,
               kOffMiscG = kOffRaw + kGRaw * kRawSlot;
 
@@ -61,6 +61,7 @@ struct GrpGemmParams {
     const int* nt_prefix;      // [E + 1] 32-token tiles before every expert
     int E;
     float* out;                // [P][R] fp32
+    long long* trace;          // optional (ktb200_debug_grouped): clock64 stamps of CTA 0, [role 3][stage 96][4]
 };
 
 // byte b of a register array (b is a compile-time constant after unrolling: no local-memory byte addressing)
@@ -98,9 +99,10 @@ __global__ void grp_tiles_kernel(const int* nt_prefix, const int* offsets, int E
     tinfo[tile] = make_int4(lo, mt * kGM, p0, min(kGN, offsets[lo + 1] - p0));
 }
 
-// The producer's share of one stage, as it sits in its raw-ring slot (16-byte units):
-//   Q4_K: 0-3 qs (64 bytes of the half), 4 block header, 5 token scale (4 bytes), 6-7 activation pieces, 8 activation 16-sums
-//   Q6_K: 0-3 ql, 4-5 qh, 6-7 activation pieces, 8 = 8 scales | d (2 of 4 bytes) | token scale
+// A producer thread's share of one stage, as it sits in its raw-ring slot (five 16-byte units, thread = (weight row, half)):
+//   Q4_K: 0-1 the 32 bytes of qs of chunk 2 hh + part, 2 block header, 3 activation piece, 4 activation 16-sums (threads 0-63) or
+//         token scale (threads 64-95)
+//   Q6_K: 0-1 ql (16 bytes at l and at 32 + l), 2 qh, 3 activation piece, 4 = 8 scales | d (2 of 4 bytes) | token scale (threads 64-95)
 template <int FMT>
 __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -121,87 +123,97 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
     tc_fence_after();
     const uint32_t tmem = misc.tmem_base;
     const int total_tiles = p.nt_prefix[p.E] * MT;
-    unsigned it = 0;   // stages done by this CTA: smem stage = it % kGStages, TMEM buffer = it & 1
+    int stage = 0, sphase = 0;   // shared-memory stage of the current iteration and how often it has wrapped (parity)
 
     if (warp < kGProdWarps) {
-        // ========================================================================== producers: thread = weight row r of the tile
-        const int r = tid, sw = r & 7, pc = r & 7;
-        const uint32_t raw_dst = base + kOffRaw + r * kRawPitch;
-        const uint8_t* raw_src = smem + kOffRaw + r * kRawPitch;
-        // fetch cursor: runs kGRaw stages ahead of the conversion, across tile boundaries
-        int ftile = blockIdx.x, fst = 0, frow0 = -1, frow1 = -1, frow2 = -1, frw = 0;
-        const uint8_t* fw = nullptr;
+        // ========================================================================== producers: thread = (weight row r, half `part`)
+        const int pt = tid, r = pt >> 1, part = pt & 1, sw = r & 7, bn = pt >> 3, pc = pt & 7;
+        const uint32_t raw_dst = base + kOffRaw + pt * kRawPitch;
+        const uint8_t* raw_src = smem + kOffRaw + pt * kRawPitch;
+        const int c16 = 4 * nblk * 16;   // Q6_K tiles: bytes between two 16-byte chunk planes of an item
+        // fetch cursor: runs kGRaw stages ahead of the conversion, across tile boundaries; plain running pointers
+        int ftile = blockIdx.x, fst = 0, ffi = 0;
+        const uint8_t *fw = nullptr, *fitem = nullptr;
+        const int8_t* fxq = nullptr;
+        const int16_t* fbs = nullptr;
+        const float* fdx = nullptr;
         auto enter_tile = [&]() {
             if (ftile >= total_tiles) return;
             const int4 ti = __ldg(p.tinfo + ftile);
-            const int n0 = r >> 3, n1 = 16 + (r >> 3), n2 = r >> 1;
-            frow0 = n0 < ti.w ? (p.rowmap ? __ldg(p.rowmap + ti.z + n0) : ti.z + n0) : -1;
-            frow1 = n1 < ti.w ? (p.rowmap ? __ldg(p.rowmap + ti.z + n1) : ti.z + n1) : -1;
-            frow2 = (r < 64 && n2 < ti.w) ? (p.rowmap ? __ldg(p.rowmap + ti.z + n2) : ti.z + n2) : -1;
+            fxq = nullptr; fbs = nullptr; fdx = nullptr;
+            if (bn < ti.w) fxq = p.xq + (long)(p.rowmap ? __ldg(p.rowmap + ti.z + bn) : ti.z + bn) * p.Kc + pc * 16;
+            if (FMT == 0 && pt < 64 && (pt >> 1) < ti.w) fbs = p.xbs + (long)(p.rowmap ? __ldg(p.rowmap + ti.z + (pt >> 1)) : ti.z + (pt >> 1)) * (p.Kc / 16) + (pt & 1) * 8;
+            if (pt >= 64 && pt < 96 && pt - 64 < ti.w) fdx = p.xd + (long)(p.rowmap ? __ldg(p.rowmap + ti.z + pt - 64) : ti.z + pt - 64) * nblk;
             const int row = ti.y + r;
-            frw = row & 3;
-            fw = p.w + (long)ti.x * p.expert_bytes + (FMT == 0 ? (long)row * nblk * SZ_Q4_K : (long)(row >> 2) * 4 * nblk * SZ_Q6_K);
+            if (FMT == 0) fw = p.w + (long)ti.x * p.expert_bytes + (long)row * nblk * SZ_Q4_K + 16 + part * 32;   // this thread's qs of block 0, first half
+            else {
+                fitem = p.w + (long)ti.x * p.expert_bytes + (long)(row >> 2) * 4 * nblk * SZ_Q6_K;
+                ffi = (row & 3) * nblk;
+                fw = fitem + (long)ffi * 16 + part * c16;
+            }
         };
-        auto issue = [&](int slot) {
+        auto issue = [&](uint32_t dst) {
             if (ftile < total_tiles) {
-                const uint32_t dst = raw_dst + slot * kRawSlot;
-                const int sb = fst >> 1, hh = fst & 1;
+                const int hh = fst & 1;
                 if (FMT == 0) {
-                    const uint8_t* blk = fw + (long)sb * SZ_Q4_K;
-                    cp_async16(dst + 64, blk);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) cp_async16(dst + 16 * i, blk + 16 + hh * 64 + i * 16);
+                    const uint8_t* q = fw + hh * 64;
+                    cp_async16(dst, q);
+                    cp_async16(dst + 16, q + 16);
+                    if (part == 0 || hh == 1) cp_async16(dst + 32, fw - 16 - part * 32);
                 } else {
-                    const int nrb = 4 * nblk, fi = frw * nblk + sb;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) cp_async16(dst + 16 * i, fw + (long)(4 * hh + i) * nrb * 16 + fi * 16);
-#pragma unroll
-                    for (int i = 0; i < 2; i++) cp_async16(dst + 64 + 16 * i, fw + (long)nrb * 128 + (long)(2 * hh + i) * nrb * 16 + fi * 16);
-                    cp_async8(dst + 128, fw + (long)nrb * 192 + fi * 16 + hh * 8);
-                    cp_async4(dst + 136, fw + (long)nrb * 208 + (fi >> 1) * 4);
+                    const uint8_t* q = fw + (long)(4 * hh) * c16;
+                    cp_async16(dst, q);
+                    cp_async16(dst + 16, q + 2 * c16);
+                    cp_async16(dst + 32, fw + (long)(8 + 2 * hh) * c16);
+                    if (part == 0) {
+                        cp_async8(dst + 64, fw + (long)12 * c16 + hh * 8);
+                        cp_async4(dst + 72, fitem + (long)13 * c16 + (ffi >> 1) * 4);
+                    }
                 }
-                if (frow0 >= 0) cp_async16(dst + 96, p.xq + (long)frow0 * p.Kc + fst * 128 + pc * 16);
-                if (frow1 >= 0) cp_async16(dst + 112, p.xq + (long)frow1 * p.Kc + fst * 128 + pc * 16);
-                if (hh == 1 && frow2 >= 0) {
-                    if ((r & 1) == 0) cp_async4(dst + (FMT == 0 ? 80 : 140), p.xd + (long)frow2 * nblk + sb);
-                    if (FMT == 0) cp_async16(dst + 128, p.xbs + (long)frow2 * (p.Kc / 16) + sb * 16 + (r & 1) * 8);
+                if (fxq) { cp_async16(dst + 48, fxq); fxq += 128; }
+                if (hh == 1) {
+                    if (FMT == 0 && fbs) { cp_async16(dst + 64, fbs); fbs += 16; }
+                    if (fdx) { cp_async4(dst + (FMT == 0 ? 64 : 76), fdx); fdx += 1; }
+                    fw += FMT == 0 ? SZ_Q4_K : 16;
+                    ffi++;
                 }
                 if (++fst == nst) { fst = 0; ftile += gridDim.x; enter_tile(); }
             }
             cp_async_commit();
         };
         enter_tile();
-        for (int i = 0; i < kGRaw; i++) issue(i);
-        unsigned cc = 0;
+        for (int i = 0; i < kGRaw; i++) issue(raw_dst + i * kRawSlot);
+        int slot = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int4 ti = __ldg(p.tinfo + tile);
             const int n_valid = ti.w;
-            for (int st = 0; st < nst; st++, it++, cc++) {
-                const int slot = cc % kGRaw, stage = it % kGStages, hh = st & 1;
+            int dsel = ((ti.y + r) & 3) * nblk;   // Q6_K: which half of the fetched word holds this block's d
+            for (int st = 0; st < nst; st++) {
+                const int hh = st & 1;
+                const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && tile == 0 && st < 96;
+                if (tr) p.trace[(0 * 96 + st) * 4 + 0] = clock64();
                 cp_async_wait<kGRaw - 1>();
+                if (tr) p.trace[(0 * 96 + st) * 4 + 1] = clock64();
                 const uint4* rs = reinterpret_cast<const uint4*>(raw_src + slot * kRawSlot);
-                uint4 f[9];
-#pragma unroll
-                for (int i = 0; i < 9; i++) f[i] = rs[i];
-                issue(slot);   // refill the slot just read (thread-private bytes: no barrier involved)
-                bar_wait(smem_u32(&misc.smem_free[stage]), ((it / kGStages) & 1) ^ 1);
+                const uint4 f0 = rs[0], f1 = rs[1], f2 = rs[2], f3 = rs[3], f4 = rs[4];
+                issue(raw_dst + slot * kRawSlot);   // refill the slot just read (thread-private bytes: no barrier involved)
+                slot = slot == kGRaw - 1 ? 0 : slot + 1;
+                bar_wait(smem_u32(&misc.smem_free[stage]), sphase ^ 1);
+                if (tr) p.trace[(0 * 96 + st) * 4 + 2] = clock64();
                 uint8_t* arow = smem + stage * kGA + r * 128;
+                const uint4 z = make_uint4(0, 0, 0, 0);
                 if (FMT == 0) {
                     // chunk c = 2 hh + part (32 bytes of qs): low nibbles = sub-block 2c (elements 64c .. 64c+31), high nibbles = sub-block 2c+1
-#pragma unroll
-                    for (int part = 0; part < 2; part++) {
-                        const uint4 q0 = f[2 * part], q1 = f[2 * part + 1];
-                        const int pi = 4 * part;
-                        *reinterpret_cast<uint4*>(arow + (((pi + 0) ^ sw) << 4)) = make_uint4(q0.x & 0x0F0F0F0Fu, q0.y & 0x0F0F0F0Fu, q0.z & 0x0F0F0F0Fu, q0.w & 0x0F0F0F0Fu);
-                        *reinterpret_cast<uint4*>(arow + (((pi + 1) ^ sw) << 4)) = make_uint4(q1.x & 0x0F0F0F0Fu, q1.y & 0x0F0F0F0Fu, q1.z & 0x0F0F0F0Fu, q1.w & 0x0F0F0F0Fu);
-                        *reinterpret_cast<uint4*>(arow + (((pi + 2) ^ sw) << 4)) =
-                            make_uint4((q0.x >> 4) & 0x0F0F0F0Fu, (q0.y >> 4) & 0x0F0F0F0Fu, (q0.z >> 4) & 0x0F0F0F0Fu, (q0.w >> 4) & 0x0F0F0F0Fu);
-                        *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) =
-                            make_uint4((q1.x >> 4) & 0x0F0F0F0Fu, (q1.y >> 4) & 0x0F0F0F0Fu, (q1.z >> 4) & 0x0F0F0F0Fu, (q1.w >> 4) & 0x0F0F0F0Fu);
-                    }
-                    misc.hdr[stage][r] = f[4];
-                    if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
-                        const uint32_t hw[4] = {f[4].x, f[4].y, f[4].z, f[4].w};
+                    const int pi = 4 * part;
+                    *reinterpret_cast<uint4*>(arow + (((pi + 0) ^ sw) << 4)) = make_uint4(f0.x & 0x0F0F0F0Fu, f0.y & 0x0F0F0F0Fu, f0.z & 0x0F0F0F0Fu, f0.w & 0x0F0F0F0Fu);
+                    *reinterpret_cast<uint4*>(arow + (((pi + 1) ^ sw) << 4)) = make_uint4(f1.x & 0x0F0F0F0Fu, f1.y & 0x0F0F0F0Fu, f1.z & 0x0F0F0F0Fu, f1.w & 0x0F0F0F0Fu);
+                    *reinterpret_cast<uint4*>(arow + (((pi + 2) ^ sw) << 4)) =
+                        make_uint4((f0.x >> 4) & 0x0F0F0F0Fu, (f0.y >> 4) & 0x0F0F0F0Fu, (f0.z >> 4) & 0x0F0F0F0Fu, (f0.w >> 4) & 0x0F0F0F0Fu);
+                    *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) =
+                        make_uint4((f1.x >> 4) & 0x0F0F0F0Fu, (f1.y >> 4) & 0x0F0F0F0Fu, (f1.z >> 4) & 0x0F0F0F0Fu, (f1.w >> 4) & 0x0F0F0F0Fu);
+                    if (part == 0) misc.hdr[stage][r] = f2;
+                    else if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
+                        const uint32_t hw[4] = {f2.x, f2.y, f2.z, f2.w};
                         int sc, mn[8];
 #pragma unroll
                         for (int j = 0; j < 8; j++) q4k_scale_min(hw, j, sc, mn[j]);
@@ -212,54 +224,46 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 } else {
                     // element 32 g + l of the half (l = 16 part + 0..15): g = 0 ql[l] & 15 | (qh & 3) << 4, g = 1 ql[32 + l] & 15 | (qh >> 2 & 3) << 4,
                     // g = 2 ql[l] >> 4 | (qh >> 4 & 3) << 4, g = 3 ql[32 + l] >> 4 | (qh >> 6 & 3) << 4; stored as q - 32 in int8
+                    const uint32_t a[4] = {f0.x, f0.y, f0.z, f0.w}, b[4] = {f1.x, f1.y, f1.z, f1.w}, h[4] = {f2.x, f2.y, f2.z, f2.w};
+                    uint32_t v[4][4];
 #pragma unroll
-                    for (int part = 0; part < 2; part++) {
-                        const uint4 wa = f[part], wb = f[2 + part], wh = f[4 + part];
-                        const uint32_t a[4] = {wa.x, wa.y, wa.z, wa.w}, b[4] = {wb.x, wb.y, wb.z, wb.w}, h[4] = {wh.x, wh.y, wh.z, wh.w};
-                        uint32_t v[4][4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            v[0][i] = (a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u);
-                            v[1][i] = (b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u);
-                            v[2][i] = ((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u);
-                            v[3][i] = ((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u);
-                        }
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {   // q - 32 per byte: flip bit 5, then copy it into bits 6 and 7 (no carries between bytes)
-                                const uint32_t tt = v[g][i] ^ 0x20202020u;
-                                v[g][i] = tt + (tt & 0x20202020u) * 6u;
-                            }
-                            *reinterpret_cast<uint4*>(arow + (((2 * g + part) ^ sw) << 4)) = make_uint4(v[g][0], v[g][1], v[g][2], v[g][3]);
-                        }
+                    for (int i = 0; i < 4; i++) {
+                        v[0][i] = (a[i] & 0x0F0F0F0Fu) | ((h[i] << 4) & 0x30303030u);
+                        v[1][i] = (b[i] & 0x0F0F0F0Fu) | ((h[i] << 2) & 0x30303030u);
+                        v[2][i] = ((a[i] >> 4) & 0x0F0F0F0Fu) | (h[i] & 0x30303030u);
+                        v[3][i] = ((b[i] >> 4) & 0x0F0F0F0Fu) | ((h[i] >> 2) & 0x30303030u);
                     }
-                    const int fi = ((ti.y + r) & 3) * nblk + (st >> 1);
-                    const uint32_t dbits = (fi & 1) ? (f[8].z >> 16) : (f[8].z & 0xffffu);
-                    misc.hdr[stage][r] = make_uint4(f[8].x, f[8].y, __float_as_uint(fp16_bits_to_f32((uint16_t)dbits)), 0);
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {   // q - 32 per byte: flip bit 5, then copy it into bits 6 and 7 (no carries between bytes)
+                            const uint32_t tt = v[g][i] ^ 0x20202020u;
+                            v[g][i] = tt + (tt & 0x20202020u) * 6u;
+                        }
+                        *reinterpret_cast<uint4*>(arow + (((2 * g + part) ^ sw) << 4)) = make_uint4(v[g][0], v[g][1], v[g][2], v[g][3]);
+                    }
+                    if (part == 0) {
+                        const uint32_t dbits = (dsel & 1) ? (f4.z >> 16) : (f4.z & 0xffffu);
+                        misc.hdr[stage][r] = make_uint4(f4.x, f4.y, __float_as_uint(fp16_bits_to_f32((uint16_t)dbits)), 0);
+                    }
+                    dsel += hh;
                 }
-                // activations: pieces (n, pc) and (16 + n, pc)
+                // activations: piece (bn, pc)
                 uint8_t* Bs = smem + kOffB + stage * kGB;
-                const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int n = (r >> 3) + 16 * u;
-                    const uint4 bv = n < n_valid ? f[6 + u] : z;
-                    if (FMT == 0) {
-                        *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = bv;
-                    } else {   // a 16-byte piece is one Q6_K sub-block: rows 0-31 keep the even pieces, rows 32-63 the odd ones
-                        *reinterpret_cast<uint4*>(Bs + n * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? z : bv;
-                        *reinterpret_cast<uint4*>(Bs + (kGN + n) * 128 + ((pc ^ (n & 7)) << 4)) = (pc & 1) ? bv : z;
-                    }
+                const uint4 bv = bn < n_valid ? f3 : z;
+                if (FMT == 0) {
+                    *reinterpret_cast<uint4*>(Bs + bn * 128 + ((pc ^ (bn & 7)) << 4)) = bv;
+                } else {   // a 16-byte piece is one Q6_K sub-block: rows 0-31 keep the even pieces, rows 32-63 the odd ones
+                    *reinterpret_cast<uint4*>(Bs + bn * 128 + ((pc ^ (bn & 7)) << 4)) = (pc & 1) ? z : bv;
+                    *reinterpret_cast<uint4*>(Bs + (kGN + bn) * 128 + ((pc ^ (bn & 7)) << 4)) = (pc & 1) ? bv : z;
                 }
-                if (hh == 1 && r < 64) {   // token scales, and (Q4_K) the sixteen 16-value sums of the super-block as fp16
-                    const int n2 = r >> 1, kg = r & 1;
-                    const bool ok = n2 < n_valid;
-                    if (kg == 0) misc.dxs[stage][n2] = ok ? __uint_as_float(FMT == 0 ? f[5].x : f[8].w) : 0.f;
-                    if (FMT == 0) {
+                if (hh == 1 && pt < 96) {   // token scales, and (Q4_K) the sixteen 16-value sums of the super-block as fp16
+                    if (pt >= 64) misc.dxs[stage][pt - 64] = pt - 64 < n_valid ? __uint_as_float(FMT == 0 ? f4.x : f4.w) : 0.f;
+                    else if (FMT == 0) {
+                        const int n2 = pt >> 1, kg = pt & 1;
                         uint4 vv = z;
-                        if (ok) {
-                            const uint32_t bw[4] = {f[8].x, f[8].y, f[8].z, f[8].w};
+                        if (n2 < n_valid) {
+                            const uint32_t bw[4] = {f4.x, f4.y, f4.z, f4.w};
 #define KTB_S16(w, hi) ((int)(short)((hi) ? ((w) >> 16) : ((w) & 0xffffu)))
                             vv = make_uint4(h2(KTB_S16(bw[0], 0), KTB_S16(bw[0], 1)), h2(KTB_S16(bw[1], 0), KTB_S16(bw[1], 1)), h2(KTB_S16(bw[2], 0), KTB_S16(bw[2], 1)),
                                             h2(KTB_S16(bw[3], 0), KTB_S16(bw[3], 1)));
@@ -271,6 +275,8 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) bar_arrive(smem_u32(&misc.ab_full[stage]));
+                if (tr) p.trace[(0 * 96 + st) * 4 + 3] = clock64();
+                if (++stage == kGStages) { stage = 0; sphase ^= 1; }
             }
         }
         cp_async_wait<0>();
@@ -278,11 +284,16 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
         // ========================================================================== tensor-core issuer (converged warp)
         constexpr uint32_t idesc_i8 = FMT == 0 ? instr_desc(2, 0, 1, 0, 0, kGM, kGN) : instr_desc(2, 1, 1, 0, 0, kGM, 2 * kGN);   // s32 += (u8 | s8) . s8
         constexpr uint32_t idesc_f16 = instr_desc(1, 0, 0, 0, 0, kGM, kGN);
+        unsigned it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int st = 0; st < nst; st++, it++) {
-                const int stage = it % kGStages, buf = it & 1;
-                bar_wait(smem_u32(&misc.ab_full[stage]), (it / kGStages) & 1);
+                const int buf = it & 1;
+                const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && tile == 0 && st < 96;
+                if (tr) p.trace[(1 * 96 + st) * 4 + 0] = clock64();
+                bar_wait(smem_u32(&misc.ab_full[stage]), sphase);
+                if (tr) p.trace[(1 * 96 + st) * 4 + 1] = clock64();
                 bar_wait(smem_u32(&misc.tmem_free[buf]), ((it >> 1) & 1) ^ 1);
+                if (tr) p.trace[(1 * 96 + st) * 4 + 2] = clock64();
                 tc_fence_after();
                 const uint32_t a = base + stage * kGA, b = base + kOffB + stage * kGB, d = tmem + buf * 256;
 #pragma unroll
@@ -292,12 +303,15 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                     mma_f16(d + 128, smem_desc(base + kOffA2 + stage * kGA2, 128, 256, kLayoutNone), smem_desc(base + kOffB2 + stage * kGB2, 128, 256, kLayoutNone), idesc_f16, 0);
                 mma_commit(smem_u32(&misc.smem_free[stage]));
                 mma_commit(smem_u32(&misc.tmem_full[buf]));
+                if (tr) p.trace[(1 * 96 + st) * 4 + 3] = clock64();
+                if (++stage == kGStages) { stage = 0; sphase ^= 1; }
             }
         }
     } else {
         // ========================================================================== epilogue: 8 warps = 128 rows x 2 column halves
         const int ew = warp - kGProdWarps - 1, sp = warp & 3, ch = ew >> 2, row = 32 * sp + lane;
         const uint32_t tbase = tmem + ((uint32_t)(32 * sp) << 16) + 16 * ch;
+        unsigned it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int4 ti = __ldg(p.tinfo + tile);
             float acc[16];
@@ -305,8 +319,11 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
 #pragma unroll
             for (int n = 0; n < 16; n++) { acc[n] = 0.f; isum[n] = 0; }
             for (int st = 0; st < nst; st++, it++) {
-                const int stage = it % kGStages, buf = it & 1, hh = st & 1;
+                const int buf = it & 1, hh = st & 1;
+                const bool tr = p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tile == 0 && st < 96;
+                if (tr) p.trace[(2 * 96 + st) * 4 + 0] = clock64();
                 bar_wait(smem_u32(&misc.tmem_full[buf]), (it >> 1) & 1);
+                if (tr) p.trace[(2 * 96 + st) * 4 + 1] = clock64();
                 tc_fence_after();
                 const uint4 hd = misc.hdr[stage][row];
                 const uint32_t hw[4] = {hd.x, hd.y, hd.z, hd.w};
@@ -365,6 +382,8 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { bar_arrive(smem_u32(&misc.tmem_free[buf])); bar_arrive(smem_u32(&misc.smem_free[stage])); }
+                if (tr) p.trace[(2 * 96 + st) * 4 + 3] = clock64();
+                if (++stage == kGStages) { stage = 0; sphase ^= 1; }
             }
 #pragma unroll
             for (int n = 0; n < 16; n++)
@@ -455,6 +474,8 @@ struct GrpScratch {
     float *xd = nullptr, *ad = nullptr, *g = nullptr, *u = nullptr, *dd = nullptr;
     int16_t *xbs = nullptr, *abs16 = nullptr;
 };
+static long long* g_grp_trace = nullptr;
+void grouped_set_trace(long long* t) { g_grp_trace = t; }
 static GrpScratch g_grp[64];   // one arena per device, shared by every handle (calls on one device are stream-ordered by the caller)
 
 static int grp_ensure(int dev, int tokens, int k, int E, int H, int I) {
@@ -530,15 +551,15 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
         GrpGemmParams gp{};
         gp.R = I; gp.Kc = H; gp.xq = g.xq; gp.xd = g.xd; gp.xbs = g.xbs; gp.rowmap = g.tokmap; gp.tinfo = g.tinfo_gu; gp.nt_prefix = g.nt_prefix; gp.E = E;
         gp.expert_bytes = (long)I * (H / 256) * SZ_Q4_K;
-        gp.w = reinterpret_cast<const uint8_t*>(c.gate_proj); gp.out = g.g;
+        gp.w = reinterpret_cast<const uint8_t*>(c.gate_proj); gp.out = g.g; gp.trace = g_grp_trace;
         grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
-        gp.w = reinterpret_cast<const uint8_t*>(c.up_proj); gp.out = g.u;
+        gp.w = reinterpret_cast<const uint8_t*>(c.up_proj); gp.out = g.u; gp.trace = nullptr;
         grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
         grp_act_quant_kernel<<<(P * (I / 256) + 7) / 8, 256, 0, s>>>(g.g, g.u, g.offsets, E, I, c.use_silu, g.aq, g.ad, g.abs16);
         GrpGemmParams gd{};
         gd.R = H; gd.Kc = I; gd.xq = g.aq; gd.xd = g.ad; gd.xbs = g.abs16; gd.rowmap = nullptr; gd.tinfo = g.tinfo_d; gd.nt_prefix = g.nt_prefix;
         gd.E = E; gd.expert_bytes = (long)H * (I / 256) * (fd == FMT_Q6K4T ? SZ_Q6_K : SZ_Q4_K);
-        gd.w = reinterpret_cast<const uint8_t*>(c.down_proj); gd.out = g.dd;
+        gd.w = reinterpret_cast<const uint8_t*>(c.down_proj); gd.out = g.dd; gd.trace = g_grp_trace ? g_grp_trace + 3 * 96 * 4 : nullptr;
         if (fd == FMT_Q6K4T) grouped_gemm_kernel<1><<<grid, kGThreads, kGSmem, s>>>(gd);
         else grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gd);
         grp_combine_kernel<<<dim3((H + 255) / 256, T), 256, 0, s>>>(g.dd, g.pos, w_c, T, k, H, bsz, t0, o_c, c.hidden_type);

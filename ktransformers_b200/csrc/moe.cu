@@ -572,10 +572,12 @@ extern "C++" {
 namespace ktb {
 bool grouped_ok(const ktb200_moe* m, int k);
 int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, const float* weights, const void* input, void* output, const int* bsz, cudaStream_t s);
+void grouped_set_trace(long long* t);
 }
 }
 // qlen from which the per-expert tensor-core GEMMs (grouped.cu) replace the per-pair GEMV kernels: the reference makes the
 // same split between MOE::forward_one and MOE::forward_many (moe.cpp:367-377, threshold group_min_len)
+void ktb200_debug_grouped(long long* trace_dev) { ktb::grouped_set_trace(trace_dev); }
 static int grouped_min_qlen() {
     static const int v = [] { const char* e = getenv("KTB200_GROUPED_MIN"); return e ? atoi(e) : 48; }();
     return v;

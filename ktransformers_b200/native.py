@@ -89,6 +89,7 @@ SYMBOLS = {
     "ktb200_mla_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "ktb200_mla_decode": (_I, [C.POINTER(MlaParams), _VP]),
     "ktb200_debug_mla": (None, [_VP]),
+    "ktb200_debug_grouped": (None, [_VP]),
     "ktb200_mla_absorb_q": (_I, [_VP, _L, _L, _VP, _I, _I, _I, _VP, _I, _VP]),
     "ktb200_mla_absorb_o": (_I, [_VP, _VP, _I, _I, _I, _VP, _I, _VP]),
     "ktb200_add_rmsnorm": (_I, [_VP, _VP, _VP, C.c_float, _VP, _I, _I, _VP]),

@@ -29,3 +29,14 @@ for qlen in [int(v) for v in os.environ.get("QLENS", "64,256,1024,4096").split("
     ms = e0.elapsed_time(e1) / n
     flops = 2.0 * qlen * k * 3 * H * I
     print(f"qlen {qlen}: {ms:.3f} ms  {qlen / ms * 1e3:.0f} tok/s  {flops / ms / 1e9:.1f} TFLOP/s-equivalent  (KTB200_GROUPED_MIN={os.environ.get('KTB200_GROUPED_MIN', '48')})", flush=True)
+
+if os.environ.get("TRACE"):
+    tr = torch.zeros(2 * 3 * 96 * 4, dtype=torch.int64, device="cuda")
+    lib.ktb200_debug_grouped(tr.data_ptr()); run(); torch.cuda.synchronize(); lib.ktb200_debug_grouped(None)
+    t = tr.cpu().numpy().reshape(2, 3, 96, 4)
+    for kname, kk in (("gate (Q4_K)", 0), ("down (Q6_K)", 1)):
+        t0 = t[kk, 0, 0, 0]
+        print(f"--- {kname}: cycles since the producer's first stage; P = wait_group done / smem_free seen / arrived, M = ab_full seen / tmem_free seen / committed, E = tmem_full seen / arrived")
+        for st in range(0, 40):
+            P, M, E = t[kk, 0, st] - t0, t[kk, 1, st] - t0, t[kk, 2, st] - t0
+            print(f"st {st:2d}  P {P[0]:6d} {P[1]:6d} {P[2]:6d} {P[3]:6d} | M {M[0]:6d} {M[1]:6d} {M[2]:6d} {M[3]:6d} | E {E[0]:6d} {E[1]:6d} {E[3]:6d}")
