@@ -257,6 +257,8 @@ class KTransformersExperts(BaseInjectedModule, KExpertsBase):
         BaseInjectedModule.__init__(self, key, gguf_loader, config, orig_module, prefill_device, generate_device, **kwargs)
         KExpertsBase.__init__(self, key, gguf_loader, config, orig_module, generate_device, **kwargs)
         n = len(orig_module)
+        prefill_op = None if prefill_op == "None" else prefill_op        # YAML spells it as a string (experts.py:1287-1290)
+        generate_op = None if generate_op == "None" else generate_op
         self.generate_experts = EXPERTS_MAP[generate_op](key, gguf_loader, config, n, device=generate_device, **kwargs) if generate_op else None
         self.prefill_experts = EXPERTS_MAP[prefill_op](key, gguf_loader, config, n, device=prefill_device, **kwargs) if prefill_op else None
         self.gpu_mlp_type = prefill_op
@@ -307,6 +309,27 @@ class KTransformersExperts(BaseInjectedModule, KExpertsBase):
             self.unload()
         else:
             raise ValueError("mode must be either InferenceState.GENERATE, InferenceState.PREFILL or InferenceState.UNLOAD")
+
+
+class KTransformersExpertsV2(KTransformersExperts):
+    """experts.py:1273-1350: the balance-serve variant whose forward carries `bsz_tensor` (device-side live batch size) and a
+    CUDA-graph slot.  With `prefill_op: None` the generate experts serve both phases (one GPU-resident KExpertsB200: per-pair
+    GEMV kernels for decode batches, the grouped tensor-core path from KTB200_GROUPED_MIN tokens up)."""
+
+    def forward(self, input_tensor, expert_ids, weights, bsz_tensor=None, cuda_graph_idx=0):
+        if self.mode == InferenceState.GENERATE or (self.mode == InferenceState.PREFILL and self.prefill_experts is None):
+            assert self.generate_experts is not None, "generate_experts is None"
+            return self.generate_experts.forward(input_tensor, expert_ids, weights, bsz_tensor, cuda_graph_idx)
+        if self.mode == InferenceState.PREFILL:
+            return self.prefill_experts.forward(input_tensor, expert_ids, weights, bsz_tensor, cuda_graph_idx)
+        raise ValueError("load or set_inference_mode before forward")
+
+    def load(self, w: dict = None, mode: InferenceState = None, warmup: bool = True):
+        if (mode or InferenceState.GENERATE) == InferenceState.PREFILL and self.prefill_experts is None:
+            self.generate_experts.load(w, warmup=warmup)
+            self.device, self.mode = self.generate_experts.device, InferenceState.PREFILL
+            return
+        super().load(w, mode, warmup)
 
 
 class _KDeepseekMoEMixin:
@@ -465,3 +488,34 @@ class KDeepseekV3MoE(_KDeepseekMoEMixin, BaseInjectedModule, _V3):
 
 class KDeepseekV2MoE(_KDeepseekMoEMixin, BaseInjectedModule, _V2):
     pass
+
+
+class KDeepseekV3MoEV2(_KDeepseekMoEMixin, BaseInjectedModule, _V3):
+    """experts.py:1172-1271: `forward(hidden_states, bsz_tensor, cuda_graph_idx)`; rows at or beyond `bsz_tensor[0]` are padding
+    and are left untouched by every kernel (kt-kernel/operators/common.hpp:255-258 semantics, on the device)."""
+
+    def forward(self, hidden_states, bsz_tensor=None, cuda_graph_idx=0):
+        if bsz_tensor is None:
+            return super().forward(hidden_states)
+        identity, orig_shape = hidden_states, hidden_states.shape
+        n_tok = hidden_states.numel() // orig_shape[-1]
+        gen = getattr(getattr(self, "experts", None), "generate_experts", None)
+        if n_tok <= self.BLOCK_MAX_TOKENS and getattr(gen, "ep_size", 1) == 1:
+            hs = self._block_handles(hidden_states)
+            if hs is not None:
+                cfg, moe, mlp = hs
+                x = hidden_states.reshape(n_tok, orig_shape[-1]).contiguous()
+                capturing = torch.cuda.is_current_stream_capturing()
+                y = KExpertsB200.output_gpu_map[gen.out_device][:n_tok] if capturing else torch.zeros_like(x)
+                idx = torch.zeros((n_tok, cfg.top_k), dtype=torch.int64, device=x.device)
+                wt = torch.zeros((n_tok, cfg.top_k), dtype=torch.float32, device=x.device)
+                native.check(native.lib().ktb200_moe_block_forward(C.byref(cfg), moe, mlp, n_tok, x.data_ptr(), y.data_ptr(), idx.data_ptr(),
+                                                                   wt.data_ptr(), bsz_tensor.data_ptr(), _stream(x.device)))
+                self.last_topk = (idx, wt)
+                return y.view(*orig_shape)
+        topk_idx, topk_weight = self.gate(hidden_states)
+        x = hidden_states.view(-1, orig_shape[-1])
+        y = self.experts(x, topk_idx, topk_weight, bsz_tensor, cuda_graph_idx).view(*orig_shape).to(device=x.device)
+        if self.config.n_shared_experts is not None:
+            y = y + self.shared_experts(identity).view(*orig_shape)
+        return y

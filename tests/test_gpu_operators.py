@@ -68,13 +68,13 @@ def test_injected_v3_moe_decodes_through_one_launch_and_matches_dense(tmp_path):
         assert isinstance(moe.experts.generate_experts, KExpertsB200) and moe.experts.generate_experts.handle is not None
 
         W = {k: torch.from_numpy(np.array(v)).cuda() for k, v in dense.items()}
-        for n_tok in (1, 3, 12):
+        for n_tok in (1, 3, 12, 64):     # block kernel | per-pair kernels | grouped tensor-core path (qlen >= KTB200_GROUPED_MIN)
             x = (torch.randn(1, n_tok, H, device="cuda") / 10).to(torch.bfloat16)
             n0 = native.launch_count()
             y = moe(x)
             torch.cuda.synchronize()
             launches = native.launch_count() - n0
-            assert (launches == 1) if n_tok <= 8 else (launches >= 5), launches     # block call | gate + 2 (experts) + shared-expert linears
+            assert (launches == 1) if n_tok <= 8 else (launches >= 5 if n_tok < 48 else launches >= 13), launches   # block call | gate + 2 (experts) + shared-expert linears | gate + 10 + linears
             # the reference's three-step control flow gives the same bits (decode) / dense fp32 agrees (all)
             if n_tok <= 8:
                 keep, KDeepseekV3MoE.BLOCK_MAX_TOKENS = KDeepseekV3MoE.BLOCK_MAX_TOKENS, 0
@@ -255,3 +255,33 @@ def test_fused_rmsnorm_and_mla_prep_match_the_module_code():
     assert (rows[:, 512:].float() - kpe_w[0, :, 0].float()).abs().max() <= tol(kpe_w)
     ckv_w = kvn(kva[:, :512])
     assert (rows[:, :512].float() - ckv_w.float()).abs().max() <= tol(ckv_w)
+
+
+def test_serve_rule_file_v2_classes_carry_bsz_tensor(tmp_path):
+    """balance-serve flavour (experts.py:1172-1350): KDeepseekV3MoEV2 / KTransformersExpertsV2 with a device-side batch size; rows
+    below bsz equal the V1 forward bit for bit, through the block kernel (3 tokens), the per-pair kernels (12) and the grouped path (64)."""
+    from ktransformers_b200.models.modeling_deepseek_v3 import DeepseekV3Config, DeepseekV3MoEOnlyForCausalLM
+    from ktransformers_b200.operators.experts import KDeepseekV3MoE, KDeepseekV3MoEV2, KTransformersExpertsV2
+    from ktransformers_b200.optimize.optimize import optimize_and_load_gguf
+    import ktransformers_b200.optimize.optimize as opt
+    _write_gguf(str(tmp_path / "tiny.gguf"))
+    rule = os.path.join(os.path.dirname(opt.__file__), "optimize_rules", "DeepSeek-V3-Chat-b200-serve.yaml")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        cfg = DeepseekV3Config(hidden_size=H, intermediate_size=I, moe_intermediate_size=I, n_routed_experts=E, n_shared_experts=1,
+                               num_experts_per_tok=K, n_group=2, topk_group=1, num_hidden_layers=2, first_k_dense_replace=1)
+        with torch.device("meta"):
+            model = DeepseekV3MoEOnlyForCausalLM(cfg)
+        optimize_and_load_gguf(model, rule, str(tmp_path), cfg, default_device="cuda")
+        moe = model.model.layers[1].mlp
+        assert isinstance(moe, KDeepseekV3MoEV2) and isinstance(moe.experts, KTransformersExpertsV2) and moe.experts.prefill_experts is None
+        for n_tok, live in ((3, 2), (12, 7), (64, 50)):
+            x = (torch.randn(1, n_tok, H, device="cuda") / 10).to(torch.bfloat16)
+            bsz = torch.tensor([live], dtype=torch.int32, device="cuda")
+            y2 = moe(x, bsz)
+            y1 = moe(x)      # bsz_tensor None -> the V1 control flow
+            torch.cuda.synchronize()
+            assert torch.equal(y2[0, :live].view(torch.int16), y1[0, :live].view(torch.int16)), n_tok
+    finally:
+        torch.set_default_dtype(old)

@@ -302,3 +302,24 @@ def test_pybind_module_exposes_the_reference_extension_surface():
         assert hasattr(ext.CPUInfer, meth), meth
     with pytest.raises(RuntimeError, match="null weight pointer"):       # C++ exception -> Python, like the reference
         ext.moe.B200_MOE(ext.moe.MOEConfig(8, 2, 512, 256))
+
+
+def test_shipped_rule_files_name_importable_classes():
+    """Every `class:` a shipped rule file names resolves (the serve flavour swaps in the V2 MoE / experts classes, experts.py:1172-1350)."""
+    import importlib
+    import yaml
+    import ktransformers_b200.optimize.optimize as opt
+    d = os.path.join(os.path.dirname(opt.__file__), "optimize_rules")
+    seen = set()
+    for fn in sorted(os.listdir(d)):
+        for rule in yaml.safe_load(open(os.path.join(d, fn))):
+            for part in ("match", "replace"):
+                c = rule.get(part, {}).get("class")
+                if c and c != "default":
+                    mod, name = c.rsplit(".", 1)
+                    assert hasattr(importlib.import_module(mod), name), c
+                    seen.add(name)
+    assert {"KDeepseekV3MoE", "KDeepseekV3MoEV2", "KTransformersExperts", "KTransformersExpertsV2"} <= seen
+    from ktransformers_b200.operators.experts import KTransformersExpertsV2
+    import inspect
+    assert list(inspect.signature(KTransformersExpertsV2.forward).parameters)[1:] == ["input_tensor", "expert_ids", "weights", "bsz_tensor", "cuda_graph_idx"]
