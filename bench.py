@@ -40,6 +40,7 @@ Q4_K, Q6_K, BF16, F32 = 12, 14, 30, 0
 BYTES_GATE_UP_PER_EXPERT = 2 * I * H * 144 // 256           # 16,515,072
 BYTES_DOWN_PER_EXPERT = H * I * 210 // 256                  # 12,042,240
 BYTES_PER_EXPERT = BYTES_GATE_UP_PER_EXPERT + BYTES_DOWN_PER_EXPERT   # 28,557,312
+PREFILL_TOKENS = 1024   # the reference's group_max_len (experts.py:209): one chunk of MOE::forward_many
 
 
 def committed_traffic(kernel):
@@ -415,6 +416,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctx", type=int, default=4096, help="cached tokens per sequence in the whole-step leg")
     ap.add_argument("--no-full-step", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the 1024-token grouped-GEMM leg")
     args = ap.parse_args()
     # This process owns the GPU and decodes on ONE stream: the persistent MoE-block kernel is launched as a plain grid
     # with programmatic dependent launch (its 148 CTAs become co-resident as the previous layer's CTAs exit) instead of
@@ -492,7 +494,7 @@ def main():
                       synth_blocks(Q6_K, H * I, dev, 1000 * l + 7))
         if l == 0:
             raw0 = dict(down=down.clone(), sg=sg.cpu().numpy(), su=su.cpu().numpy(), sd=sd.cpu().numpy())
-        cfg = native.MoeConfig(E_local, K, H, I, 64, 10, max(8, world), 1, gate.data_ptr(), up.data_ptr(), down.data_ptr(),
+        cfg = native.MoeConfig(E_local, K, H, I, 64, 10, PREFILL_TOKENS if world == 1 else max(8, world), 1, gate.data_ptr(), up.data_ptr(), down.data_ptr(),
                                Q4_K, Q4_K, Q6_K, hid, rank * E_local)
         h = C.c_void_p()
         native.check(lib.ktb200_moe_create(C.byref(cfg), local_rank, C.byref(h)))
@@ -767,6 +769,43 @@ def main():
         roof_down = {"kernel": "reduce_bulk_kernel<BulkQ6K4T> (down GEMV + weighted sum; separate-launch path)", "bound": "hbm", "achieved": achd, "peak": peak, "unit": "GB/s",
                      "frac": achd / peak, "bytes_per_launch": K * BYTES_DOWN_PER_EXPERT, "ms_per_launch": ms_dn}
 
+    # ---- prefill-sized batch through the same handles: router + grouped tensor-core expert GEMMs (MOE::forward_many) ---------
+    prefill = None
+    if rank == 0 and world == 1 and not args.no_prefill:
+        try:
+            Tp = PREFILL_TOKENS
+            gp_ = torch.Generator(device=dev); gp_.manual_seed(4242)
+            xp = (torch.randn((Tp, H), device=dev, generator=gp_) / 10).to(torch.bfloat16)
+            idp = torch.zeros((Tp, K), dtype=torch.int64, device=dev)
+            wtp = torch.zeros((Tp, K), dtype=torch.float32, device=dev)
+            yp = torch.zeros((Tp, H), dtype=torch.bfloat16, device=dev)
+
+            def prefill_layer(l):
+                Lr = layers[l % L]
+                native.check(lib.ktb200_moe_gate_forward(C.byref(Lr["gcfg"]), Tp, xp.data_ptr(), idp.data_ptr(), wtp.data_ptr(), None, None, S()))
+                native.check(lib.ktb200_moe_forward(Lr["moe"], Tp, K, idp.data_ptr(), wtp.data_ptr(), xp.data_ptr(), yp.data_ptr(), None, S()))
+            for l in range(L):
+                prefill_layer(l)
+            torch.cuda.synchronize()
+            n0 = native.launch_count()
+            reps = 2 * L
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for l in range(reps):
+                prefill_layer(l)        # L resident layer sets of 7.3 GB each: far larger than L2, every pass is cold
+            e1.record(); torch.cuda.synchronize()
+            ms_l = e0.elapsed_time(e1) / reps
+            experts_hit = int(torch.unique(idp).numel())
+            peak, how = measured_peak_gbs()
+            bytes_l = experts_hit * BYTES_PER_EXPERT
+            prefill = {"tokens": Tp, "ms_per_layer": ms_l, "launches_per_layer": (native.launch_count() - n0) // reps,
+                       "tok_s_moe_58_layers": Tp / (N_MOE_LAYERS * ms_l * 1e-3), "experts_hit": experts_hit,
+                       "tflops_equiv": 2.0 * Tp * K * 3 * H * I / (ms_l * 1e-3) / 1e12,
+                       "hbm": {"algorithmic_bytes": bytes_l, "achieved_GBps": bytes_l / (ms_l * 1e-3) / 1e9, "frac": bytes_l / (ms_l * 1e-3) / 1e9 / peak, "peak_source": how},
+                       "path": "router + count/scan/scatter + Q8_K quantise + 3 grouped tcgen05 kind::i8 GEMMs + combine (csrc/grouped.cu); parity: tests/test_gpu_parity.py -k grouped"}
+        except Exception as e:  # pragma: no cover
+            prefill = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- the whole decode step (attention + dense + MoE + lm_head), every rank its own token ------------------------
     full = None
     if not args.no_full_step:
@@ -810,7 +849,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
                 "gpu_launches": launches_per_step * args.steps, "cuda_graph": graph is not None,
                 "roofline": roof_block if roof_block else roof, "roofline_gate_up": roof, "roofline_down": roof_down, "cpu_baseline": cpu_baseline,
-                "parity_check": parity, "full_decode": full,
+                "parity_check": parity, "full_decode": full, "prefill_grouped": prefill,
                 "step_hbm": {"algorithmic_bytes_per_token_per_gpu": step_bytes, "achieved_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac_of_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / measured_peak_gbs()[0]}}
         print(json.dumps(line), flush=True)

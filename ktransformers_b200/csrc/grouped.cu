@@ -31,7 +31,7 @@ namespace ktb {
 
 using namespace umma;
 
-constexpr int kGM = 128, kGN = 32, kGStages = 3, kGRaw = 6;
+constexpr int kGM = 128, kGN = 32, kGStages = 3, kGRaw = 6, kGHdr = 6;
 constexpr int kGProdWarps = 8, kGEpiWarps = 8, kGThreads = (kGProdWarps + 1 + kGEpiWarps) * 32;   // 17 warps: at most 5 per scheduler, 96 registers each
 constexpr int kGA = kGM * 128;            // 16,384: 128 rows x 128 int8 of K, one swizzle atom column
 constexpr int kGB = 2 * kGN * 128;        //  8,192: 32 rows (Q4_K) or 64 rows (Q6_K even / odd variants)
@@ -41,10 +41,11 @@ constexpr int kOffB = kGStages * kGA, kOffA2 = kOffB + kGStages * kGB, kOffB2 = 
               kOffMiscG = kOffRaw + kGRaw * kRawSlot;
 
 struct GrpMisc {
-    unsigned long long ab_full[kGStages], smem_free[kGStages], tmem_full[2], tmem_free[2];
+    unsigned long long ab_full[kGStages], smem_free[kGStages], tmem_full[2], tmem_free[2], hdr_free[kGHdr];
     uint32_t tmem_base, pad[3];
-    float dxs[kGStages][kGN];
-    uint4 hdr[kGStages][kGM];   // Q4_K: the block header (d, dmin, 12 scale bytes); Q6_K: 8 scales of the half, d as f32
+    // what only the epilogue reads rides in its own, deeper ring: the operand stages are released by the MMAs alone
+    float dxs[kGHdr][kGN];
+    uint4 hdr[kGHdr][kGM];      // Q4_K: the block header (d, dmin, 12 scale bytes); Q6_K: 8 scales of the half, d as f32
 };
 constexpr int kGSmem = kOffMiscG + (int)sizeof(GrpMisc) + 1024;
 static_assert(kGSmem <= 227 * 1024, "shared memory budget");
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = p.Kc / QK_K, nst = 2 * nblk, MT = p.R / kGM;
     if (tid == 0) {
-        for (int s = 0; s < kGStages; s++) { bar_init(smem_u32(&misc.ab_full[s]), kGProdWarps); bar_init(smem_u32(&misc.smem_free[s]), 1 + kGEpiWarps); }
+        for (int s = 0; s < kGStages; s++) { bar_init(smem_u32(&misc.ab_full[s]), kGProdWarps); bar_init(smem_u32(&misc.smem_free[s]), 1); }
+        for (int s = 0; s < kGHdr; s++) bar_init(smem_u32(&misc.hdr_free[s]), kGEpiWarps);
         for (int b = 0; b < 2; b++) { bar_init(smem_u32(&misc.tmem_full[b]), 1); bar_init(smem_u32(&misc.tmem_free[b]), kGEpiWarps); }
         bar_fence_init();
     }
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
     const uint32_t tmem = misc.tmem_base;
     const int total_tiles = p.nt_prefix[p.E] * MT;
     int stage = 0, sphase = 0;   // shared-memory stage of the current iteration and how often it has wrapped (parity)
+    int hs = 0, hphase = 0;      // the same for the header ring
 
     if (warp < kGProdWarps) {
         // ========================================================================== producers: thread = (weight row r, half `part`)
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 issue(raw_dst + slot * kRawSlot);   // refill the slot just read (thread-private bytes: no barrier involved)
                 slot = slot == kGRaw - 1 ? 0 : slot + 1;
                 bar_wait(smem_u32(&misc.smem_free[stage]), sphase ^ 1);
+                bar_wait(smem_u32(&misc.hdr_free[hs]), hphase ^ 1);
                 if (tr) p.trace[(0 * 96 + st) * 4 + 2] = clock64();
                 uint8_t* arow = smem + stage * kGA + r * 128;
                 const uint4 z = make_uint4(0, 0, 0, 0);
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                         make_uint4((f0.x >> 4) & 0x0F0F0F0Fu, (f0.y >> 4) & 0x0F0F0F0Fu, (f0.z >> 4) & 0x0F0F0F0Fu, (f0.w >> 4) & 0x0F0F0F0Fu);
                     *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) =
                         make_uint4((f1.x >> 4) & 0x0F0F0F0Fu, (f1.y >> 4) & 0x0F0F0F0Fu, (f1.z >> 4) & 0x0F0F0F0Fu, (f1.w >> 4) & 0x0F0F0F0Fu);
-                    if (part == 0) misc.hdr[stage][r] = f2;
+                    if (part == 0) misc.hdr[hs][r] = f2;
                     else if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
                         const uint32_t hw[4] = {f2.x, f2.y, f2.z, f2.w};
                         int sc, mn[8];
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                     }
                     if (part == 0) {
                         const uint32_t dbits = (dsel & 1) ? (f4.z >> 16) : (f4.z & 0xffffu);
-                        misc.hdr[stage][r] = make_uint4(f4.x, f4.y, __float_as_uint(fp16_bits_to_f32((uint16_t)dbits)), 0);
+                        misc.hdr[hs][r] = make_uint4(f4.x, f4.y, __float_as_uint(fp16_bits_to_f32((uint16_t)dbits)), 0);
                     }
                     dsel += hh;
                 }
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                     *reinterpret_cast<uint4*>(Bs + (kGN + bn) * 128 + ((pc ^ (bn & 7)) << 4)) = (pc & 1) ? bv : z;
                 }
                 if (hh == 1 && pt < 96) {   // token scales, and (Q4_K) the sixteen 16-value sums of the super-block as fp16
-                    if (pt >= 64) misc.dxs[stage][pt - 64] = pt - 64 < n_valid ? __uint_as_float(FMT == 0 ? f4.x : f4.w) : 0.f;
+                    if (pt >= 64) misc.dxs[hs][pt - 64] = pt - 64 < n_valid ? __uint_as_float(FMT == 0 ? f4.x : f4.w) : 0.f;
                     else if (FMT == 0) {
                         const int n2 = pt >> 1, kg = pt & 1;
                         uint4 vv = z;
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 if (lane == 0) bar_arrive(smem_u32(&misc.ab_full[stage]));
                 if (tr) p.trace[(0 * 96 + st) * 4 + 3] = clock64();
                 if (++stage == kGStages) { stage = 0; sphase ^= 1; }
+                if (++hs == kGHdr) { hs = 0; hphase ^= 1; }
             }
         }
         cp_async_wait<0>();
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 bar_wait(smem_u32(&misc.tmem_full[buf]), (it >> 1) & 1);
                 if (tr) p.trace[(2 * 96 + st) * 4 + 1] = clock64();
                 tc_fence_after();
-                const uint4 hd = misc.hdr[stage][row];
+                const uint4 hd = misc.hdr[hs][row];
                 const uint32_t hw[4] = {hd.x, hd.y, hd.z, hd.w};
                 const uint32_t d = tbase + buf * 256;
                 if (FMT == 0) {
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                         tmem_wait_ld();
 #pragma unroll
                         for (int n = 0; n < 16; n++) {
-                            const float dx = misc.dxs[stage][16 * ch + n];
+                            const float dx = misc.dxs[hs][16 * ch + n];
                             acc[n] += (dw * dx) * (float)isum[n] - (dmin * dx) * __uint_as_float(ms[n]);
                             isum[n] = 0;
                         }
@@ -374,16 +379,16 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                         const float dw = __uint_as_float(hw[2]);
 #pragma unroll
                         for (int n = 0; n < 16; n++) {
-                            acc[n] += (dw * misc.dxs[stage][16 * ch + n]) * (float)isum[n];
+                            acc[n] += (dw * misc.dxs[hs][16 * ch + n]) * (float)isum[n];
                             isum[n] = 0;
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { bar_arrive(smem_u32(&misc.tmem_free[buf])); bar_arrive(smem_u32(&misc.smem_free[stage])); }
+                if (lane == 0) { bar_arrive(smem_u32(&misc.tmem_free[buf])); bar_arrive(smem_u32(&misc.hdr_free[hs])); }
                 if (tr) p.trace[(2 * 96 + st) * 4 + 3] = clock64();
-                if (++stage == kGStages) { stage = 0; sphase ^= 1; }
+                if (++hs == kGHdr) { hs = 0; hphase ^= 1; }
             }
 #pragma unroll
             for (int n = 0; n < 16; n++)
