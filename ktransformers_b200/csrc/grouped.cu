@@ -100,7 +100,7 @@ __global__ void grp_tiles_kernel(const int* nt_prefix, const int* offsets, int E
     tinfo[tile] = make_int4(lo, mt * kGM, p0, min(kGN, offsets[lo + 1] - p0));
 }
 
-// A producer thread's share of one stage, as it sits in its raw-ring slot (five 16-byte units, thread = (weight row, half)):
+// A producer thread's share of one stage, as it sits in its raw-ring slot (five 16-byte units, thread = (weight row, half `part`)):
 //   Q4_K: 0-1 the 32 bytes of qs of chunk 2 hh + part, 2 block header, 3 activation piece, 4 activation 16-sums (threads 0-63) or
 //         token scale (threads 64-95)
 //   Q6_K: 0-1 ql (16 bytes at l and at 32 + l), 2 qh, 3 activation piece, 4 = 8 scales | d (2 of 4 bytes) | token scale (threads 64-95)
@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
 
     if (warp < kGProdWarps) {
         // ========================================================================== producers: thread = (weight row r, half `part`)
-        const int pt = tid, r = pt >> 1, part = pt & 1, sw = r & 7, bn = pt >> 3, pc = pt & 7;
+        // `part` is warp-uniform (warps 0-3: first half of the row's share, warps 4-7: second) so that no branch below diverges
+        const int pt = tid, r = pt & (kGM - 1), part = pt >> 7, sw = r & 7, bn = pt >> 3, pc = pt & 7;
         const uint32_t raw_dst = base + kOffRaw + pt * kRawPitch;
         const uint8_t* raw_src = smem + kOffRaw + pt * kRawPitch;
         const int c16 = 4 * nblk * 16;   // Q6_K tiles: bytes between two 16-byte chunk planes of an item
@@ -216,14 +217,18 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                     *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) =
                         make_uint4((f1.x >> 4) & 0x0F0F0F0Fu, (f1.y >> 4) & 0x0F0F0F0Fu, (f1.z >> 4) & 0x0F0F0F0Fu, (f1.w >> 4) & 0x0F0F0F0Fu);
                     if (part == 0) misc.hdr[hs][r] = f2;
-                    else if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums
+                    if (hh == 1) {   // A2 row: [m_0 m_0 m_1 m_1 ... m_7 m_7] against the sixteen 16-value activation sums; 4 mins per part
                         const uint32_t hw[4] = {f2.x, f2.y, f2.z, f2.w};
-                        int sc, mn[8];
+                        int sc, mn[4];
+                        if (part == 0) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) q4k_scale_min(hw, j, sc, mn[j]);
-                        uint8_t* a2 = smem + kOffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16;
+                            for (int j = 0; j < 4; j++) q4k_scale_min(hw, j, sc, mn[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) q4k_scale_min(hw, 4 + j, sc, mn[j]);
+                        }
+                        uint8_t* a2 = smem + kOffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16 + part * 128;
                         *reinterpret_cast<uint4*>(a2) = make_uint4(h2(mn[0], mn[0]), h2(mn[1], mn[1]), h2(mn[2], mn[2]), h2(mn[3], mn[3]));
-                        *reinterpret_cast<uint4*>(a2 + 128) = make_uint4(h2(mn[4], mn[4]), h2(mn[5], mn[5]), h2(mn[6], mn[6]), h2(mn[7], mn[7]));
                     }
                 } else {
                     // element 32 g + l of the half (l = 16 part + 0..15): g = 0 ql[l] & 15 | (qh & 3) << 4, g = 1 ql[32 + l] & 15 | (qh >> 2 & 3) << 4,
