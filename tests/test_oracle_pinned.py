@@ -178,3 +178,32 @@ def test_shimmed_amx_backend_runs_the_reference_int4_moe():
             ref[t] += ((a / (1 + np.exp(-a))) * (uf[e] @ xf[t])) @ df[e].T * w[t, j]
     assert np.abs(out - ref).mean() / np.abs(ref).mean() < 0.35
     amx.moe_destroy(h)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_fp8_oracle_matches_the_references_triton_kernels(golden_dir, name):
+    """oracle/fp8_oracle.py against tests/golden/fp8_ref.npz — outputs of the reference's own act_quant / fp8_gemm_kernel
+    (fp8gemm.py) run by Triton's CPU interpreter (tests/golden/make_fp8_golden.py): scales exact, quantised bytes exact up to the
+    interpreter's two cast artifacts (fp32 -> e4m3 carry, fp32 -> bf16 truncation); the fp32 GEMM accumulator is bit-identical."""
+    from oracle import fp8_oracle as F
+    from oracle.bindings import bf16_to_f32, f32_to_bf16_bits
+    g = np.load(os.path.join(golden_dir, "fp8_ref.npz"))
+    x = bf16_to_f32(g[f"{name}_x"])
+    q, s = F.act_quant(x)
+    assert np.array_equal(s, g[f"{name}_s"])
+    # Triton's CPU interpreter casts fp32 -> e4m3 in software and drops the carry when rounding to nearest crosses a binade
+    # (124.16 -> 64 instead of 128; the GPU's cvt.rn gives 128): exactly those bytes differ, by one exponent step (8), and
+    # nothing else does
+    diff = q != g[f"{name}_q"]
+    assert diff.mean() < 0.03
+    assert ((q[diff] & 7) == 0).all() and (q[diff].astype(int) - g[f"{name}_q"][diff].astype(int) == 8).all()
+    v = np.abs(x.reshape(x.shape[0], -1, 128) / s[..., None]).reshape(x.shape)[diff]
+    assert (np.abs(F.e4m3_bytes_to_f32(q[diff])) >= v).all()          # the oracle rounded UP to the power of two, as RN must
+    # the GEMM is pinned on the golden's own quantised bytes
+    acc = F.fp8_gemm(g[f"{name}_q"], g[f"{name}_s"], g[f"{name}_w"], g[f"{name}_ws"])
+    # ... and is bit-exact at fp32: the interpreter narrows fp32 -> bf16 by truncation (the GPU rounds to nearest even), so the
+    # golden equals the upper 16 bits of this accumulator, every element
+    assert np.array_equal((acc.view(np.uint32) >> 16).astype(np.uint16), g[f"{name}_c"])
+    # weight_dequant (fp8gemm.py:63-73) x fp32 matmul agrees with the blockwise GEMM to fp8-activation accuracy
+    dense = x @ F.weight_dequant(g[f"{name}_w"], g[f"{name}_ws"]).T
+    assert np.abs(dense - acc).max() <= 0.08 * np.abs(dense).max()
