@@ -9,9 +9,9 @@ CPU restatement of the reference's FP8 linear — DeepSeek's 128-block e4m3 sche
 Pinned: tests/golden/fp8_ref.npz holds outputs of the reference's OWN Triton kernels, run on the CPU by Triton's interpreter
 (TRITON_INTERPRET=1; tests/golden/make_fp8_golden.py — the autotuner needs a device to time configs, so the script launches the
 un-tuned `fp8_gemm_kernel.fn` with the first of the reference's own configs).  tests/test_oracle_pinned.py checks this file
-against those vectors: scales exactly; quantised bytes exactly except where round-to-nearest carries into the next binade — the
-interpreter's software cast drops that carry (124.16 -> 64), the GPU's cvt.rn and this file give 128, and the test checks that
-this is the ONLY difference; the GEMM's fp32 accumulator (on the golden's own bytes) bit for bit — the interpreter narrows it to
+against those vectors: scales exactly; quantised bytes exactly except for two artifacts of the interpreter's software cast — it
+drops the carry when round-to-nearest crosses a binade (124.16 -> 64; the GPU's cvt.rn and this file give 128) and rounds exact
+ties away from zero instead of to even — and the test checks that these are the ONLY differences; the GEMM's fp32 accumulator (on the golden's own bytes) bit for bit — the interpreter narrows it to
 bf16 by truncation where the GPU rounds to nearest even, so the golden equals the accumulator's upper 16 bits."""
 from __future__ import annotations
 

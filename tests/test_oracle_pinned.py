@@ -191,14 +191,18 @@ def test_fp8_oracle_matches_the_references_triton_kernels(golden_dir, name):
     x = bf16_to_f32(g[f"{name}_x"])
     q, s = F.act_quant(x)
     assert np.array_equal(s, g[f"{name}_s"])
-    # Triton's CPU interpreter casts fp32 -> e4m3 in software and drops the carry when rounding to nearest crosses a binade
-    # (124.16 -> 64 instead of 128; the GPU's cvt.rn gives 128): exactly those bytes differ, by one exponent step (8), and
-    # nothing else does
-    diff = q != g[f"{name}_q"]
+    # Triton's CPU interpreter casts fp32 -> e4m3 in software: it drops the carry when rounding to nearest crosses a binade
+    # (124.16 -> 64 instead of 128) and rounds exact ties away from zero; the GPU's cvt.rn.satfinite and the oracle round to
+    # nearest even.  Exactly those bytes differ and nothing else does:
+    gq = g[f"{name}_q"]
+    diff = q != gq
     assert diff.mean() < 0.03
-    assert ((q[diff] & 7) == 0).all() and (q[diff].astype(int) - g[f"{name}_q"][diff].astype(int) == 8).all()
-    v = np.abs(x.reshape(x.shape[0], -1, 128) / s[..., None]).reshape(x.shape)[diff]
-    assert (np.abs(F.e4m3_bytes_to_f32(q[diff])) >= v).all()          # the oracle rounded UP to the power of two, as RN must
+    v = np.abs(x.reshape(x.shape[0], -1, 128) / s[..., None]).reshape(x.shape)
+    lo, hi = np.abs(F.e4m3_bytes_to_f32(q)), np.abs(F.e4m3_bytes_to_f32(gq))
+    carry = diff & ((q & 7) == 0)          # (1) RN carried into the next binade: the interpreter kept the old exponent
+    tie = diff & ~carry                    # (2) exact ties: the interpreter rounds half away from zero, RN (GPU, oracle) to even
+    assert (q[carry].astype(int) - gq[carry].astype(int) == 8).all() and (lo[carry] >= v[carry]).all()
+    assert (gq[tie].astype(int) - q[tie].astype(int) == 1).all() and (v[tie] == (lo[tie] + hi[tie]) / 2).all() and ((q[tie] & 1) == 0).all()
     # the GEMM is pinned on the golden's own quantised bytes
     acc = F.fp8_gemm(g[f"{name}_q"], g[f"{name}_s"], g[f"{name}_w"], g[f"{name}_ws"])
     # ... and is bit-exact at fp32: the interpreter narrows fp32 -> bf16 by truncation (the GPU rounds to nearest even), so the
