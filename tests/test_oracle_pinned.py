@@ -199,10 +199,12 @@ def test_fp8_oracle_matches_the_references_triton_kernels(golden_dir, name):
     assert diff.mean() < 0.03
     v = np.abs(x.reshape(x.shape[0], -1, 128) / s[..., None]).reshape(x.shape)
     lo, hi = np.abs(F.e4m3_bytes_to_f32(q)), np.abs(F.e4m3_bytes_to_f32(gq))
-    carry = diff & ((q & 7) == 0)          # (1) RN carried into the next binade: the interpreter kept the old exponent
-    tie = diff & ~carry                    # (2) exact ties: the interpreter rounds half away from zero, RN (GPU, oracle) to even
-    assert (q[carry].astype(int) - gq[carry].astype(int) == 8).all() and (lo[carry] >= v[carry]).all()
-    assert (gq[tie].astype(int) - q[tie].astype(int) == 1).all() and (v[tie] == (lo[tie] + hi[tie]) / 2).all() and ((q[tie] & 1) == 0).all()
+    step = q.astype(int) - gq.astype(int)
+    carry = diff & (step == 8)             # (1) RN carried into the next binade: the interpreter kept the old exponent
+    tie = diff & (step == -1)              # (2) exact ties: the interpreter rounds half away from zero, RN (GPU, oracle) to even
+    assert (diff == (carry | tie)).all()
+    assert ((q[carry] & 7) == 0).all() and (lo[carry] >= v[carry]).all()
+    assert (v[tie] == (lo[tie] + hi[tie]) / 2).all() and ((q[tie] & 1) == 0).all()
     # the GEMM is pinned on the golden's own quantised bytes
     acc = F.fp8_gemm(g[f"{name}_q"], g[f"{name}_s"], g[f"{name}_w"], g[f"{name}_ws"])
     # ... and is bit-exact at fp32: the interpreter narrows fp32 -> bf16 by truncation (the GPU rounds to nearest even), so the
