@@ -119,6 +119,21 @@ int ktb200_moe_forward_timed(ktb200_moe* moe, int qlen, int k, const int64_t* ex
 float* ktb200_moe_intermediate(ktb200_moe* moe);
 
 /* ------------------------------------------------------------------------------------------
+ * FP8 (e4m3, 128 x 128 block scales) linear — DeepSeek-V3's native checkpoint format.  Replaces KLinearFP8
+ * (archive/ktransformers/operators/linear.py:388-435) = act_quant + fp8_gemm of
+ * archive/ktransformers/ktransformers_ext/triton/fp8gemm.py:10-47, 104-192 (BASELINE configs 3 / 5: FP8 linears beside GGUF experts).
+ * weight: DEVICE ptr, e4m3 bytes [out][in] (16-byte aligned, in % 128 == 0); weight_scale_inv: DEVICE fp32 [ceil(out/128)][in/128].
+ * forward: x [qlen][in] -> y [qlen][out] in hidden_type (x is quantised per token and 128 values inside the kernel, exactly like
+ * act_quant; rows >= *bsz untouched).  An all-zero 128-block of x yields NaN outputs, as it does in the reference (0 / 0).
+ * TMA + tcgen05.mma.kind::f8f6f4 + TMEM; stream-ordered; everything is allocated at create -> CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ktb200_fp8_linear ktb200_fp8_linear;
+int ktb200_fp8_linear_create(int in_features, int out_features, const void* weight_e4m3_dev, const float* weight_scale_inv_dev, int hidden_type, int device,
+                             ktb200_fp8_linear** out);
+void ktb200_fp8_linear_destroy(ktb200_fp8_linear* l);
+int ktb200_fp8_linear_forward(ktb200_fp8_linear* l, int qlen, const void* x, void* y, const int* bsz, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dense quantised linear and gated MLP (shared experts / dense layers / projections / lm_head).
  * Replaces cpuinfer_ext.linear.Linear / mlp.MLP (archive ext_bindings.cpp, operators/llamafile/
  * linear.cpp:37-70, mlp.cpp:47-125) and the dequant->Marlin path of KLinearMarlin

@@ -1,0 +1,268 @@
+// FP8 (e4m3, 128 x 128 block scales) linear for decode batches — KLinearFP8 (archive/ktransformers/operators/linear.py:388-435)
+// = act_quant (fp8gemm.py:10-47) -> fp8_gemm (fp8gemm.py:104-192), DeepSeek-V3's native checkpoint format:
+//     s[t][kb] = max|x[t][128 kb .. +128]| / 448,   xq = e4m3(x / s)                         (per token and 128 of K)
+//     acc[t][n] += dot_e4m3(xq[t][kb], W[n][kb]) * s[t][kb] * scale_inv[n / 128][kb]          fp32, kb ascending
+//     y = cast(acc)
+// One byte per weight: a pure HBM stream.  The weights never pass through registers: TMA drops [128 rows x 128 bytes] boxes of W
+// into shared memory in the 128-byte-swizzle layout, which IS the K-major A operand of tcgen05.mma.kind::f8f6f4; the quantised
+// activations (16 token rows, padded) are the B operand; the products of two e4m3 values are exact in the fp32 accumulator (TMEM).
+// After every 128 of K (4 MMAs) the epilogue takes the partial dot out of TMEM and applies the two scales in the reference's order.
+//     grid = (ceil(N / 128) row tiles, K splits); 192 threads: warp 0 TMA producer (8-stage ring, 128 KB in flight), warp 1 issuer,
+//     warps 2-5 quantise x for the CTA's K range while the first weight boxes are in flight, then run the epilogue.
+// K splits add their fp32 partial sums with atomics into a zeroed workspace; the last CTA of a row tile converts and re-zeroes.
+#include <cuda.h>
+#include <cuda_fp8.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "handles.cuh"
+#include "umma.cuh"
+
+namespace ktb {
+using namespace umma;
+
+constexpr int kFT = 16;                    // token rows per pass (the MMA's N)
+constexpr int kFStages = 8, kFA = 128 * 128, kFB = kFT * 128, kFMaxKb = 40;
+constexpr int kFOffB = kFStages * kFA, kFOffS = kFOffB + kFMaxKb * kFB, kFOffMisc = kFOffS + kFT * kFMaxKb * 4;
+struct Fp8Misc {
+    unsigned long long a_full[kFStages], a_free[kFStages], d_full[2], d_free[2], b_ready;
+    uint32_t tmem_base;
+    int last;
+};
+constexpr int kFSmem = kFOffMisc + (int)sizeof(Fp8Misc) + 1024;
+
+struct Fp8Params {
+    const void* x;            // [T][K] hidden type
+    void* y;                  // [T][N]
+    const float* scale_inv;   // [ceil(N/128)][nkb]
+    float* ws;                // [kFT][N] fp32, zero between calls (K splits only)
+    unsigned* tickets;        // [row tiles], zero between calls
+    const int* bsz;
+    int hidden_type, T, K, N, nkb, kb_per_split, ksplit, t0;
+};
+
+__global__ void __launch_bounds__(192, 1) fp8_linear_kernel(const __grid_constant__ CUtensorMap wmap, const Fp8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    Fp8Misc& misc = *reinterpret_cast<Fp8Misc*>(smem + kFOffMisc);
+    float* a_s = reinterpret_cast<float*>(smem + kFOffS);   // [kFT][kb_per_split]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * 128;
+    const int kb0 = blockIdx.y * p.kb_per_split, nk = min(p.kb_per_split, p.nkb - kb0);
+    if (tid == 0) {
+        for (int s = 0; s < kFStages; s++) { bar_init(smem_u32(&misc.a_full[s]), 1); bar_init(smem_u32(&misc.a_free[s]), 1); }
+        for (int b = 0; b < 2; b++) { bar_init(smem_u32(&misc.d_full[b]), 1); bar_init(smem_u32(&misc.d_free[b]), 4); }
+        bar_init(smem_u32(&misc.b_ready), 4);
+        bar_fence_init();
+        tma_prefetch_desc(&wmap);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&misc.tmem_base), 32);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = misc.tmem_base;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- weight boxes: independent of x, start at once
+        if (lane == 0) {
+            for (int i = 0; i < nk; i++) {
+                const int s = i % kFStages;
+                bar_wait(smem_u32(&misc.a_free[s]), ((i / kFStages) & 1) ^ 1);
+                bar_expect_tx(smem_u32(&misc.a_full[s]), kFA);
+                tma_load_2d(base + s * kFA, &wmap, smem_u32(&misc.a_full[s]), (kb0 + i) * 128, row0);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- issuer (converged warp)
+        constexpr uint32_t idesc = instr_desc(1, 0, 0, 0, 0, 128, kFT);   // f32 += e4m3 . e4m3, K-major both
+        bar_wait(smem_u32(&misc.b_ready), 0);
+        for (int i = 0; i < nk; i++) {
+            const int s = i % kFStages, buf = i & 1;
+            bar_wait(smem_u32(&misc.a_full[s]), (i / kFStages) & 1);
+            bar_wait(smem_u32(&misc.d_free[buf]), ((i >> 1) & 1) ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                mma_f8(tmem + buf * kFT, smem_desc(base + s * kFA + j * 32, 16, 1024, kLayoutSw128), smem_desc(base + kFOffB + i * kFB + j * 32, 16, 1024, kLayoutSw128), idesc,
+                       j != 0);
+            mma_commit(smem_u32(&misc.a_free[s]));
+            mma_commit(smem_u32(&misc.d_full[buf]));
+        }
+    } else {
+        // ---------------------------------------------------------------- act_quant for this K range, then the epilogue
+        const int ew = warp - 2;
+        // rows T .. 15 of the B tiles: zeros (their accumulator columns are never read)
+        for (int i = (tid - 64); i < nk * (kFB / 16); i += 128) {
+            const int r = (i >> 3) & (kFT - 1);
+            if (r >= p.T) *reinterpret_cast<uint4*>(smem + kFOffB + i * 16) = make_uint4(0, 0, 0, 0);
+        }
+        for (int blk = ew; blk < p.T * nk; blk += 4) {   // one warp per (token, 128 of K); lane owns 4 consecutive values
+            const int t = blk / nk, kb = blk - t * nk;
+            const long off = (long)t * p.K + (long)(kb0 + kb) * 128 + lane * 4;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = load_hidden(p.x, off + e, p.hidden_type);
+            float am = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+            const float s = __fdiv_rn(am, 448.f);
+            uint32_t packed = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++)   // x / s in IEEE fp32, round to nearest even into e4m3 (0 / 0 = NaN like the reference)
+                packed |= (uint32_t)__nv_cvt_float_to_fp8(__fdiv_rn(v[e], s), __NV_SATFINITE, __NV_E4M3) << (8 * e);
+            *reinterpret_cast<uint32_t*>(smem + kFOffB + kb * kFB + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4) = packed;
+            if (lane == 0) a_s[t * p.kb_per_split + kb] = s;
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // a_s is read by all four epilogue warps
+        if (lane == 0) bar_arrive(smem_u32(&misc.b_ready));
+
+        const int sp = warp & 3, row = 32 * sp + lane;
+        float acc[kFT];
+#pragma unroll
+        for (int t = 0; t < kFT; t++) acc[t] = 0.f;
+        const float* sinv = p.scale_inv + (long)blockIdx.x * p.nkb + kb0;
+        for (int i = 0; i < nk; i++) {
+            const int buf = i & 1;
+            const float bs = __ldg(sinv + i);
+            bar_wait(smem_u32(&misc.d_full[buf]), (i >> 1) & 1);
+            tc_fence_after();
+            uint32_t d[kFT];
+            tmem_ld16(tmem + ((uint32_t)(32 * sp) << 16) + buf * kFT, d);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(smem_u32(&misc.d_free[buf]));
+#pragma unroll
+            for (int t = 0; t < kFT; t++)
+                if (t < p.T) acc[t] = __fadd_rn(acc[t], __fmul_rn(__fmul_rn(__uint_as_float(d[t]), a_s[t * p.kb_per_split + i]), bs));   // (dot * a_s) * b_s, then +=
+        }
+        const int n = row0 + row;
+        const int live = p.bsz ? max(0, min(p.T, *p.bsz - p.t0)) : p.T;   // rows at or beyond the live batch size stay untouched
+        if (p.ksplit == 1) {
+            if (n < p.N)
+#pragma unroll
+                for (int t = 0; t < kFT; t++)
+                    if (t < live) store_hidden(p.y, (long)t * p.N + n, p.hidden_type, acc[t]);
+        } else {
+            if (n < p.N)
+#pragma unroll
+                for (int t = 0; t < kFT; t++)
+                    if (t < p.T) atomicAdd(p.ws + (long)t * p.N + n, acc[t]);
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 64) misc.last = atomicAdd(p.tickets + blockIdx.x, 1u) == (unsigned)(p.ksplit - 1);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (misc.last) {
+                __threadfence();
+                if (n < p.N)
+                    for (int t = 0; t < p.T; t++) {
+                        const float v = __ldcg(p.ws + (long)t * p.N + n);
+                        p.ws[(long)t * p.N + n] = 0.f;
+                        if (t < live) store_hidden(p.y, (long)t * p.N + n, p.hidden_type, v);
+                    }
+                if (tid == 64) p.tickets[blockIdx.x] = 0;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 32);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn8)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn8 encode_tiled8() {
+    static EncodeTiledFn8 fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeTiledFn8)f;
+    }();
+    return fn;
+}
+}  // namespace ktb
+
+struct ktb200_fp8_linear {
+    int K, N, hidden_type, device, nkb, row_tiles, ksplit, kb_per_split;
+    const void* w;
+    const float* scale_inv;
+    CUtensorMap map;
+    float* ws;
+    unsigned* tickets;
+};
+
+extern "C" {
+
+int ktb200_fp8_linear_create(int in_features, int out_features, const void* weight_e4m3, const float* weight_scale_inv, int hidden_type, int device,
+                             ktb200_fp8_linear** out) {
+    using namespace ktb;
+    if (!out || !weight_e4m3 || !weight_scale_inv) { set_error("fp8_linear: null argument"); return KTB200_EINVAL; }
+    if (in_features <= 0 || out_features <= 0 || in_features % 128) { set_error("fp8_linear: in_features %d must be a positive multiple of 128 (act_quant block)", in_features); return KTB200_EINVAL; }
+    if (!is_hidden_type(hidden_type)) { set_error("fp8_linear: bad hidden_type %d", hidden_type); return KTB200_EINVAL; }
+    if ((uintptr_t)weight_e4m3 & 15) { set_error("fp8_linear: weight must be 16-byte aligned"); return KTB200_EINVAL; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return KTB200_ECUDA; }
+    EncodeTiledFn8 enc = encode_tiled8();
+    if (!enc) { set_error("fp8_linear: cuTensorMapEncodeTiled is not available from this driver"); return KTB200_ECUDA; }
+    ktb200_fp8_linear* l = new (std::nothrow) ktb200_fp8_linear();
+    if (!l) return KTB200_ENOMEM;
+    l->K = in_features; l->N = out_features; l->hidden_type = hidden_type; l->device = device; l->w = weight_e4m3; l->scale_inv = weight_scale_inv;
+    l->nkb = in_features / 128; l->row_tiles = (out_features + 127) / 128;
+    // K splits: enough CTAs for two per SM when the row tiles alone are few, and never more than kFMaxKb blocks of B per CTA
+    int ks = (2 * num_sms(device) + l->row_tiles - 1) / l->row_tiles;
+    const int ks_min = (l->nkb + kFMaxKb - 1) / kFMaxKb;
+    if (ks < ks_min) ks = ks_min;
+    if (ks > l->nkb) ks = l->nkb;
+    l->kb_per_split = (l->nkb + ks - 1) / ks;
+    l->ksplit = (l->nkb + l->kb_per_split - 1) / l->kb_per_split;
+    const cuuint64_t gdim[2] = {(cuuint64_t)in_features, (cuuint64_t)out_features};
+    const cuuint64_t gstr[1] = {(cuuint64_t)in_features};
+    const cuuint32_t box[2] = {128, 128}, estr[2] = {1, 1};
+    const CUresult cr = enc(&l->map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(weight_e4m3), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("fp8_linear: cuTensorMapEncodeTiled failed (%d)", (int)cr); delete l; return KTB200_ECUDA; }
+    l->ws = nullptr; l->tickets = nullptr;
+    cudaError_t e = cudaMalloc(&l->ws, (size_t)kFT * out_features * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(l->ws, 0, (size_t)kFT * out_features * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&l->tickets, (size_t)l->row_tiles * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(l->tickets, 0, (size_t)l->row_tiles * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fp8_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem);
+    if (e != cudaSuccess) { set_error("fp8_linear: %s", cudaGetErrorString(e)); cudaFree(l->ws); cudaFree(l->tickets); delete l; return KTB200_ENOMEM; }
+    *out = l;
+    return KTB200_OK;
+}
+
+void ktb200_fp8_linear_destroy(ktb200_fp8_linear* l) {
+    if (!l) return;
+    DeviceGuard g(l->device);
+    cudaFree(l->ws); cudaFree(l->tickets);
+    delete l;
+}
+
+int ktb200_fp8_linear_forward(ktb200_fp8_linear* l, int qlen, const void* x, void* y, const int* bsz, void* stream) {
+    using namespace ktb;
+    if (!l || !x || !y) { set_error("fp8_linear: null pointer"); return KTB200_EINVAL; }
+    if (qlen <= 0) return KTB200_OK;
+    DeviceGuard g(l->device);
+    const size_t hb = type_size(l->hidden_type);
+    for (int t0 = 0; t0 < qlen; t0 += kFT) {   // decode-sized passes; a prefill batch re-streams the weights every 16 tokens
+        Fp8Params p{};
+        p.x = reinterpret_cast<const uint8_t*>(x) + (size_t)t0 * l->K * hb;
+        p.y = reinterpret_cast<uint8_t*>(y) + (size_t)t0 * l->N * hb;
+        p.scale_inv = l->scale_inv; p.ws = l->ws; p.tickets = l->tickets; p.bsz = bsz; p.t0 = t0;
+        p.hidden_type = l->hidden_type; p.T = qlen - t0 < kFT ? qlen - t0 : kFT; p.K = l->K; p.N = l->N; p.nkb = l->nkb;
+        p.kb_per_split = l->kb_per_split; p.ksplit = l->ksplit;
+        fp8_linear_kernel<<<dim3(l->row_tiles, l->ksplit), 192, kFSmem, (cudaStream_t)stream>>>(l->map, p);
+        KTB_LAUNCH_CHECK();
+    }
+    return KTB200_OK;
+}
+
+}  // extern "C"

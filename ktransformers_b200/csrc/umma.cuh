@@ -145,6 +145,19 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// e4m3 / e5m2 / 6- and 4-bit float inputs, fp32 accumulate: K = 32 per instruction for the 8-bit types
+__device__ __forceinline__ void mma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 r;\n"
+        "elect.sync r|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // makes `bar` complete (one arrival) when all tcgen05 operations issued so far have finished; called by a converged
 // warp like mma_f16 (the same elected lane issues it)
 __device__ __forceinline__ void mma_commit(uint32_t bar) {

@@ -64,6 +64,9 @@ SYMBOLS = {
     "ktb200_moe_forward_host": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "ktb200_moe_forward_timed": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ktb200_moe_intermediate": (_VP, [_VP]),
+    "ktb200_fp8_linear_create": (_I, [_I, _I, _VP, _VP, _I, _I, C.POINTER(_VP)]),
+    "ktb200_fp8_linear_destroy": (None, [_VP]),
+    "ktb200_fp8_linear_forward": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "ktb200_linear_create": (_I, [_I, _I, _VP, _I, _I, _I, _I, C.POINTER(_VP)]),
     "ktb200_linear_destroy": (None, [_VP]),
     "ktb200_linear_load_weights": (_I, [_VP, _VP]),

@@ -171,8 +171,75 @@ class KLinearB200(KLinearBase):
             pass
 
 
+class KLinearFP8(KLinearBase):
+    """DeepSeek-V3's native FP8 checkpoints: e4m3 weight [out][in] + fp32 `weight_scale_inv` per 128 x 128 block, activations
+    quantised per token and 128 values inside the kernel.  Same contract as the reference's KLinearFP8 (operators/linear.py:388-435:
+    `load(w=(weight, weight_scale_inv))`, `forward(x, bsz_tensor)`), which runs Triton's act_quant + fp8_gemm; here one launch of
+    `ktb200_fp8_linear_forward` (TMA -> tcgen05.mma.kind::f8f6f4 -> TMEM, csrc/fp8_linear.cu)."""
+
+    def __init__(self, key, gguf_loader, config, orig_module=None, device: str = "cuda", block_size: int = 128, **kwargs):
+        super().__init__(key, gguf_loader, config, orig_module, device, **kwargs)
+        assert block_size == 128, "the checkpoint format fixes 128 x 128 weight blocks"
+        self.block_size = block_size
+        self.handle = None
+        self.weight = self.weight_scale_inv = None
+
+    def load(self, w=None, device: str | None = None):
+        if self.loaded:
+            return
+        device = device or self.device
+        assert "cuda" in str(device).lower(), "KLinearFP8 can only be loaded on a CUDA device"
+        lib = native.lib()
+        if w is None:
+            ld = self.gguf_loader       # a SafeTensorLoader (util/custom_loader.py): `<key>.weight` (float8_e4m3fn) + `<key>.weight_scale_inv`
+            w = (ld.load_tensor(self.key + ".weight"), ld.load_tensor(self.key + ".weight_scale_inv"))
+        if not isinstance(w, tuple) or len(w) != 2:
+            raise ValueError("Invalid weight type")                       # linear.py:427
+        weight, scale = (t.data if isinstance(t, nn.Parameter) else t for t in w)
+        if weight.dtype != torch.float8_e4m3fn or tuple(weight.shape) != (self.out_features, self.in_features):
+            raise ValueError(f"KLinearFP8: weight must be float8_e4m3fn [{self.out_features}][{self.in_features}], got {weight.dtype} {tuple(weight.shape)}")
+        want = ((self.out_features + 127) // 128, self.in_features // 128)
+        if tuple(scale.shape) != want:
+            raise ValueError(f"KLinearFP8: weight_scale_inv must be {want}, got {tuple(scale.shape)}")
+        self.weight = weight.to(device).contiguous()
+        self.weight_scale_inv = scale.to(device=device, dtype=torch.float32).contiguous()
+        self.hidden_type = TORCH_TO_GGML_HIDDEN.get(self.dtype, 30)
+        dev = torch.device(device)
+        self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        native.check(lib.ktb200_fp8_linear_create(self.in_features, self.out_features, self.weight.data_ptr(), self.weight_scale_inv.data_ptr(),
+                                                  self.hidden_type, self.dev_index, C.byref(h)))
+        self.handle = h
+        self.loaded = True
+
+    def forward(self, x: torch.Tensor, bsz_tensor: torch.Tensor = None, **kwargs) -> torch.Tensor:
+        if self.handle is None:
+            raise native.KTB200Error("Not Loaded")
+        orig_shape, in_dtype = x.shape, x.dtype
+        x2 = x.reshape(-1, x.shape[-1]).to(_GGML_TO_TORCH[self.hidden_type]).contiguous()
+        out = torch.empty((x2.shape[0], self.out_features), dtype=x2.dtype, device=x2.device)
+        native.check(native.lib().ktb200_fp8_linear_forward(self.handle, x2.shape[0], x2.data_ptr(), out.data_ptr(),
+                                                            bsz_tensor.data_ptr() if bsz_tensor is not None else None,
+                                                            torch.cuda.current_stream(x2.device).cuda_stream))
+        return out.reshape(*orig_shape[:-1], self.out_features).to(in_dtype)
+
+    def unload(self):
+        if self.handle is not None:
+            native.lib().ktb200_fp8_linear_destroy(self.handle)
+            self.handle = None
+        self.weight = self.weight_scale_inv = None
+        self.loaded = False
+
+    def __del__(self):
+        try:
+            self.unload()
+        except Exception:
+            pass
+
+
 LINEAR_MAP = {
     "KLinearB200": KLinearB200,
+    "KLinearFP8": KLinearFP8,
     "KLinearTorch": KLinearTorch,
 }
 

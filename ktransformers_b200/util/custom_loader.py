@@ -212,9 +212,41 @@ class GGUFLoader(ModelLoader):
         return values.view(t["shape"][-2::-1])
 
 
+class SafeTensorLoader(ModelLoader):
+    """custom_loader.py:52-112: key -> file map over a directory of *.safetensors, `load_tensor(key, device)`; what KLinearFP8 needs
+    to find `<key>.weight` (float8_e4m3fn) and `<key>.weight_scale_inv`.  (The FP8 + GGUF hybrid produced by
+    archive/merge_tensors is a separate on-disk contract and not read here.)"""
+
+    def __init__(self, file_path: str):
+        from safetensors import safe_open
+        self._open = safe_open
+        self.tensor_file_map: dict = {}
+        root = os.path.dirname(file_path) if os.path.isfile(file_path) else file_path
+        found = False
+        for cur, _, files in os.walk(root):
+            for fn in sorted(files):
+                if fn.endswith(".safetensors"):
+                    found = True
+                    full = os.path.join(cur, fn)
+                    with safe_open(full, framework="pt") as f:
+                        for k in f.keys():
+                            self.tensor_file_map[k] = full
+        if not found:
+            raise FileNotFoundError(f"No Safetensor files found in {root}")
+
+    def has_tensor(self, name: str) -> bool:
+        return name in self.tensor_file_map
+
+    def load_tensor(self, key: str, device: str = "cpu"):
+        if key not in self.tensor_file_map:
+            raise KeyError(f"Key {key} not found in Safetensor files")
+        with self._open(self.tensor_file_map[key], framework="pt") as f:
+            return f.get_tensor(key).to(device)
+
+
 class ModelLoaderFactory:
-    """create_loader(path): GGUF directories/files -> GGUFLoader (custom_loader.py:531-598; the
-    safetensors branch of the reference is outside this path's scope)."""
+    """create_loader(path): GGUF directories/files -> GGUFLoader, directories of *.safetensors -> SafeTensorLoader
+    (custom_loader.py:531-598)."""
 
     @staticmethod
     def create_loader(path: str) -> ModelLoader:
@@ -224,4 +256,7 @@ class ModelLoaderFactory:
         for _, _, files in os.walk(root):
             if any(f.endswith(".gguf") for f in files):
                 return GGUFLoader(path)
-        raise FileNotFoundError(f"No .gguf files found in: {path}")
+        for _, _, files in os.walk(root):
+            if any(f.endswith(".safetensors") for f in files):
+                return SafeTensorLoader(path)
+        raise FileNotFoundError(f"No .gguf or .safetensors files found in: {path}")

@@ -285,3 +285,37 @@ def test_serve_rule_file_v2_classes_carry_bsz_tensor(tmp_path):
             assert torch.equal(y2[0, :live].view(torch.int16), y1[0, :live].view(torch.int16)), n_tok
     finally:
         torch.set_default_dtype(old)
+
+
+def test_klinear_fp8_operator_from_safetensors(tmp_path):
+    """KLinearFP8 (operators/linear.py:388-435 contract) through KTransformersLinear, weights found by the SafeTensorLoader as
+    `<key>.weight` (float8_e4m3fn) + `<key>.weight_scale_inv`; output against the dequantised dense fp32 product."""
+    from safetensors.torch import save_file
+    from ktransformers_b200.operators.linear import KLinearFP8, KTransformersLinear, LINEAR_MAP
+    from ktransformers_b200.util.custom_loader import ModelLoaderFactory, SafeTensorLoader
+    from ktransformers_b200.util.utils import InferenceState
+    assert LINEAR_MAP["KLinearFP8"] is KLinearFP8
+    Kf, Nf = 1024, 384
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn(Nf, Kf, generator=g) * 0.5).to(torch.float8_e4m3fn)
+    s = torch.rand(Nf // 128, Kf // 128, generator=g) * 0.02 + 0.001
+    save_file({"model.layers.0.self_attn.o_proj.weight": w, "model.layers.0.self_attn.o_proj.weight_scale_inv": s}, str(tmp_path / "m.safetensors"))
+    ld = ModelLoaderFactory.create_loader(str(tmp_path))
+    assert isinstance(ld, SafeTensorLoader) and ld.has_tensor("model.layers.0.self_attn.o_proj.weight_scale_inv")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        lin = KTransformersLinear("model.layers.0.self_attn.o_proj", ld, None, torch.nn.Linear(Kf, Nf, bias=False, device="meta"),
+                                  generate_op="KLinearFP8", prefill_op=None)
+        lin.load(mode=InferenceState.GENERATE)
+        x = (torch.randn(2, 3, Kf, device="cuda") / 10).to(torch.bfloat16)
+        y = lin(x)
+        assert y.shape == (2, 3, Nf) and y.dtype == torch.bfloat16
+        dense = w.float().view(Nf // 128, 128, Kf // 128, 128) * s.view(Nf // 128, 1, Kf // 128, 1)
+        want = x.float().cpu().view(-1, Kf) @ dense.view(Nf, Kf).T
+        assert (y.float().cpu().view(-1, Nf) - want).abs().max() <= 0.06 * want.abs().max()     # fp8 activations: a few %
+        lin.unload()
+        with pytest.raises(Exception):
+            lin.generate_linear.forward(x)
+    finally:
+        torch.set_default_dtype(old)

@@ -5,6 +5,7 @@
 Tolerances: activation quantisation and routed ids are exact; fp32 outputs within 1e-3 of the reference
 (north_star) — typically 1e-6, the bound leaves room for the one-LSB int8 knife-edge flips that even two
 builds of the reference exhibit between each other; bf16 outputs additionally within 1 bf16 ulp."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -736,3 +737,66 @@ def test_moe_grouped_vs_compiled_reference_forward_many(ref, qlen):
     want = ref.moe_forward(E, H, I, g_np, u_np, d_np, Q4_K, Q4_K, Q6_K, F32, ids, w, x, group_max_len=4096)
     assert relmax(got, want) < FP_TOL
     m.close()
+
+
+# ------------------------------------------------------------------------------------------ FP8 128 x 128 linear
+def _fp8_case(rng, T, K, N):
+    from oracle import fp8_oracle as F
+    x = f32_to_bf16_bits((rng.standard_normal((T, K)) / 10).astype(np.float32))
+    w = F.to_e4m3_bytes((rng.standard_normal((N, K)) * 0.7).astype(np.float32))
+    ws = (rng.random(((N + 127) // 128, K // 128)) * 0.02 + 0.001).astype(np.float32)
+    return x, w, ws
+
+
+def _fp8_run(x_bits, w, ws, bsz=None, out=None):
+    lib = native.lib()
+    T, K = x_bits.shape
+    N = w.shape[0]
+    w_d, ws_d = torch.from_numpy(w).cuda(), torch.from_numpy(ws).cuda()
+    x_d = torch.from_numpy(x_bits.view(np.int16)).view(torch.bfloat16).cuda()
+    y_d = torch.zeros((T, N), dtype=torch.bfloat16, device="cuda") if out is None else out
+    h = C.c_void_p()
+    native.check(lib.ktb200_fp8_linear_create(K, N, w_d.data_ptr(), ws_d.data_ptr(), BF16, 0, C.byref(h)))
+    bsz_d = torch.tensor([bsz], dtype=torch.int32, device="cuda") if bsz is not None else None
+    for _ in range(2):   # twice: the K-split workspace and tickets must come back zeroed
+        native.check(lib.ktb200_fp8_linear_forward(h, T, x_d.data_ptr(), y_d.data_ptr(), bsz_d.data_ptr() if bsz_d is not None else None,
+                                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    lib.ktb200_fp8_linear_destroy(h)
+    return y_d.cpu().view(torch.int16).numpy().view(np.uint16)
+
+
+@pytest.mark.parametrize("T,K,N", [(1, 256, 256), (3, 1536, 24576), (8, 7168, 2112), (16, 16384, 7168), (20, 1024, 200), (1, 7168, 7168), (5, 128, 128)])
+def test_fp8_linear_vs_oracle(T, K, N):
+    """ktb200_fp8_linear_forward (TMA + tcgen05 kind::f8f6f4) against oracle/fp8_oracle.py (pinned to the reference's Triton
+    kernels): act_quant inside the kernel, exact e4m3 products, (dot * a_s) * b_s per 128 of K in fp32; the K-split and the tensor
+    core's summation order move the fp32 sum by round-off only -> bf16 outputs within 1 ulp, > 97 % identical."""
+    from oracle import fp8_oracle as F
+    rng = np.random.default_rng(T * 100003 + K + N)
+    x, w, ws = _fp8_case(rng, T, K, N)
+    got = _fp8_run(x, w, ws)
+    want = f32_to_bf16_bits(F.linear_forward(bf16_to_f32(x), w, ws))
+    assert_bf16_close(got, want)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_fp8_linear_vs_reference_golden(golden_dir, name):
+    """The golden vectors are the reference's own Triton kernels under the CPU interpreter, whose software casts drop a carry in
+    ~2 % of the e4m3 bytes and truncate to bf16 (tests/test_oracle_pinned.py pins the oracle around both): the GPU result must
+    equal the oracle and sit within those artifacts' reach of the golden output."""
+    from oracle import fp8_oracle as F
+    g = np.load(os.path.join(golden_dir, "fp8_ref.npz"))
+    x, w, ws = g[f"{name}_x"], g[f"{name}_w"], g[f"{name}_ws"]
+    got = _fp8_run(x, w, ws)
+    assert_bf16_close(got, f32_to_bf16_bits(F.linear_forward(bf16_to_f32(x), w, ws)))
+    a, b = bf16_to_f32(got), bf16_to_f32(g[f"{name}_c"])
+    assert np.abs(a - b).max() <= 0.05 * np.abs(b).max()
+
+
+def test_fp8_linear_bsz_rows_untouched():
+    rng = np.random.default_rng(3)
+    x, w, ws = _fp8_case(rng, 20, 512, 384)
+    full = _fp8_run(x, w, ws)
+    sentinel = torch.full((20, 384), 7.0, dtype=torch.bfloat16, device="cuda")
+    part = _fp8_run(x, w, ws, bsz=18, out=sentinel)
+    assert np.array_equal(part[:18], full[:18]) and (sentinel[18:] == 7.0).all()
