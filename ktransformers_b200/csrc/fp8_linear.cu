@@ -7,7 +7,7 @@
 // into shared memory in the 128-byte-swizzle layout, which IS the K-major A operand of tcgen05.mma.kind::f8f6f4; the quantised
 // activations (16 token rows, padded) are the B operand; the products of two e4m3 values are exact in the fp32 accumulator (TMEM).
 // After every 128 of K (4 MMAs) the epilogue takes the partial dot out of TMEM and applies the two scales in the reference's order.
-//     grid = (ceil(N / 128) row tiles, K splits); 192 threads: warp 0 TMA producer (8-stage ring, 128 KB in flight), warp 1 issuer,
+//     grid = (ceil(N / 128) row tiles, K splits), two CTAs per SM; 192 threads: warp 0 TMA producer (4-stage ring), warp 1 issuer,
 //     warps 2-5 quantise x for the CTA's K range while the first weight boxes are in flight, then run the epilogue.
 // K splits add their fp32 partial sums with atomics into a zeroed workspace; the last CTA of a row tile converts and re-zeroes.
 #include <cuda.h>
@@ -23,7 +23,7 @@ namespace ktb {
 using namespace umma;
 
 constexpr int kFT = 16;                    // token rows per pass (the MMA's N)
-constexpr int kFStages = 8, kFA = 128 * 128, kFB = kFT * 128, kFMaxKb = 40;
+constexpr int kFStages = 4, kFA = 128 * 128, kFB = kFT * 128, kFMaxKb = 16;   // 64 + 32 KB: two CTAs per SM, 128 KB of weight boxes in flight
 constexpr int kFOffB = kFStages * kFA, kFOffS = kFOffB + kFMaxKb * kFB, kFOffMisc = kFOffS + kFT * kFMaxKb * 4;
 struct Fp8Misc {
     unsigned long long a_full[kFStages], a_free[kFStages], d_full[2], d_free[2], b_ready;
@@ -42,7 +42,7 @@ struct Fp8Params {
     int hidden_type, T, K, N, nkb, kb_per_split, ksplit, t0;
 };
 
-__global__ void __launch_bounds__(192, 1) fp8_linear_kernel(const __grid_constant__ CUtensorMap wmap, const Fp8Params p) {
+__global__ void __launch_bounds__(192, 2) fp8_linear_kernel(const __grid_constant__ CUtensorMap wmap, const Fp8Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -99,22 +99,46 @@ __global__ void __launch_bounds__(192, 1) fp8_linear_kernel(const __grid_constan
             const int r = (i >> 3) & (kFT - 1);
             if (r >= p.T) *reinterpret_cast<uint4*>(smem + kFOffB + i * 16) = make_uint4(0, 0, 0, 0);
         }
-        for (int blk = ew; blk < p.T * nk; blk += 4) {   // one warp per (token, 128 of K); lane owns 4 consecutive values
-            const int t = blk / nk, kb = blk - t * nk;
-            const long off = (long)t * p.K + (long)(kb0 + kb) * 128 + lane * 4;
-            float v[4];
+        // one warp per (token, 128 of K), lane owns 4 consecutive values; 8 blocks' loads are issued before the first is reduced
+        for (int g0 = ew; g0 < p.T * nk; g0 += 4 * 8) {
+            float v[8][4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) v[e] = load_hidden(p.x, off + e, p.hidden_type);
-            float am = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+            for (int u = 0; u < 8; u++) {
+                const int blk = g0 + 4 * u;
+                if (blk < p.T * nk) {
+                    const int t = blk / nk, kb = blk - t * nk;
+                    const long off = (long)t * p.K + (long)(kb0 + kb) * 128 + lane * 4;
+                    if (p.hidden_type == KTB200_TYPE_F32) {
+                        const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + off);
+                        v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
+                    } else {
+                        const uint2 w2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.x) + off);
+                        const uint32_t ww[2] = {w2.x, w2.y};
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-            const float s = __fdiv_rn(am, 448.f);
-            uint32_t packed = 0;
+                        for (int e = 0; e < 2; e++) {
+                            if (p.hidden_type == KTB200_TYPE_BF16) { v[u][2 * e] = __uint_as_float(ww[e] << 16); v[u][2 * e + 1] = __uint_as_float(ww[e] & 0xffff0000u); }
+                            else { v[u][2 * e] = fp16_bits_to_f32((uint16_t)(ww[e] & 0xffff)); v[u][2 * e + 1] = fp16_bits_to_f32((uint16_t)(ww[e] >> 16)); }
+                        }
+                    }
+                }
+            }
 #pragma unroll
-            for (int e = 0; e < 4; e++)   // x / s in IEEE fp32, round to nearest even into e4m3 (0 / 0 = NaN like the reference)
-                packed |= (uint32_t)__nv_cvt_float_to_fp8(__fdiv_rn(v[e], s), __NV_SATFINITE, __NV_E4M3) << (8 * e);
-            *reinterpret_cast<uint32_t*>(smem + kFOffB + kb * kFB + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4) = packed;
-            if (lane == 0) a_s[t * p.kb_per_split + kb] = s;
+            for (int u = 0; u < 8; u++) {
+                const int blk = g0 + 4 * u;
+                if (blk < p.T * nk) {   // warp-uniform
+                    const int t = blk / nk, kb = blk - t * nk;
+                    float am = fmaxf(fmaxf(fabsf(v[u][0]), fabsf(v[u][1])), fmaxf(fabsf(v[u][2]), fabsf(v[u][3])));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+                    const float s = __fdiv_rn(am, 448.f);
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; e++)   // x / s in IEEE fp32, round to nearest even into e4m3 (0 / 0 = NaN like the reference)
+                        packed |= (uint32_t)__nv_cvt_float_to_fp8(__fdiv_rn(v[u][e], s), __NV_SATFINITE, __NV_E4M3) << (8 * e);
+                    *reinterpret_cast<uint32_t*>(smem + kFOffB + kb * kFB + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4) = packed;
+                    if (lane == 0) a_s[t * p.kb_per_split + kb] = s;
+                }
+            }
         }
         fence_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // a_s is read by all four epilogue warps
@@ -215,12 +239,13 @@ int ktb200_fp8_linear_create(int in_features, int out_features, const void* weig
     if (!l) return KTB200_ENOMEM;
     l->K = in_features; l->N = out_features; l->hidden_type = hidden_type; l->device = device; l->w = weight_e4m3; l->scale_inv = weight_scale_inv;
     l->nkb = in_features / 128; l->row_tiles = (out_features + 127) / 128;
-    // K splits: enough CTAs for two per SM when the row tiles alone are few, and never more than kFMaxKb blocks of B per CTA
-    int ks = (2 * num_sms(device) + l->row_tiles - 1) / l->row_tiles;
+    // K splits: at most kFMaxKb blocks of B per CTA, and enough CTAs for two resident waves (2 per SM) when the row tiles are few
+    int ks = (4 * num_sms(device) + l->row_tiles - 1) / l->row_tiles;
     const int ks_min = (l->nkb + kFMaxKb - 1) / kFMaxKb;
     if (ks < ks_min) ks = ks_min;
     if (ks > l->nkb) ks = l->nkb;
     l->kb_per_split = (l->nkb + ks - 1) / ks;
+    if (l->kb_per_split < 4 && l->nkb >= 4) l->kb_per_split = 4;   // a CTA should at least fill its ring
     l->ksplit = (l->nkb + l->kb_per_split - 1) / l->kb_per_split;
     const cuuint64_t gdim[2] = {(cuuint64_t)in_features, (cuuint64_t)out_features};
     const cuuint64_t gstr[1] = {(cuuint64_t)in_features};
