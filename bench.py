@@ -675,12 +675,19 @@ def main():
     for _ in range(max(3, args.warmup)):
         fresh_input(); x_own.copy_(x_host, non_blocking=True); run_step()
     barrier()
-    if sampler is not None and sampler.p is not None:
-        # nvidia-smi needs up to a few seconds before its first row on a fresh box, the timed region lasts ~0.1 s: keep the GPU
-        # under the same load (more untimed steps) until the sampler is live, so that the timed region is actually sampled
-        t_wait = time.perf_counter()
-        while sampler.rows() == 0 and time.perf_counter() - t_wait < 8.0:
-            run_step(); torch.cuda.synchronize()
+    # nvidia-smi needs up to a few seconds before its first row on a fresh box and the timed region lasts ~0.1 s: keep the GPU(s)
+    # under the same load (more untimed steps) until rank 0's sampler is live, so that the timed region is actually sampled.
+    # Every rank must run the same steps (the expert-parallel layer is a collective): rank 0 decides, everyone follows.
+    t_wait = time.perf_counter()
+    while True:
+        more = 1 if (sampler is not None and sampler.p is not None and sampler.rows() == 0 and time.perf_counter() - t_wait < 8.0) else 0
+        if world > 1:
+            flag = torch.tensor([more], device=dev, dtype=torch.int32)
+            dist.broadcast(flag, 0)
+            more = int(flag.item())
+        if not more:
+            break
+        run_step(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     fresh_input(); x_own.copy_(x_host); barrier()
