@@ -112,18 +112,25 @@ class KTMoEWrapper:
         x = hidden_states.view(-1, hidden_states.shape[-1])
         if x.shape[0] > self._out.shape[0]:
             raise ValueError(f"batch {x.shape[0]} exceeds chunked_prefill_size {self._out.shape[0]}")
-        ids = topk_ids.view(x.shape[0], -1).to(torch.int64)
-        if self._mask_dev is not None:
-            valid = (ids >= 0) & (ids < self.num_experts)
-            masked = self._mask_dev[ids.clamp(0, self.num_experts - 1)] & valid
-            ids = torch.where(masked, torch.full_like(ids, -1), ids)
         stream = torch.cuda.ExternalStream(int(cuda_stream)) if isinstance(cuda_stream, int) and cuda_stream else (cuda_stream or torch.cuda.current_stream(x.device))
         with torch.cuda.stream(stream):
+            # the id cast and the gpu_experts_mask masking are kernels too: they run on the SAME stream as the expert kernels, so a
+            # caller-supplied stream other than the current one never reads ids that are still being written
+            ids = topk_ids.view(x.shape[0], -1).to(torch.int64)
+            if self._mask_dev is not None:
+                valid = (ids >= 0) & (ids < self.num_experts)
+                masked = self._mask_dev[ids.clamp(0, self.num_experts - 1)] & valid
+                ids = torch.where(masked, torch.full_like(ids, -1), ids)
             self.moe._launch(x, ids, topk_weights.view(x.shape[0], -1), self._out[: x.shape[0]])
         self._pending = x.shape[0]
 
     def sync_forward(self, hidden_states: torch.Tensor, cuda_stream=None) -> torch.Tensor:
         n = hidden_states.view(-1, hidden_states.shape[-1]).shape[0]
+        if getattr(self, "_pending", None) is None:
+            raise RuntimeError("sync_forward without a pending submit_forward")
+        if n != self._pending:
+            raise ValueError(f"sync_forward for {n} tokens, but {self._pending} were submitted")
+        self._pending = None
         return self._out[:n]          # ordered on cuda_stream behind the launches of submit_forward
 
     def forward(self, hidden_states, topk_ids, topk_weights, cuda_stream=None) -> torch.Tensor:
