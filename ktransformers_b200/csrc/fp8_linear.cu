@@ -39,8 +39,50 @@ struct Fp8Params {
     float* ws;                // [kFT][N] fp32, zero between calls (K splits only)
     unsigned* tickets;        // [row tiles], zero between calls
     const int* bsz;
+    const uint8_t* xq;        // [kFT][K] e4m3 and
+    const float* xs;          // [kFT][nkb] scales from fp8_act_quant_kernel (batches of more than 2 tokens), else null
     int hidden_type, T, K, N, nkb, kb_per_split, ksplit, t0;
 };
+
+// act_quant (fp8gemm.py:10-27) for one (token, 128 values) block held 4 values per lane: returns the scale, packs the 4 e4m3 bytes
+__device__ __forceinline__ float fp8_quant_block(const float (&v)[4], uint32_t& packed) {
+    float am = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    const float s = __fdiv_rn(am, 448.f);
+    packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++)   // x / s in IEEE fp32, round to nearest even into e4m3 (0 / 0 = NaN like the reference)
+        packed |= (uint32_t)__nv_cvt_float_to_fp8(__fdiv_rn(v[e], s), __NV_SATFINITE, __NV_E4M3) << (8 * e);
+    return s;
+}
+__device__ __forceinline__ void fp8_load4(const void* x, long off, int hidden_type, float (&v)[4]) {
+    if (hidden_type == KTB200_TYPE_F32) {
+        const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + off);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+        const uint2 w2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + off);
+        const uint32_t ww[2] = {w2.x, w2.y};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (hidden_type == KTB200_TYPE_BF16) { v[2 * e] = __uint_as_float(ww[e] << 16); v[2 * e + 1] = __uint_as_float(ww[e] & 0xffff0000u); }
+            else { v[2 * e] = fp16_bits_to_f32((uint16_t)(ww[e] & 0xffff)); v[2 * e + 1] = fp16_bits_to_f32((uint16_t)(ww[e] >> 16)); }
+        }
+    }
+}
+// batches of more than 2 tokens: quantise x ONCE (one warp per block) instead of once per row tile
+__global__ void __launch_bounds__(256) fp8_act_quant_kernel(const void* x, int hidden_type, int T, int K, uint8_t* xq, float* xs) {
+    const int lane = threadIdx.x & 31, blk = blockIdx.x * 8 + (threadIdx.x >> 5), nkb = K / 128;
+    griddep_launch_dependents();
+    if (blk >= T * nkb) return;
+    const int t = blk / nkb, kb = blk - t * nkb;
+    float v[4];
+    fp8_load4(x, (long)t * K + (long)kb * 128 + lane * 4, hidden_type, v);
+    uint32_t packed;
+    const float s = fp8_quant_block(v, packed);
+    reinterpret_cast<uint32_t*>(xq + (long)t * K + (long)kb * 128)[lane] = packed;
+    if (lane == 0) xs[t * nkb + kb] = s;
+}
 
 __global__ void __launch_bounds__(192, 2) fp8_linear_kernel(const __grid_constant__ CUtensorMap wmap, const Fp8Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -99,44 +141,37 @@ __global__ void __launch_bounds__(192, 2) fp8_linear_kernel(const __grid_constan
             const int r = (i >> 3) & (kFT - 1);
             if (r >= p.T) *reinterpret_cast<uint4*>(smem + kFOffB + i * 16) = make_uint4(0, 0, 0, 0);
         }
-        // one warp per (token, 128 of K), lane owns 4 consecutive values; 8 blocks' loads are issued before the first is reduced
-        for (int g0 = ew; g0 < p.T * nk; g0 += 4 * 8) {
-            float v[8][4];
+        if (p.xq) {
+            // already quantised by fp8_act_quant_kernel: copy this CTA's K range into the swizzled B tiles (16-byte pieces)
+            griddep_wait();
+            for (int i = tid - 64; i < p.T * nk * 8; i += 128) {
+                const int pc = i & 7, kb = (i >> 3) % nk, t = (i >> 3) / nk;
+                *reinterpret_cast<uint4*>(smem + kFOffB + kb * kFB + t * 128 + ((pc ^ (t & 7)) << 4)) =
+                    *reinterpret_cast<const uint4*>(p.xq + (long)t * p.K + (long)(kb0 + kb) * 128 + pc * 16);
+            }
+            for (int i = tid - 64; i < p.T * nk; i += 128) a_s[(i / nk) * p.kb_per_split + (i % nk)] = p.xs[(i / nk) * p.nkb + kb0 + (i % nk)];
+        } else {
+            // one warp per (token, 128 of K), lane owns 4 consecutive values; 8 blocks' loads are issued before the first is reduced
+            for (int g0 = ew; g0 < p.T * nk; g0 += 4 * 8) {
+                float v[8][4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int blk = g0 + 4 * u;
-                if (blk < p.T * nk) {
-                    const int t = blk / nk, kb = blk - t * nk;
-                    const long off = (long)t * p.K + (long)(kb0 + kb) * 128 + lane * 4;
-                    if (p.hidden_type == KTB200_TYPE_F32) {
-                        const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + off);
-                        v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
-                    } else {
-                        const uint2 w2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.x) + off);
-                        const uint32_t ww[2] = {w2.x, w2.y};
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            if (p.hidden_type == KTB200_TYPE_BF16) { v[u][2 * e] = __uint_as_float(ww[e] << 16); v[u][2 * e + 1] = __uint_as_float(ww[e] & 0xffff0000u); }
-                            else { v[u][2 * e] = fp16_bits_to_f32((uint16_t)(ww[e] & 0xffff)); v[u][2 * e + 1] = fp16_bits_to_f32((uint16_t)(ww[e] >> 16)); }
-                        }
+                for (int u = 0; u < 8; u++) {
+                    const int blk = g0 + 4 * u;
+                    if (blk < p.T * nk) {
+                        const int t = blk / nk, kb = blk - t * nk;
+                        fp8_load4(p.x, (long)t * p.K + (long)(kb0 + kb) * 128 + lane * 4, p.hidden_type, v[u]);
                     }
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int blk = g0 + 4 * u;
-                if (blk < p.T * nk) {   // warp-uniform
-                    const int t = blk / nk, kb = blk - t * nk;
-                    float am = fmaxf(fmaxf(fabsf(v[u][0]), fabsf(v[u][1])), fmaxf(fabsf(v[u][2]), fabsf(v[u][3])));
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-                    const float s = __fdiv_rn(am, 448.f);
-                    uint32_t packed = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; e++)   // x / s in IEEE fp32, round to nearest even into e4m3 (0 / 0 = NaN like the reference)
-                        packed |= (uint32_t)__nv_cvt_float_to_fp8(__fdiv_rn(v[u][e], s), __NV_SATFINITE, __NV_E4M3) << (8 * e);
-                    *reinterpret_cast<uint32_t*>(smem + kFOffB + kb * kFB + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4) = packed;
-                    if (lane == 0) a_s[t * p.kb_per_split + kb] = s;
+                for (int u = 0; u < 8; u++) {
+                    const int blk = g0 + 4 * u;
+                    if (blk < p.T * nk) {   // warp-uniform
+                        const int t = blk / nk, kb = blk - t * nk;
+                        uint32_t packed;
+                        const float s = fp8_quant_block(v[u], packed);
+                        *reinterpret_cast<uint32_t*>(smem + kFOffB + kb * kFB + t * 128 + (((lane >> 2) ^ (t & 7)) << 4) + (lane & 3) * 4) = packed;
+                        if (lane == 0) a_s[t * p.kb_per_split + kb] = s;
+                    }
                 }
             }
         }
@@ -220,6 +255,8 @@ struct ktb200_fp8_linear {
     CUtensorMap map;
     float* ws;
     unsigned* tickets;
+    uint8_t* xq;   // [kFT][K] e4m3
+    float* xs;     // [kFT][nkb]
 };
 
 extern "C" {
@@ -253,13 +290,15 @@ int ktb200_fp8_linear_create(int in_features, int out_features, const void* weig
     const CUresult cr = enc(&l->map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(weight_e4m3), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("fp8_linear: cuTensorMapEncodeTiled failed (%d)", (int)cr); delete l; return KTB200_ECUDA; }
-    l->ws = nullptr; l->tickets = nullptr;
+    l->ws = nullptr; l->tickets = nullptr; l->xq = nullptr; l->xs = nullptr;
     cudaError_t e = cudaMalloc(&l->ws, (size_t)kFT * out_features * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(l->ws, 0, (size_t)kFT * out_features * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&l->tickets, (size_t)l->row_tiles * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(l->tickets, 0, (size_t)l->row_tiles * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&l->xq, (size_t)kFT * in_features);
+    if (e == cudaSuccess) e = cudaMalloc(&l->xs, (size_t)kFT * l->nkb * sizeof(float));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fp8_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem);
-    if (e != cudaSuccess) { set_error("fp8_linear: %s", cudaGetErrorString(e)); cudaFree(l->ws); cudaFree(l->tickets); delete l; return KTB200_ENOMEM; }
+    if (e != cudaSuccess) { set_error("fp8_linear: %s", cudaGetErrorString(e)); cudaFree(l->ws); cudaFree(l->tickets); cudaFree(l->xq); cudaFree(l->xs); delete l; return KTB200_ENOMEM; }
     *out = l;
     return KTB200_OK;
 }
@@ -267,7 +306,7 @@ int ktb200_fp8_linear_create(int in_features, int out_features, const void* weig
 void ktb200_fp8_linear_destroy(ktb200_fp8_linear* l) {
     if (!l) return;
     DeviceGuard g(l->device);
-    cudaFree(l->ws); cudaFree(l->tickets);
+    cudaFree(l->ws); cudaFree(l->tickets); cudaFree(l->xq); cudaFree(l->xs);
     delete l;
 }
 
@@ -284,8 +323,15 @@ int ktb200_fp8_linear_forward(ktb200_fp8_linear* l, int qlen, const void* x, voi
         p.scale_inv = l->scale_inv; p.ws = l->ws; p.tickets = l->tickets; p.bsz = bsz; p.t0 = t0;
         p.hidden_type = l->hidden_type; p.T = qlen - t0 < kFT ? qlen - t0 : kFT; p.K = l->K; p.N = l->N; p.nkb = l->nkb;
         p.kb_per_split = l->kb_per_split; p.ksplit = l->ksplit;
-        fp8_linear_kernel<<<dim3(l->row_tiles, l->ksplit), 192, kFSmem, (cudaStream_t)stream>>>(l->map, p);
-        KTB_LAUNCH_CHECK();
+        if (p.T > 2) {   // quantise once, then the GEMM as a programmatic dependent launch: its weight boxes stream while the quantiser drains
+            p.xq = l->xq; p.xs = l->xs;
+            fp8_act_quant_kernel<<<(p.T * l->nkb + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p.x, l->hidden_type, p.T, l->K, l->xq, l->xs);
+            KTB_CUDA_CHECK(launch_pdl(fp8_linear_kernel, dim3(l->row_tiles, l->ksplit), dim3(192), (size_t)kFSmem, (cudaStream_t)stream, l->map, p));
+            count_launch(2);
+        } else {
+            fp8_linear_kernel<<<dim3(l->row_tiles, l->ksplit), 192, kFSmem, (cudaStream_t)stream>>>(l->map, p);
+            KTB_LAUNCH_CHECK();
+        }
     }
     return KTB200_OK;
 }
