@@ -323,3 +323,29 @@ def test_shipped_rule_files_name_importable_classes():
     from ktransformers_b200.operators.experts import KTransformersExpertsV2
     import inspect
     assert list(inspect.signature(KTransformersExpertsV2.forward).parameters)[1:] == ["input_tensor", "expert_ids", "weights", "bsz_tensor", "cuda_graph_idx"]
+
+
+def test_safetensor_loader_and_klinear_fp8_contract(tmp_path):
+    """util/custom_loader.py SafeTensorLoader (custom_loader.py:52-112) finds `<key>.weight` / `<key>.weight_scale_inv`; KLinearFP8
+    keeps the reference's constructor / load contract (linear.py:388-435) and refuses anything but a CUDA device (no CPU fallback)."""
+    import torch
+    from safetensors.torch import save_file
+    from ktransformers_b200.operators.linear import KLinearFP8, LINEAR_MAP
+    from ktransformers_b200.util.custom_loader import GGUFLoader, ModelLoaderFactory, SafeTensorLoader
+    w = torch.randn(256, 128).to(torch.float8_e4m3fn)
+    s = torch.rand(2, 1)
+    save_file({"blk.q_proj.weight": w, "blk.q_proj.weight_scale_inv": s}, str(tmp_path / "a.safetensors"))
+    ld = ModelLoaderFactory.create_loader(str(tmp_path))
+    assert isinstance(ld, SafeTensorLoader) and not isinstance(ld, GGUFLoader)
+    assert ld.has_tensor("blk.q_proj.weight") and not ld.has_tensor("blk.k_proj.weight")
+    assert torch.equal(ld.load_tensor("blk.q_proj.weight").view(torch.uint8), w.view(torch.uint8)) and torch.equal(ld.load_tensor("blk.q_proj.weight_scale_inv"), s)
+    with pytest.raises(KeyError):
+        ld.load_tensor("blk.k_proj.weight")
+    with pytest.raises(FileNotFoundError):
+        ModelLoaderFactory.create_loader(str(tmp_path / "nothing_here"))
+    lin = LINEAR_MAP["KLinearFP8"]("blk.q_proj", ld, None, torch.nn.Linear(128, 256, bias=False, device="meta"), device="cuda")
+    assert isinstance(lin, KLinearFP8) and lin.block_size == 128 and (lin.in_features, lin.out_features) == (128, 256)
+    with pytest.raises(AssertionError):
+        lin.load(device="cpu")
+    with pytest.raises(Exception):
+        lin.forward(torch.zeros(1, 128))           # Not Loaded
