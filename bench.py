@@ -717,7 +717,7 @@ def main():
             return out_host
         h2d = N_MOE_LAYERS * H * 2
         d2h = N_MOE_LAYERS * H * 2
-        e2e_api = "per layer: ktb200_moe_block_forward_host(pinned host token -> pinned host output): H2D, one launch, D2H, sync"
+        e2e_api = "per layer: ktb200_moe_block_forward_host(pinned host token -> pinned host output): H2D copy, one launch whose stores land in the pinned output (the D2H transfer), sync"
     else:
         # same shape as N=1: every layer is one plugin call with HOST buffers (token up, layer, output back, synchronise)
         def e2e_step():

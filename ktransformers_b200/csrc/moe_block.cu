@@ -1264,9 +1264,15 @@ extern "C" int ktb200_moe_block_forward_host(const ktb200_gate_config* gc, ktb20
     cudaStream_t s = (cudaStream_t)stream;
     const size_t hid = (size_t)qlen * c.hidden_size * type_size(c.hidden_type);
     KTB_CUDA_CHECK(cudaMemcpyAsync(m->in_d, input, hid, cudaMemcpyHostToDevice, s));
-    int rc = ktb200_moe_block_forward(gc, m, sh, qlen, m->in_d, m->out_d, m->ids_d, m->w_d, nullptr, stream);
+    // a pinned (mapped) output buffer is written by the kernel's own stores — the device-to-host transfer without a copy-engine
+    // launch behind the kernel; pageable memory takes the staged copy
+    void* out_dev = m->out_d;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, output) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) out_dev = pa.devicePointer;
+    else (void)cudaGetLastError();
+    int rc = ktb200_moe_block_forward(gc, m, sh, qlen, m->in_d, out_dev, m->ids_d, m->w_d, nullptr, stream);
     if (rc) return rc;
-    KTB_CUDA_CHECK(cudaMemcpyAsync(output, m->out_d, hid, cudaMemcpyDeviceToHost, s));
+    if (out_dev == m->out_d) KTB_CUDA_CHECK(cudaMemcpyAsync(output, m->out_d, hid, cudaMemcpyDeviceToHost, s));
     if (idx) KTB_CUDA_CHECK(cudaMemcpyAsync(idx, m->ids_d, (size_t)qlen * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     if (w) KTB_CUDA_CHECK(cudaMemcpyAsync(w, m->w_d, (size_t)qlen * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     KTB_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -801,3 +801,31 @@ def test_fp8_linear_bsz_rows_untouched():
     sentinel = torch.full((20, 384), 7.0, dtype=torch.bfloat16, device="cuda")
     part = _fp8_run(x, w, ws, bsz=18, out=sentinel)
     assert np.array_equal(part[:18], full[:18]) and (sentinel[18:] == 7.0).all()
+
+
+def test_moe_block_forward_host_pinned_and_pageable_match_the_device_call():
+    """ktb200_moe_block_forward_host (the reference-facing call with HOST buffers, bench.py's e2e leg): a pinned output is written
+    by the kernel's own stores, pageable memory takes the staged copy — both must equal the device-pointer call bit for bit."""
+    lib = native.lib()
+    E, k, H, I = 8, 4, 4096, 512
+    gate, up, down = _synth(Q4_K, E * I * H, 51), _synth(Q4_K, E * I * H, 52), _synth(Q6_K, E * H * I, 53)
+    m = G.Moe(E, k, H, I, gate, up, down, Q4_K, Q4_K, Q6_K, BF16, max_tokens=8)
+    rng = np.random.default_rng(12)
+    Wg = torch.from_numpy(rng.standard_normal((E, H)).astype(np.float32)).cuda()
+    bg = torch.from_numpy((0.01 * rng.standard_normal(E)).astype(np.float32)).cuda()
+    gc = native.GateConfig(E, H, k, 1, 1, 0, 0, 1, 2.5, Wg.data_ptr(), bg.data_ptr(), BF16)
+    s = torch.cuda.current_stream().cuda_stream
+    for qlen in (1, 3):
+        x = (torch.randn(qlen, H) / 10).to(torch.bfloat16)
+        x_d = x.cuda()
+        y_d, idx_d, w_d = torch.zeros_like(x_d), torch.zeros((qlen, k), dtype=torch.int64, device="cuda"), torch.zeros((qlen, k), device="cuda")
+        native.check(lib.ktb200_moe_block_forward(C.byref(gc), m.h, None, qlen, x_d.data_ptr(), y_d.data_ptr(), idx_d.data_ptr(), w_d.data_ptr(), None, s))
+        torch.cuda.synchronize()
+        xp, yp = x.clone().pin_memory(), torch.zeros(qlen, H, dtype=torch.bfloat16).pin_memory()
+        idp, wp = torch.zeros((qlen, k), dtype=torch.int64).pin_memory(), torch.zeros((qlen, k)).pin_memory()
+        native.check(lib.ktb200_moe_block_forward_host(C.byref(gc), m.h, None, qlen, xp.data_ptr(), yp.data_ptr(), idp.data_ptr(), wp.data_ptr(), s))
+        assert torch.equal(yp.view(torch.int16), y_d.cpu().view(torch.int16)) and torch.equal(idp, idx_d.cpu()) and torch.equal(wp, w_d.cpu())
+        xn, yn = x.clone(), torch.zeros(qlen, H, dtype=torch.bfloat16)          # pageable
+        native.check(lib.ktb200_moe_block_forward_host(C.byref(gc), m.h, None, qlen, xn.data_ptr(), yn.data_ptr(), None, None, s))
+        assert torch.equal(yn.view(torch.int16), y_d.cpu().view(torch.int16))
+    m.close()
