@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(192, 2) fp8_linear_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = misc.tmem_base;
+    griddep_launch_dependents();   // a PDL-launched successor may set up and prefetch its own weights while this grid streams
 
     if (warp == 0) {
         // ---------------------------------------------------------------- weight boxes: independent of x, start at once
@@ -141,9 +142,9 @@ __global__ void __launch_bounds__(192, 2) fp8_linear_kernel(const __grid_constan
             const int r = (i >> 3) & (kFT - 1);
             if (r >= p.T) *reinterpret_cast<uint4*>(smem + kFOffB + i * 16) = make_uint4(0, 0, 0, 0);
         }
+        griddep_wait();   // x (or its quantised copy) comes from the kernel before this one; the weight boxes above did not wait
         if (p.xq) {
             // already quantised by fp8_act_quant_kernel: copy this CTA's K range into the swizzled B tiles (16-byte pieces)
-            griddep_wait();
             for (int i = tid - 64; i < p.T * nk * 8; i += 128) {
                 const int pc = i & 7, kb = (i >> 3) % nk, t = (i >> 3) / nk;
                 *reinterpret_cast<uint4*>(smem + kFOffB + kb * kFB + t * 128 + ((pc ^ (t & 7)) << 4)) =
@@ -329,8 +330,8 @@ int ktb200_fp8_linear_forward(ktb200_fp8_linear* l, int qlen, const void* x, voi
             KTB_CUDA_CHECK(launch_pdl(fp8_linear_kernel, dim3(l->row_tiles, l->ksplit), dim3(192), (size_t)kFSmem, (cudaStream_t)stream, l->map, p));
             count_launch(2);
         } else {
-            fp8_linear_kernel<<<dim3(l->row_tiles, l->ksplit), 192, kFSmem, (cudaStream_t)stream>>>(l->map, p);
-            KTB_LAUNCH_CHECK();
+            KTB_CUDA_CHECK(launch_pdl(fp8_linear_kernel, dim3(l->row_tiles, l->ksplit), dim3(192), (size_t)kFSmem, (cudaStream_t)stream, l->map, p));
+            count_launch(1);
         }
     }
     return KTB200_OK;
