@@ -382,7 +382,10 @@ class _KDeepseekMoEMixin:
         names = [f"{self.key}.shared_experts.{n}_proj.weight" for n in ("gate", "up", "down")]
         if ld is None or not all(ld.has_tensor(n) for n in names):
             return None
-        types = [int(ld.get_ggml_type(n)) for n in names]
+        try:
+            types = [int(ld.get_ggml_type(n)) for n in names]
+        except KeyError:      # e.g. FP8 shared experts in a hybrid safetensors file: they stay KLinearFP8 modules
+            return None
         if any(GGML_NAMES.get(t) not in B200_WEIGHT_TYPES for t in types):
             return None
         dev = torch.device("cuda", gen.dev_index)

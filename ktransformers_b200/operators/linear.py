@@ -250,6 +250,8 @@ class KTransformersLinear(BaseInjectedModule, KLinearBase):
                  prefill_op: str | None = "KLinearTorch", **kwargs):
         BaseInjectedModule.__init__(self, key, gguf_loader, config, orig_module, prefill_device, generate_device, **kwargs)
         KLinearBase.__init__(self, key, gguf_loader, config, orig_module, generate_device, **kwargs)
+        prefill_op = None if prefill_op == "None" else prefill_op        # YAML spells it as a string
+        generate_op = None if generate_op == "None" else generate_op
         for op in (prefill_op, generate_op):
             assert op is None or op in LINEAR_MAP, f"linear_type {op} not supported"
         self.prefill_linear = LINEAR_MAP[prefill_op](key, gguf_loader, config, orig_module, prefill_device, **kwargs) if prefill_op else None
@@ -257,15 +259,19 @@ class KTransformersLinear(BaseInjectedModule, KLinearBase):
         self.mode = InferenceState.UNLOAD
 
     def forward(self, x, bsz_tensor=None):
-        if self.mode == InferenceState.PREFILL:
-            assert self.prefill_linear is not None, "prefill linear is not initialized"
+        if self.mode == InferenceState.PREFILL and self.prefill_linear is not None:
             return self.prefill_linear.forward(x, bsz_tensor)
         assert self.generate_linear is not None, "generate linear is not initialized"
         return self.generate_linear.forward(x, bsz_tensor)
 
     def load(self, w=None, mode: InferenceState = InferenceState.GENERATE):
         mode = mode or InferenceState.GENERATE
-        if mode == InferenceState.PREFILL:
+        if mode == InferenceState.PREFILL and self.prefill_linear is None:
+            # `prefill_op: None`: the generate linear serves both phases (GPU-resident weights, nothing to swap)
+            self.generate_linear.load(w=w)
+            self.device = self.generate_linear.device
+            self.weight = self.generate_linear.weight
+        elif mode == InferenceState.PREFILL:
             if self.generate_linear is not None:
                 self.generate_linear.unload()
             self.prefill_linear.load(w=w)

@@ -234,14 +234,62 @@ class SafeTensorLoader(ModelLoader):
         if not found:
             raise FileNotFoundError(f"No Safetensor files found in {root}")
 
+    # The FP8 + GGUF hybrid written by archive/merge_tensors (BASELINE configs 3 / 5): FP8 linears under their HF names
+    # (`*.weight` float8_e4m3fn + `*.weight_scale_inv`), routed experts as RAW ggml blocks under their GGUF names
+    # (`blk.N.ffn_{gate,up,down}_exps.weight` uint8 + a scalar `*.ggml_type`), router / norms as plain tensors under GGUF names.
+    # The methods below give that file the GGUFLoader surface the operators use (custom_loader.py:114-262).
+    def _resolve(self, name: str):
+        if name in self.tensor_file_map:
+            return name
+        g = translate_name_to_gguf(name)
+        return g if g in self.tensor_file_map else None
+
     def has_tensor(self, name: str) -> bool:
-        return name in self.tensor_file_map
+        return self._resolve(name) is not None
 
     def load_tensor(self, key: str, device: str = "cpu"):
-        if key not in self.tensor_file_map:
+        k = self._resolve(key)
+        if k is None:
             raise KeyError(f"Key {key} not found in Safetensor files")
-        with self._open(self.tensor_file_map[key], framework="pt") as f:
-            return f.get_tensor(key).to(device)
+        with self._open(self.tensor_file_map[k], framework="pt") as f:
+            return f.get_tensor(k).to(device)
+
+    def get_ggml_type(self, name: str) -> int:
+        k = self._resolve(name)
+        tk = (k[:-len(".weight")] if k and k.endswith(".weight") else str(k)) + ".ggml_type"
+        if k is None or tk not in self.tensor_file_map:
+            raise KeyError(f"{name} is not stored as raw ggml blocks (no {tk})")
+        return int(self.load_tensor(tk).item())
+
+    def get_mmap_tensor(self, name: str) -> np.ndarray:
+        self.get_ggml_type(name)                         # raw blocks only
+        return self.load_tensor(name).contiguous().view(torch.uint8).reshape(-1).numpy()
+
+    def load_gguf_tensor(self, name: str, device: str = "cpu", target_dtype=None) -> torch.Tensor:
+        """plain (unquantised) tensors of the hybrid file: router weight, e_score_correction_bias, norms"""
+        t = self.load_tensor(name, device)
+        if t.dtype in (torch.uint8, torch.float8_e4m3fn):
+            raise NotImplementedError(f"{name}: quantised tensors of a safetensors file are consumed raw (get_mmap_tensor / KLinearFP8), not dequantised")
+        return t.to(target_dtype) if target_dtype is not None else t
+
+    def load_experts(self, key: str, device: str = "cpu") -> dict:
+        """custom_loader.py:114-148 (hybrid branch): {gate, up, down: raw ggml bytes, *_type: ggml type}"""
+        base = translate_name_to_gguf(key)
+        if not self.has_tensor(base + ".ffn_gate_exps.weight"):
+            raise ValueError(f"No experts found for key {key}")
+        out = {}
+        for n in ("gate", "up", "down"):
+            out[n] = self.get_mmap_tensor(f"{base}.ffn_{n}_exps.weight")
+            out[n + "_type"] = self.get_ggml_type(f"{base}.ffn_{n}_exps.weight")
+        return out
+
+    def load_gate(self, key: str, device: str = "cpu") -> dict:
+        """custom_loader.py:225-250: {'weight', 'e_score_correction_bias'} (None when absent)"""
+        res = {"weight": None, "e_score_correction_bias": None}
+        for k in res:
+            if self.has_tensor(f"{key}.{k}"):
+                res[k] = self.load_tensor(f"{key}.{k}", device)
+        return res
 
 
 class ModelLoaderFactory:

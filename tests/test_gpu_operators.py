@@ -319,3 +319,72 @@ def test_klinear_fp8_operator_from_safetensors(tmp_path):
             lin.generate_linear.forward(x)
     finally:
         torch.set_default_dtype(old)
+
+
+def test_fp8_linear_ggml_experts_rule_file_on_a_hybrid_safetensors(tmp_path):
+    """BASELINE config 3's layout end to end on the host side: the FP8 + GGUF hybrid safetensors (FP8 128x128 linears under HF
+    names, raw GGUF expert blocks + `.ggml_type` under GGUF names) through `optimize_and_load_gguf` with
+    DeepSeek-V3-Chat-fp8-linear-ggml-experts-b200.yaml: KLinearFP8 linears, KExpertsB200 experts, KMoEGateB200 router."""
+    from safetensors.torch import save_file
+    from ktransformers_b200.models.modeling_deepseek_v3 import DeepseekV3Config, DeepseekV3MoEOnlyForCausalLM
+    from ktransformers_b200.operators.experts import KDeepseekV3MoE, KExpertsB200
+    from ktransformers_b200.operators.linear import KLinearFP8, KTransformersLinear
+    from ktransformers_b200.optimize.optimize import optimize_and_load_gguf
+    from ktransformers_b200.util.synth import synth_blocks
+    from oracle.bindings import Oracle
+    import ktransformers_b200.optimize.optimize as opt
+    orc = Oracle()
+    g = torch.Generator().manual_seed(11)
+    tensors, dense = {}, {}
+
+    def add_fp8(name, out_f, in_f):
+        w = (torch.randn(out_f, in_f, generator=g) * 0.3).to(torch.float8_e4m3fn)
+        s = torch.rand((out_f + 127) // 128, in_f // 128, generator=g) * 0.02 + 0.005
+        tensors[name + ".weight"], tensors[name + ".weight_scale_inv"] = w, s
+        d = w.float().view(-1, 128, in_f // 128, 128) * s.view(-1, 1, in_f // 128, 1) if out_f % 128 == 0 else None
+        dense[name] = d.reshape(out_f, in_f)
+
+    for n, (o, i) in {"gate_proj": (I, H), "up_proj": (I, H), "down_proj": (H, I)}.items():
+        add_fp8(f"model.layers.0.mlp.{n}", o, i)
+        add_fp8(f"model.layers.1.mlp.shared_experts.{n}", o, i)
+    for n, qt, shape in (("gate", 12, (E, I, H)), ("up", 12, (E, I, H)), ("down", 14, (E, H, I))):
+        q = synth_blocks(qt, int(np.prod(shape)), "cpu", 300 + qt + len(n)).numpy()
+        tensors[f"blk.1.ffn_{n}_exps.weight"] = torch.from_numpy(q.copy())
+        tensors[f"blk.1.ffn_{n}_exps.ggml_type"] = torch.tensor(qt)
+        dense[f"exps.{n}"] = torch.from_numpy(orc.to_float(q, qt, int(np.prod(shape))).reshape(shape))
+    tensors["blk.1.ffn_gate_inp.weight"] = torch.randn(E, H, generator=g)
+    tensors["blk.1.exp_probs_b.bias"] = 0.01 * torch.randn(E, generator=g)
+    save_file(tensors, str(tmp_path / "hybrid.safetensors"))
+    rule = os.path.join(os.path.dirname(opt.__file__), "optimize_rules", "DeepSeek-V3-Chat-fp8-linear-ggml-experts-b200.yaml")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        cfg = DeepseekV3Config(hidden_size=H, intermediate_size=I, moe_intermediate_size=I, n_routed_experts=E, n_shared_experts=1,
+                               num_experts_per_tok=K, n_group=2, topk_group=1, num_hidden_layers=2, first_k_dense_replace=1)
+        with torch.device("meta"):
+            model = DeepseekV3MoEOnlyForCausalLM(cfg)
+        optimize_and_load_gguf(model, rule, str(tmp_path), cfg, default_device="cuda")
+        moe = model.model.layers[1].mlp
+        assert isinstance(moe, KDeepseekV3MoE) and isinstance(moe.experts.generate_experts, KExpertsB200) and moe.experts.generate_experts.handle is not None
+        sh = moe.shared_experts.gate_proj
+        assert isinstance(sh, KTransformersLinear) and isinstance(sh.generate_linear, KLinearFP8) and sh.generate_linear.handle is not None
+        assert isinstance(model.model.layers[0].mlp.down_proj.generate_linear, KLinearFP8)
+        x = (torch.randn(1, 3, H, device="cuda") / 10).to(torch.bfloat16)
+        y = moe(x)
+        xf = x.view(-1, H).float().cpu()
+        idx, wt = moe.gate(x)
+        idx, wt = idx.cpu(), wt.cpu()
+        want = torch.zeros_like(xf)
+        for t in range(xf.shape[0]):
+            for j in range(K):
+                e = int(idx[t, j])
+                want[t] += (torch.nn.functional.silu(dense["exps.gate"][e] @ xf[t]) * (dense["exps.up"][e] @ xf[t])) @ dense["exps.down"][e].T * wt[t, j]
+        p = "model.layers.1.mlp.shared_experts."
+        want += (torch.nn.functional.silu(xf @ dense[p + "gate_proj"].T) * (xf @ dense[p + "up_proj"].T)) @ dense[p + "down_proj"].T
+        assert (y.view(-1, H).float().cpu() - want).abs().max() <= 0.06 * want.abs().max()
+        y0 = model.model.layers[0].mlp(x)                       # the dense layer: three KLinearFP8 projections
+        p0 = "model.layers.0.mlp."
+        want0 = (torch.nn.functional.silu(xf @ dense[p0 + "gate_proj"].T) * (xf @ dense[p0 + "up_proj"].T)) @ dense[p0 + "down_proj"].T
+        assert (y0.view(-1, H).float().cpu() - want0).abs().max() <= 0.06 * want0.abs().max()
+    finally:
+        torch.set_default_dtype(old)

@@ -349,3 +349,36 @@ def test_safetensor_loader_and_klinear_fp8_contract(tmp_path):
         lin.load(device="cpu")
     with pytest.raises(Exception):
         lin.forward(torch.zeros(1, 128))           # Not Loaded
+
+
+def test_hybrid_safetensors_serve_the_gguf_loader_surface(tmp_path):
+    """The FP8 + GGUF hybrid of archive/merge_tensors (custom_loader.py:114-250): raw ggml expert blocks + scalar `.ggml_type`
+    under GGUF names, router tensors under GGUF names, FP8 linears under HF names — read through the calls the operators make."""
+    import torch
+    from safetensors.torch import save_file
+    from ktransformers_b200.util.custom_loader import SafeTensorLoader
+    E, nbytes = 4, 144 * 8
+    raw = {n: torch.randint(0, 255, (E, nbytes), dtype=torch.uint8) for n in ("gate", "up", "down")}
+    tensors = {f"blk.1.ffn_{n}_exps.weight": raw[n] for n in raw}
+    tensors.update({f"blk.1.ffn_{n}_exps.ggml_type": torch.tensor(12 if n != "down" else 14) for n in raw})
+    tensors["blk.1.ffn_gate_inp.weight"] = torch.randn(E, 64)
+    tensors["blk.1.exp_probs_b.bias"] = torch.randn(E)
+    tensors["model.layers.1.mlp.shared_experts.up_proj.weight"] = torch.randn(128, 128).to(torch.float8_e4m3fn)
+    tensors["model.layers.1.mlp.shared_experts.up_proj.weight_scale_inv"] = torch.rand(1, 1)
+    save_file(tensors, str(tmp_path / "hybrid.safetensors"))
+    ld = SafeTensorLoader(str(tmp_path))
+    key = "model.layers.1.mlp.experts"
+    assert ld.has_tensor(key + ".ffn_gate_exps.weight") and ld.has_tensor("blk.1.ffn_down_exps.weight")
+    assert ld.get_ggml_type(key + ".ffn_down_exps.weight") == 14 and ld.get_ggml_type("blk.1.ffn_up_exps.weight") == 12
+    assert np.array_equal(ld.get_mmap_tensor(key + ".ffn_up_exps.weight"), raw["up"].numpy().reshape(-1))
+    ex = ld.load_experts(key)
+    assert ex["gate_type"] == 12 and ex["down_type"] == 14 and np.array_equal(ex["down"], raw["down"].numpy().reshape(-1))
+    g = ld.load_gate("model.layers.1.mlp.gate")
+    assert torch.equal(g["weight"], tensors["blk.1.ffn_gate_inp.weight"]) and torch.equal(g["e_score_correction_bias"], tensors["blk.1.exp_probs_b.bias"])
+    assert ld.load_gguf_tensor("model.layers.1.mlp.gate.weight", target_dtype=torch.float32).shape == (E, 64)
+    with pytest.raises(KeyError):
+        ld.get_ggml_type("model.layers.1.mlp.shared_experts.up_proj.weight")      # an FP8 linear, not raw ggml blocks
+    with pytest.raises(NotImplementedError):
+        ld.load_gguf_tensor("model.layers.1.mlp.shared_experts.up_proj.weight")
+    with pytest.raises(ValueError):
+        ld.load_experts("model.layers.7.mlp.experts")
