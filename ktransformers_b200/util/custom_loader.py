@@ -221,6 +221,8 @@ class SafeTensorLoader(ModelLoader):
         from safetensors import safe_open
         self._open = safe_open
         self.tensor_file_map: dict = {}
+        self.tensor_device_map: dict = {}        # filled by optimize.inject, like GGUFLoader's
+        self.tensor_info: dict = {}
         root = os.path.dirname(file_path) if os.path.isfile(file_path) else file_path
         found = False
         for cur, _, files in os.walk(root):
@@ -231,6 +233,7 @@ class SafeTensorLoader(ModelLoader):
                     with safe_open(full, framework="pt") as f:
                         for k in f.keys():
                             self.tensor_file_map[k] = full
+                            self.tensor_info[k] = {"shape": list(f.get_slice(k).get_shape())}
         if not found:
             raise FileNotFoundError(f"No Safetensor files found in {root}")
 
