@@ -222,6 +222,29 @@ def test_moe_with_shared_expert_matches_two_rounded_terms(oracle, sgt, sdt, fuse
     m.close(); mlp.close()
 
 
+def test_moe_with_shared_expert_prefill_sized_batch(oracle):
+    """ktb200_moe_forward_shared at 60 tokens: the routed experts take the grouped tensor-core path, the shared expert follows as a
+    separate MLP that accumulates in bf16 — the same two rounded terms."""
+    E, k, H, I, qlen = 8, 4, 1024, 512, 60
+    gate, up, down = _synth(Q4_K, E * I * H, 81), _synth(Q4_K, E * I * H, 82), _synth(Q6_K, E * H * I, 83)
+    sg, su, sd = _synth(Q4_K, I * H, 84), _synth(Q4_K, I * H, 85), _synth(Q6_K, H * I, 86)
+    g_np, u_np, d_np, sg_np, su_np, sd_np = (t.cpu().numpy() for t in (gate, up, down, sg, su, sd))
+    m = G.Moe(E, k, H, I, gate, up, down, Q4_K, Q4_K, Q6_K, BF16)
+    mlp = G.Mlp(H, I, sg, su, sd, Q4_K, Q4_K, Q6_K, BF16)
+    rng = np.random.default_rng(23)
+    x = f32_to_bf16_bits((rng.standard_normal((qlen, H)) / 100).astype(np.float32))
+    ids = np.stack([rng.permutation(E)[:k] for _ in range(qlen)]).astype(np.int64)
+    w = rng.random((qlen, k)).astype(np.float32)
+    n0 = native.launch_count()
+    got = G.moe_forward_shared(m, mlp, ids, w, x)
+    assert native.launch_count() - n0 >= 12          # 10 grouped launches + the shared MLP's
+    routed = oracle.moe_forward(E, H, I, g_np, u_np, d_np, Q4_K, Q4_K, Q6_K, BF16, ids, w, x)
+    shared = oracle.mlp_forward(H, I, sg_np, su_np, sd_np, Q4_K, Q4_K, Q6_K, BF16, x)
+    want = (torch.from_numpy(routed.view(np.int16)).view(torch.bfloat16) + torch.from_numpy(shared.view(np.int16)).view(torch.bfloat16))
+    assert_bf16_close(got, want.view(torch.int16).numpy().view(np.uint16))
+    m.close(); mlp.close()
+
+
 # ------------------------------------------------------------------------------------------ linear / mlp
 def test_linear_and_mlp_vs_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "linear_mlp.npz"))
