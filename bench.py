@@ -830,6 +830,39 @@ def main():
         except Exception as e:  # pragma: no cover
             prefill = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- FP8 128 x 128 linear (KLinearFP8, BASELINE configs 3 / 5) at two DeepSeek-V3 projection shapes, bs 1 -------------------
+    fp8 = None
+    if rank == 0 and world == 1 and not args.no_prefill:
+        try:
+            fp8 = {"kernel": "fp8_linear_kernel (TMA -> tcgen05.mma.kind::f8f6f4 -> TMEM, csrc/fp8_linear.cu)", "bound": "hbm", "shapes": {}}
+            peak, how = measured_peak_gbs()
+            for name, Kf, Nf, copies in (("lm_head 7168->129280", 7168, 129280, 2), ("o_proj 16384->7168", 16384, 7168, 4)):
+                hs, keep = [], []
+                for c in range(copies):     # cycled weight copies: no call finds its weights in L2
+                    wq = torch.randint(0, 120, (Nf, Kf), dtype=torch.uint8, device=dev)
+                    wsc = torch.rand(((Nf + 127) // 128, Kf // 128), device=dev) * 0.01 + 0.001
+                    hh_ = C.c_void_p()
+                    native.check(lib.ktb200_fp8_linear_create(Kf, Nf, wq.data_ptr(), wsc.data_ptr(), BF16, local_rank, C.byref(hh_)))
+                    hs.append(hh_); keep.append((wq, wsc))
+                xf = (torch.randn(1, Kf, device=dev) / 10).to(torch.bfloat16); yf = torch.zeros(1, Nf, dtype=torch.bfloat16, device=dev)
+                for i in range(copies):
+                    native.check(lib.ktb200_fp8_linear_forward(hs[i], 1, xf.data_ptr(), yf.data_ptr(), None, S()))
+                torch.cuda.synchronize()
+                n_it = 5 * copies
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(n_it):
+                    native.check(lib.ktb200_fp8_linear_forward(hs[i % copies], 1, xf.data_ptr(), yf.data_ptr(), None, S()))
+                e1.record(); torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) / n_it * 1e3
+                fp8["shapes"][name] = {"us": us, "achieved_GBps": Kf * Nf / us / 1e3, "frac": Kf * Nf / us / 1e3 / peak, "bytes": Kf * Nf}
+                for hh_ in hs:
+                    lib.ktb200_fp8_linear_destroy(hh_)
+                del keep
+            fp8["peak"], fp8["peak_source"] = peak, how
+        except Exception as e:  # pragma: no cover
+            fp8 = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- the whole decode step (attention + dense + MoE + lm_head), every rank its own token ------------------------
     full = None
     if not args.no_full_step:
@@ -873,7 +906,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
                 "gpu_launches": launches_per_step * args.steps, "cuda_graph": graph is not None,
                 "roofline": roof_block if roof_block else roof, "roofline_gate_up": roof, "roofline_down": roof_down, "cpu_baseline": cpu_baseline,
-                "parity_check": parity, "full_decode": full, "prefill_grouped": prefill,
+                "parity_check": parity, "full_decode": full, "prefill_grouped": prefill, "fp8_linear": fp8,
                 "step_hbm": {"algorithmic_bytes_per_token_per_gpu": step_bytes, "achieved_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac_of_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / measured_peak_gbs()[0]}}
         print(json.dumps(line), flush=True)
