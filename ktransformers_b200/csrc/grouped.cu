@@ -37,16 +37,8 @@ constexpr int kGA = kGM * 128;            // 16,384: 128 rows x 128 int8 of K, o
 constexpr int kGB = 2 * kGN * 128;        //  8,192: 32 rows (Q4_K) or 64 rows (Q6_K even / odd variants)
 constexpr int kGA2 = kGM * 32, kGB2 = kGN * 32;
 constexpr int kRawPitch = 80, kRawSlot = 2 * kGM * kRawPitch;   // 5 x 16 bytes per producer thread and stage (odd pitch: conflict-free LDS.128)
-// Shared-memory map per operand format (FMT 0 Q4_K with one accumulator per sub-block, 1 Q6_K 4-row tiles, 2 Q4_K with the
-// sub-block scale split into two 3-bit digits: two u8 operand tiles per stage, accumulators per SUPER-block)
-template <int FMT>
-struct GrpLayout {
-    static constexpr int A = FMT == 2 ? 2 * kGA : kGA;        // operand stage: [128 rows x 128 B] (x 2 digit tiles)
-    static constexpr int B = FMT == 2 ? kGB / 2 : kGB;        // 32 token rows (64 for Q6_K's even / odd variants)
-    static constexpr int Raw = FMT == 2 ? 4 : kGRaw;          // raw-ring slots
-    static constexpr int OffB = kGStages * A, OffA2 = OffB + kGStages * B, OffB2 = OffA2 + kGStages * kGA2, OffRaw = OffB2 + kGStages * kGB2,
-                         OffMisc = OffRaw + Raw * kRawSlot;
-};
+constexpr int kOffB = kGStages * kGA, kOffA2 = kOffB + kGStages * kGB, kOffB2 = kOffA2 + kGStages * kGA2, kOffRaw = kOffB2 + kGStages * kGB2,
+              kOffMiscG = kOffRaw + kGRaw * kRawSlot;
 
 struct GrpMisc {
     unsigned long long ab_full[kGStages], smem_free[kGStages], tmem_full[2], tmem_free[2], hdr_free[kGHdr];
@@ -55,9 +47,8 @@ struct GrpMisc {
     float dxs[kGHdr][kGN];
     uint4 hdr[kGHdr][kGM];      // Q4_K: the block header (d, dmin, 12 scale bytes); Q6_K: 8 scales of the half, d as f32
 };
-template <int FMT>
-constexpr int grp_smem() { return GrpLayout<FMT>::OffMisc + (int)sizeof(GrpMisc) + 1024; }
-static_assert(grp_smem<0>() <= 227 * 1024 && grp_smem<1>() <= 227 * 1024 && grp_smem<2>() <= 227 * 1024, "shared memory budget");
+constexpr int kGSmem = kOffMiscG + (int)sizeof(GrpMisc) + 1024;
+static_assert(kGSmem <= 227 * 1024, "shared memory budget");
 
 struct GrpGemmParams {
     const uint8_t* w;          // expert weights
@@ -119,9 +110,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    using L = GrpLayout<FMT>;
-    constexpr bool Q4 = FMT != 1;   // Q4_K blocks (FMT 0 and 2) or Q6_K tiles
-    GrpMisc& misc = *reinterpret_cast<GrpMisc*>(smem + L::OffMisc);
+    GrpMisc& misc = *reinterpret_cast<GrpMisc*>(smem + kOffMiscG);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = p.Kc / QK_K, nst = 2 * nblk, MT = p.R / kGM;
     if (tid == 0) {
@@ -143,8 +132,8 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
         // ========================================================================== producers: thread = (weight row r, half `part`)
         // `part` is warp-uniform (warps 0-3: first half of the row's share, warps 4-7: second) so that no branch below diverges
         const int pt = tid, r = pt & (kGM - 1), part = pt >> 7, sw = r & 7, bn = pt >> 3, pc = pt & 7;
-        const uint32_t raw_dst = base + L::OffRaw + pt * kRawPitch;
-        const uint8_t* raw_src = smem + L::OffRaw + pt * kRawPitch;
+        const uint32_t raw_dst = base + kOffRaw + pt * kRawPitch;
+        const uint8_t* raw_src = smem + kOffRaw + pt * kRawPitch;
         const int c16 = 4 * nblk * 16;   // Q6_K tiles: bytes between two 16-byte chunk planes of an item
         // fetch cursor: runs kGRaw stages ahead of the conversion, across tile boundaries; plain running pointers
         int ftile = blockIdx.x, fst = 0, ffi = 0;
@@ -157,10 +146,10 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
             const int4 ti = __ldg(p.tinfo + ftile);
             fxq = nullptr; fbs = nullptr; fdx = nullptr;
             if (bn < ti.w) fxq = p.xq + (long)(p.rowmap ? __ldg(p.rowmap + ti.z + bn) : ti.z + bn) * p.Kc + pc * 16;
-            if (Q4 && pt < 64 && (pt >> 1) < ti.w) fbs = p.xbs + (long)(p.rowmap ? __ldg(p.rowmap + ti.z + (pt >> 1)) : ti.z + (pt >> 1)) * (p.Kc / 16) + (pt & 1) * 8;
+            if (FMT == 0 && pt < 64 && (pt >> 1) < ti.w) fbs = p.xbs + (long)(p.rowmap ? __ldg(p.rowmap + ti.z + (pt >> 1)) : ti.z + (pt >> 1)) * (p.Kc / 16) + (pt & 1) * 8;
             if (pt >= 64 && pt < 96 && pt - 64 < ti.w) fdx = p.xd + (long)(p.rowmap ? __ldg(p.rowmap + ti.z + pt - 64) : ti.z + pt - 64) * nblk;
             const int row = ti.y + r;
-            if (Q4) fw = p.w + (long)ti.x * p.expert_bytes + (long)row * nblk * SZ_Q4_K + 16 + part * 32;   // this thread's qs of block 0, first half
+            if (FMT == 0) fw = p.w + (long)ti.x * p.expert_bytes + (long)row * nblk * SZ_Q4_K + 16 + part * 32;   // this thread's qs of block 0, first half
             else {
                 fitem = p.w + (long)ti.x * p.expert_bytes + (long)(row >> 2) * 4 * nblk * SZ_Q6_K;
                 ffi = (row & 3) * nblk;
@@ -170,11 +159,11 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
         auto issue = [&](uint32_t dst) {
             if (ftile < total_tiles) {
                 const int hh = fst & 1;
-                if (Q4) {
+                if (FMT == 0) {
                     const uint8_t* q = fw + hh * 64;
                     cp_async16(dst, q);
                     cp_async16(dst + 16, q + 16);
-                    if (FMT == 2 || part == 0 || hh == 1) cp_async16(dst + 32, fw - 16 - part * 32);   // digits: every stage needs its two scales
+                    if (part == 0 || hh == 1) cp_async16(dst + 32, fw - 16 - part * 32);
                 } else {
                     const uint8_t* q = fw + (long)(4 * hh) * c16;
                     cp_async16(dst, q);
@@ -187,9 +176,9 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 }
                 if (fxq) { cp_async16(dst + 48, fxq); fxq += 128; }
                 if (hh == 1) {
-                    if (Q4 && fbs) { cp_async16(dst + 64, fbs); fbs += 16; }
-                    if (fdx) { cp_async4(dst + (Q4 ? 64 : 76), fdx); fdx += 1; }
-                    fw += Q4 ? SZ_Q4_K : 16;
+                    if (FMT == 0 && fbs) { cp_async16(dst + 64, fbs); fbs += 16; }
+                    if (fdx) { cp_async4(dst + (FMT == 0 ? 64 : 76), fdx); fdx += 1; }
+                    fw += FMT == 0 ? SZ_Q4_K : 16;
                     ffi++;
                 }
                 if (++fst == nst) { fst = 0; ftile += gridDim.x; enter_tile(); }
@@ -197,7 +186,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
             cp_async_commit();
         };
         enter_tile();
-        for (int i = 0; i < L::Raw; i++) issue(raw_dst + i * kRawSlot);
+        for (int i = 0; i < kGRaw; i++) issue(raw_dst + i * kRawSlot);
         int slot = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int4 ti = __ldg(p.tinfo + tile);
@@ -207,58 +196,18 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 const int hh = st & 1;
                 const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && tile == 0 && st < 96;
                 if (tr) p.trace[(0 * 96 + st) * 4 + 0] = clock64();
-                cp_async_wait<L::Raw - 1>();
+                cp_async_wait<kGRaw - 1>();
                 if (tr) p.trace[(0 * 96 + st) * 4 + 1] = clock64();
                 const uint4* rs = reinterpret_cast<const uint4*>(raw_src + slot * kRawSlot);
                 const uint4 f0 = rs[0], f1 = rs[1], f2 = rs[2], f3 = rs[3], f4 = rs[4];
                 issue(raw_dst + slot * kRawSlot);   // refill the slot just read (thread-private bytes: no barrier involved)
-                slot = slot == L::Raw - 1 ? 0 : slot + 1;
+                slot = slot == kGRaw - 1 ? 0 : slot + 1;
                 bar_wait(smem_u32(&misc.smem_free[stage]), sphase ^ 1);
                 bar_wait(smem_u32(&misc.hdr_free[hs]), hphase ^ 1);
                 if (tr) p.trace[(0 * 96 + st) * 4 + 2] = clock64();
-                uint8_t* arow = smem + stage * L::A + r * 128;
+                uint8_t* arow = smem + stage * kGA + r * 128;
                 const uint4 z = make_uint4(0, 0, 0, 0);
-                if (FMT == 2) {
-                    // the 6-bit sub-block scale as two 3-bit digits, sc = 8 hi + lo: q * hi and q * lo stay below 106, so ONE integer
-                    // multiply scales four packed nibbles, both products are u8 operands, and the tensor core sums whole super-blocks:
-                    // isum = 8 * (q hi . x) + (q lo . x), exact
-                    const uint32_t hw[4] = {f2.x, f2.y, f2.z, f2.w};
-                    int sc0 = 0, sc1 = 0, mnx;
-                    switch (2 * hh + part) {   // constant sub-block indices: header bytes stay in registers
-                        case 0: q4k_scale_min(hw, 0, sc0, mnx); q4k_scale_min(hw, 1, sc1, mnx); break;
-                        case 1: q4k_scale_min(hw, 2, sc0, mnx); q4k_scale_min(hw, 3, sc1, mnx); break;
-                        case 2: q4k_scale_min(hw, 4, sc0, mnx); q4k_scale_min(hw, 5, sc1, mnx); break;
-                        default: q4k_scale_min(hw, 6, sc0, mnx); q4k_scale_min(hw, 7, sc1, mnx); break;
-                    }
-                    const uint32_t h0 = sc0 >> 3, l0 = sc0 & 7, h1 = sc1 >> 3, l1 = sc1 & 7;
-                    const uint32_t qlo[8] = {f0.x & 0x0F0F0F0Fu, f0.y & 0x0F0F0F0Fu, f0.z & 0x0F0F0F0Fu, f0.w & 0x0F0F0F0Fu,
-                                             f1.x & 0x0F0F0F0Fu, f1.y & 0x0F0F0F0Fu, f1.z & 0x0F0F0F0Fu, f1.w & 0x0F0F0F0Fu};
-                    const uint32_t qhi[8] = {(f0.x >> 4) & 0x0F0F0F0Fu, (f0.y >> 4) & 0x0F0F0F0Fu, (f0.z >> 4) & 0x0F0F0F0Fu, (f0.w >> 4) & 0x0F0F0F0Fu,
-                                             (f1.x >> 4) & 0x0F0F0F0Fu, (f1.y >> 4) & 0x0F0F0F0Fu, (f1.z >> 4) & 0x0F0F0F0Fu, (f1.w >> 4) & 0x0F0F0F0Fu};
-                    const int pi = 4 * part;
-                    uint8_t* alo = arow + kGA;   // the low-digit tile follows the high-digit tile
-                    *reinterpret_cast<uint4*>(arow + (((pi + 0) ^ sw) << 4)) = make_uint4(qlo[0] * h0, qlo[1] * h0, qlo[2] * h0, qlo[3] * h0);
-                    *reinterpret_cast<uint4*>(arow + (((pi + 1) ^ sw) << 4)) = make_uint4(qlo[4] * h0, qlo[5] * h0, qlo[6] * h0, qlo[7] * h0);
-                    *reinterpret_cast<uint4*>(arow + (((pi + 2) ^ sw) << 4)) = make_uint4(qhi[0] * h1, qhi[1] * h1, qhi[2] * h1, qhi[3] * h1);
-                    *reinterpret_cast<uint4*>(arow + (((pi + 3) ^ sw) << 4)) = make_uint4(qhi[4] * h1, qhi[5] * h1, qhi[6] * h1, qhi[7] * h1);
-                    *reinterpret_cast<uint4*>(alo + (((pi + 0) ^ sw) << 4)) = make_uint4(qlo[0] * l0, qlo[1] * l0, qlo[2] * l0, qlo[3] * l0);
-                    *reinterpret_cast<uint4*>(alo + (((pi + 1) ^ sw) << 4)) = make_uint4(qlo[4] * l0, qlo[5] * l0, qlo[6] * l0, qlo[7] * l0);
-                    *reinterpret_cast<uint4*>(alo + (((pi + 2) ^ sw) << 4)) = make_uint4(qhi[0] * l1, qhi[1] * l1, qhi[2] * l1, qhi[3] * l1);
-                    *reinterpret_cast<uint4*>(alo + (((pi + 3) ^ sw) << 4)) = make_uint4(qhi[4] * l1, qhi[5] * l1, qhi[6] * l1, qhi[7] * l1);
-                    if (hh == 1) {
-                        if (part == 0) misc.hdr[hs][r] = f2;   // the epilogue reads d / dmin once per super-block
-                        int sc, mn[4];
-                        if (part == 0) {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) q4k_scale_min(hw, j, sc, mn[j]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) q4k_scale_min(hw, 4 + j, sc, mn[j]);
-                        }
-                        uint8_t* a2 = smem + L::OffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16 + part * 128;
-                        *reinterpret_cast<uint4*>(a2) = make_uint4(h2(mn[0], mn[0]), h2(mn[1], mn[1]), h2(mn[2], mn[2]), h2(mn[3], mn[3]));
-                    }
-                } else if (FMT == 0) {
+                if (FMT == 0) {
                     // chunk c = 2 hh + part (32 bytes of qs): low nibbles = sub-block 2c (elements 64c .. 64c+31), high nibbles = sub-block 2c+1
                     const int pi = 4 * part;
                     *reinterpret_cast<uint4*>(arow + (((pi + 0) ^ sw) << 4)) = make_uint4(f0.x & 0x0F0F0F0Fu, f0.y & 0x0F0F0F0Fu, f0.z & 0x0F0F0F0Fu, f0.w & 0x0F0F0F0Fu);
@@ -278,7 +227,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
 #pragma unroll
                             for (int j = 0; j < 4; j++) q4k_scale_min(hw, 4 + j, sc, mn[j]);
                         }
-                        uint8_t* a2 = smem + L::OffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16 + part * 128;
+                        uint8_t* a2 = smem + kOffA2 + stage * kGA2 + (r >> 3) * 256 + (r & 7) * 16 + part * 128;
                         *reinterpret_cast<uint4*>(a2) = make_uint4(h2(mn[0], mn[0]), h2(mn[1], mn[1]), h2(mn[2], mn[2]), h2(mn[3], mn[3]));
                     }
                 } else {
@@ -309,17 +258,17 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                     dsel += hh;
                 }
                 // activations: piece (bn, pc)
-                uint8_t* Bs = smem + L::OffB + stage * L::B;
+                uint8_t* Bs = smem + kOffB + stage * kGB;
                 const uint4 bv = bn < n_valid ? f3 : z;
-                if (Q4) {
+                if (FMT == 0) {
                     *reinterpret_cast<uint4*>(Bs + bn * 128 + ((pc ^ (bn & 7)) << 4)) = bv;
                 } else {   // a 16-byte piece is one Q6_K sub-block: rows 0-31 keep the even pieces, rows 32-63 the odd ones
                     *reinterpret_cast<uint4*>(Bs + bn * 128 + ((pc ^ (bn & 7)) << 4)) = (pc & 1) ? z : bv;
                     *reinterpret_cast<uint4*>(Bs + (kGN + bn) * 128 + ((pc ^ (bn & 7)) << 4)) = (pc & 1) ? bv : z;
                 }
                 if (hh == 1 && pt < 96) {   // token scales, and (Q4_K) the sixteen 16-value sums of the super-block as fp16
-                    if (pt >= 64) misc.dxs[hs][pt - 64] = pt - 64 < n_valid ? __uint_as_float(Q4 ? f4.x : f4.w) : 0.f;
-                    else if (Q4) {
+                    if (pt >= 64) misc.dxs[hs][pt - 64] = pt - 64 < n_valid ? __uint_as_float(FMT == 0 ? f4.x : f4.w) : 0.f;
+                    else if (FMT == 0) {
                         const int n2 = pt >> 1, kg = pt & 1;
                         uint4 vv = z;
                         if (n2 < n_valid) {
@@ -329,7 +278,7 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                                             h2(KTB_S16(bw[3], 0), KTB_S16(bw[3], 1)));
 #undef KTB_S16
                         }
-                        *reinterpret_cast<uint4*>(smem + L::OffB2 + stage * kGB2 + (n2 >> 3) * 256 + kg * 128 + (n2 & 7) * 16) = vv;
+                        *reinterpret_cast<uint4*>(smem + kOffB2 + stage * kGB2 + (n2 >> 3) * 256 + kg * 128 + (n2 & 7) * 16) = vv;
                     }
                 }
                 fence_async_smem();
@@ -343,44 +292,27 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
         cp_async_wait<0>();
     } else if (warp == kGProdWarps) {
         // ========================================================================== tensor-core issuer (converged warp)
-        constexpr uint32_t idesc_i8 = Q4 ? instr_desc(2, 0, 1, 0, 0, kGM, kGN) : instr_desc(2, 1, 1, 0, 0, kGM, 2 * kGN);   // s32 += (u8 | s8) . s8
+        constexpr uint32_t idesc_i8 = FMT == 0 ? instr_desc(2, 0, 1, 0, 0, kGM, kGN) : instr_desc(2, 1, 1, 0, 0, kGM, 2 * kGN);   // s32 += (u8 | s8) . s8
         constexpr uint32_t idesc_f16 = instr_desc(1, 0, 0, 0, 0, kGM, kGN);
         unsigned it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int st = 0; st < nst; st++, it++) {
-                // FMT 0 / 1: one TMEM buffer (256 columns) per stage; FMT 2: one buffer (128 columns) per SUPER-block
-                const int buf = FMT == 2 ? (it >> 1) & 1 : it & 1;
-                const unsigned use = FMT == 2 ? it >> 2 : it >> 1;      // how often this buffer has been used before
+                const int buf = it & 1;
                 const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && tile == 0 && st < 96;
                 if (tr) p.trace[(1 * 96 + st) * 4 + 0] = clock64();
                 bar_wait(smem_u32(&misc.ab_full[stage]), sphase);
                 if (tr) p.trace[(1 * 96 + st) * 4 + 1] = clock64();
-                if (FMT != 2 || (st & 1) == 0) bar_wait(smem_u32(&misc.tmem_free[buf]), (use & 1) ^ 1);
+                bar_wait(smem_u32(&misc.tmem_free[buf]), ((it >> 1) & 1) ^ 1);
                 if (tr) p.trace[(1 * 96 + st) * 4 + 2] = clock64();
                 tc_fence_after();
-                const uint32_t a = base + stage * L::A, b = base + L::OffB + stage * L::B;
-                if (FMT == 2) {
-                    const uint32_t d = tmem + buf * 128;
+                const uint32_t a = base + stage * kGA, b = base + kOffB + stage * kGB, d = tmem + buf * 256;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {   // high digits -> columns [0, 32), low digits -> [32, 64), summed over the whole super-block
-                        const uint32_t accum = ((st & 1) | c) != 0;
-                        mma_i8(d, smem_desc(a + c * 32, 16, 1024, kLayoutSw128), smem_desc(b + c * 32, 16, 1024, kLayoutSw128), idesc_i8, accum);
-                        mma_i8(d + 32, smem_desc(a + kGA + c * 32, 16, 1024, kLayoutSw128), smem_desc(b + c * 32, 16, 1024, kLayoutSw128), idesc_i8, accum);
-                    }
-                    if (st & 1)
-                        mma_f16(d + 64, smem_desc(base + L::OffA2 + stage * kGA2, 128, 256, kLayoutNone), smem_desc(base + L::OffB2 + stage * kGB2, 128, 256, kLayoutNone), idesc_f16, 0);
-                    mma_commit(smem_u32(&misc.smem_free[stage]));
-                    if (st & 1) mma_commit(smem_u32(&misc.tmem_full[buf]));
-                } else {
-                    const uint32_t d = tmem + buf * 256;
-#pragma unroll
-                    for (int c = 0; c < 4; c++)
-                        mma_i8(d + c * (Q4 ? 32 : 64), smem_desc(a + c * 32, 16, 1024, kLayoutSw128), smem_desc(b + c * 32, 16, 1024, kLayoutSw128), idesc_i8, 0);
-                    if (Q4 && (st & 1))
-                        mma_f16(d + 128, smem_desc(base + L::OffA2 + stage * kGA2, 128, 256, kLayoutNone), smem_desc(base + L::OffB2 + stage * kGB2, 128, 256, kLayoutNone), idesc_f16, 0);
-                    mma_commit(smem_u32(&misc.smem_free[stage]));
-                    mma_commit(smem_u32(&misc.tmem_full[buf]));
-                }
+                for (int c = 0; c < 4; c++)
+                    mma_i8(d + c * (FMT == 0 ? 32 : 64), smem_desc(a + c * 32, 16, 1024, kLayoutSw128), smem_desc(b + c * 32, 16, 1024, kLayoutSw128), idesc_i8, 0);
+                if (FMT == 0 && (st & 1))
+                    mma_f16(d + 128, smem_desc(base + kOffA2 + stage * kGA2, 128, 256, kLayoutNone), smem_desc(base + kOffB2 + stage * kGB2, 128, 256, kLayoutNone), idesc_f16, 0);
+                mma_commit(smem_u32(&misc.smem_free[stage]));
+                mma_commit(smem_u32(&misc.tmem_full[buf]));
                 if (tr) p.trace[(1 * 96 + st) * 4 + 3] = clock64();
                 if (++stage == kGStages) { stage = 0; sphase ^= 1; }
             }
@@ -400,45 +332,13 @@ __global__ void __launch_bounds__(kGThreads, 1) grouped_gemm_kernel(const GrpGem
                 const int buf = it & 1, hh = st & 1;
                 const bool tr = p.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tile == 0 && st < 96;
                 if (tr) p.trace[(2 * 96 + st) * 4 + 0] = clock64();
-                if (FMT == 2) {
-                    // accumulators per SUPER-block: nothing to read after the first half (its header slot is released unread)
-                    const int b2 = (it >> 1) & 1;
-                    if (hh == 1) {
-                        bar_wait(smem_u32(&misc.tmem_full[b2]), (it >> 2) & 1);
-                        if (tr) p.trace[(2 * 96 + st) * 4 + 1] = clock64();
-                        tc_fence_after();
-                        const uint4 hd2 = misc.hdr[hs][row];
-                        const uint32_t d = tbase + b2 * 128;
-                        uint32_t vh[16], vl[16], ms[16];
-                        tmem_ld16(d, vh);
-                        tmem_ld16(d + 32, vl);
-                        tmem_ld16(d + 64, ms);
-                        const __half2 dm = *reinterpret_cast<const __half2*>(&hd2.x);
-                        const float dw = __low2float(dm), dmin = __high2float(dm);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int n = 0; n < 16; n++) {
-                            const float dx = misc.dxs[hs][16 * ch + n];
-                            acc[n] += (dw * dx) * (float)(8 * (int)vh[n] + (int)vl[n]) - (dmin * dx) * __uint_as_float(ms[n]);
-                        }
-                        tc_fence_before();
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (hh == 1) bar_arrive(smem_u32(&misc.tmem_free[b2]));
-                        bar_arrive(smem_u32(&misc.hdr_free[hs]));
-                    }
-                    if (tr) p.trace[(2 * 96 + st) * 4 + 3] = clock64();
-                    if (++hs == kGHdr) { hs = 0; hphase ^= 1; }
-                    continue;
-                }
                 bar_wait(smem_u32(&misc.tmem_full[buf]), (it >> 1) & 1);
                 if (tr) p.trace[(2 * 96 + st) * 4 + 1] = clock64();
                 tc_fence_after();
                 const uint4 hd = misc.hdr[hs][row];
                 const uint32_t hw[4] = {hd.x, hd.y, hd.z, hd.w};
                 const uint32_t d = tbase + buf * 256;
-                if (Q4) {
+                if (FMT == 0) {
                     int sc[4], mn;
                     if (hh == 0) {
 #pragma unroll
@@ -637,9 +537,8 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
     GrpScratch& g = g_grp[dev & 63];
     static bool attr[64] = {};
     if (!attr[dev & 63]) {
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, grp_smem<0>()));
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, grp_smem<1>()));
-        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, grp_smem<2>()));
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem));
+        KTB_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem));
         attr[dev & 63] = true;
     }
     const FmtId fd = pick_fmt(c.down_type, m->down_layout);
@@ -663,21 +562,16 @@ int moe_forward_grouped(ktb200_moe* m, int qlen, int k, const int64_t* ids, cons
         gp.R = I; gp.Kc = H; gp.xq = g.xq; gp.xd = g.xd; gp.xbs = g.xbs; gp.rowmap = g.tokmap; gp.tinfo = g.tinfo_gu; gp.nt_prefix = g.nt_prefix; gp.E = E;
         gp.expert_bytes = (long)I * (H / 256) * SZ_Q4_K;
         gp.w = reinterpret_cast<const uint8_t*>(c.gate_proj); gp.out = g.g; gp.trace = g_grp_trace;
-        // Q4_K: scale digits (FMT 2, accumulators per super-block) or one accumulator per sub-block (FMT 0, KTB200_GROUPED_DIGITS=0)
-        static const bool digits = [] { const char* e = getenv("KTB200_GROUPED_DIGITS"); return e ? atoi(e) != 0 : false; }();
-        if (digits) grouped_gemm_kernel<2><<<grid, kGThreads, grp_smem<2>(), s>>>(gp);
-        else grouped_gemm_kernel<0><<<grid, kGThreads, grp_smem<0>(), s>>>(gp);
+        grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
         gp.w = reinterpret_cast<const uint8_t*>(c.up_proj); gp.out = g.u; gp.trace = nullptr;
-        if (digits) grouped_gemm_kernel<2><<<grid, kGThreads, grp_smem<2>(), s>>>(gp);
-        else grouped_gemm_kernel<0><<<grid, kGThreads, grp_smem<0>(), s>>>(gp);
+        grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gp);
         grp_act_quant_kernel<<<(P * (I / 256) + 7) / 8, 256, 0, s>>>(g.g, g.u, g.offsets, E, I, c.use_silu, g.aq, g.ad, g.abs16);
         GrpGemmParams gd{};
         gd.R = H; gd.Kc = I; gd.xq = g.aq; gd.xd = g.ad; gd.xbs = g.abs16; gd.rowmap = nullptr; gd.tinfo = g.tinfo_d; gd.nt_prefix = g.nt_prefix;
         gd.E = E; gd.expert_bytes = (long)H * (I / 256) * (fd == FMT_Q6K4T ? SZ_Q6_K : SZ_Q4_K);
         gd.w = reinterpret_cast<const uint8_t*>(c.down_proj); gd.out = g.dd; gd.trace = g_grp_trace ? g_grp_trace + 3 * 96 * 4 : nullptr;
-        if (fd == FMT_Q6K4T) grouped_gemm_kernel<1><<<grid, kGThreads, grp_smem<1>(), s>>>(gd);
-        else if (digits) grouped_gemm_kernel<2><<<grid, kGThreads, grp_smem<2>(), s>>>(gd);
-        else grouped_gemm_kernel<0><<<grid, kGThreads, grp_smem<0>(), s>>>(gd);
+        if (fd == FMT_Q6K4T) grouped_gemm_kernel<1><<<grid, kGThreads, kGSmem, s>>>(gd);
+        else grouped_gemm_kernel<0><<<grid, kGThreads, kGSmem, s>>>(gd);
         grp_combine_kernel<<<dim3((H + 255) / 256, T), 256, 0, s>>>(g.dd, g.pos, w_c, T, k, H, bsz, t0, o_c, c.hidden_type);
         KTB_LAUNCH_CHECK();
         count_launch(9);   // + the one KTB_LAUNCH_CHECK counts = 10 launches per chunk
